@@ -1,0 +1,98 @@
+// common.hpp -- error handling, RAII device buffers, timers shared by the host side of libgeneob200.
+#pragma once
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace geneo {
+
+struct Error : public std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define GENEO_CHECK(cond, msg)                                                                   \
+  do {                                                                                           \
+    if (!(cond)) throw ::geneo::Error(std::string("geneo_b200: ") + (msg) + " [" #cond "] at " + \
+                                      __FILE__ + ":" + std::to_string(__LINE__));                \
+  } while (0)
+
+#define CUDA_CHECK(call)                                                                              \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      throw ::geneo::Error(std::string("geneo_b200: CUDA error ") + cudaGetErrorString(e__) + " in " + \
+                           #call + " at " + __FILE__ + ":" + std::to_string(__LINE__));               \
+  } while (0)
+
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// The product has NO CPU fallback: every numeric entry point calls this first.
+inline void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    throw Error("geneo_b200: no CUDA device available -- this library has no CPU fallback (" +
+                std::string(cudaGetErrorString(e)) + ")");
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void alloc(size_t n_) {
+    release();
+    n = n_;
+    if (n) CUDA_CHECK(cudaMalloc((void**)&p, n * sizeof(T)));
+  }
+  void zero(cudaStream_t s = 0) { if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const T* h, size_t cnt, cudaStream_t s = 0) {
+    if (cnt > n) alloc(cnt);
+    if (cnt) CUDA_CHECK(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s = 0) {
+    if (h.size() != n) alloc(h.size());
+    upload(h.data(), h.size(), s);
+  }
+  void download(T* h, size_t cnt, cudaStream_t s = 0) const {
+    if (cnt) CUDA_CHECK(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  std::vector<T> to_host(cudaStream_t s = 0) const {
+    std::vector<T> h(n);
+    download(h.data(), n, s);
+    return h;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// Host CSR (square unless stated), 32-bit column indices, 64-bit row pointers where nnz may exceed 2^31.
+struct CsrHost {
+  int n = 0, ncols = 0;
+  std::vector<int64_t> ptr;
+  std::vector<int> idx;
+  std::vector<double> val;
+  int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
+};
+
+}  // namespace geneo

@@ -1,0 +1,167 @@
+// eigen.cu -- see eigen.hpp.
+#include "eigen.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+#include "dense_host.hpp"
+
+namespace geneo {
+namespace {
+
+__global__ void k_fill_random(int64_t n, int ld, int ncols, uint64_t seed, double* __restrict__ x) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * ld; t += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % ld);
+    uint64_t z = (uint64_t)t * 0x9E3779B97F4A7C15ull + seed;  // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    x[t] = j < ncols ? ((double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5) : 0.;
+  }
+}
+// dst[r*ldd + j] = src[r*lds + j], j < ncols ; zero-fills dst columns ncols..ldfill-1
+__global__ void k_copy_block(int64_t n, const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd,
+                             int ncols, int ldfill) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * ldfill; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / ldfill;
+    const int j = (int)(t % ldfill);
+    dst[r * ldd + j] = j < ncols ? src[r * lds + j] : 0.;
+  }
+}
+inline int gridn(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8)); }
+
+}  // namespace
+
+void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* idx, const double* valB, int nev,
+                   const EigOptions& opt, EigResult& res, cudaStream_t st) {
+  res = EigResult();
+  GENEO_CHECK(nev >= 1 && nev <= n, "block_lanczos: bad nev");
+  int b, maxDim;
+  if (n <= 64) { b = n; maxDim = n; }
+  else {
+    b = std::max(1, opt.block);
+    maxDim = opt.maxDim > 0 ? opt.maxDim : std::max(3 * nev + 4 * b, 64);
+    maxDim = std::min(maxDim, n);
+    maxDim = std::max(b, maxDim / b * b);
+  }
+  const int bp = (b + 7) / 8 * 8;
+  DevBuf<double> Q((size_t)n * maxDim), BQ((size_t)n * maxDim), W((size_t)n * bp), W2((size_t)n * bp), BW((size_t)n * bp),
+      BW2((size_t)n * bp), Xs((size_t)n * bp), dC((size_t)maxDim * std::max(bp, nev));
+  double* w = W.p; double* w2 = W2.p; double* bw = BW.p; double* bw2 = BW2.p;
+
+  auto spmmB = [&](const double* X, double* Y) {  // Y = B X for ld = bp blocks
+    for (int j0 = 0; j0 < bp; j0 += 8) csr_spmm(n, ptr, idx, valB, X + j0, bp, Y + j0, bp, 8, st);
+  };
+  std::vector<double> hG((size_t)bp * bp), hR((size_t)b * b), hRinv((size_t)b * b);
+  // B-orthonormalise the block in w (n x b, ld bp); on success w, bw hold W R^-1 and B W R^-1, hR holds R.
+  auto orth_block = [&]() -> int {
+    spmmB(w, bw);
+    CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * b * b, st));
+    ts_gram(n, w, bp, b, bw, bp, b, dC.p, b, st);
+    CUDA_CHECK(cudaMemcpyAsync(hR.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < b; i++)
+      for (int j = i + 1; j < b; j++) hR[i * b + j] = hR[j * b + i] = 0.5 * (hR[i * b + j] + hR[j * b + i]);
+    const int bad = chol_upper(b, hR.data(), 1e-13);
+    if (bad >= 0) return bad + 1;
+    triu_inverse(b, hR.data(), hRinv.data());
+    CUDA_CHECK(cudaMemcpyAsync(dC.p, hRinv.data(), sizeof(double) * b * b, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemsetAsync(w2, 0, sizeof(double) * (size_t)n * bp, st));
+    CUDA_CHECK(cudaMemsetAsync(bw2, 0, sizeof(double) * (size_t)n * bp, st));
+    ts_update(n, w, bp, b, dC.p, b, b, w2, bp, 1., 0., st);
+    ts_update(n, bw, bp, b, dC.p, b, b, bw2, bp, 1., 0., st);
+    std::swap(w, w2);
+    std::swap(bw, bw2);
+    return 0;
+  };
+
+  k_fill_random<<<gridn((int64_t)n * bp), 256, 0, st>>>(n, bp, b, 0x1234567ull, w);
+  std::vector<double> R0;
+  for (int pass = 0; pass < 2; pass++) {  // CholQR2
+    const int rc = orth_block();
+    GENEO_CHECK(rc == 0, "block_lanczos: the B matrix of the pencil is not positive definite");
+  }
+  k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, w, bp, Q.p, maxDim, b, b);
+  k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, bw, bp, BQ.p, maxDim, b, b);
+
+  std::vector<double> Hm((size_t)maxDim * maxDim, 0.), T, theta, hC1, hC2, Rfirst;
+  std::vector<double> ritzVal, ritzRes;
+  std::vector<double> Ysel;
+  int dim = 0, steps = 0;
+  bool done = false;
+  while (!done) {
+    const int j = steps;
+    dim = (j + 1) * b;
+    // W = F^-1 (B Q_j)
+    k_copy_block<<<gridn((int64_t)n * bp), 256, 0, st>>>(n, BQ.p + (size_t)j * b, maxDim, Xs.p, bp, b, bp);
+    for (int j0 = 0; j0 < bp; j0 += 8) F.solve_permuted(Xs.p, w, bp, j0, 8, st);
+    // two passes of block classical Gram-Schmidt against Q[:, 0:dim] in the B inner product
+    hC1.assign((size_t)dim * b, 0.);
+    for (int pass = 0; pass < 2; pass++) {
+      CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * (size_t)dim * b, st));
+      ts_gram(n, BQ.p, maxDim, dim, w, bp, b, dC.p, b, st);
+      ts_update(n, Q.p, maxDim, dim, dC.p, b, b, w, bp, -1., 1., st);
+      hC2.resize((size_t)dim * b);
+      CUDA_CHECK(cudaMemcpyAsync(hC2.data(), dC.p, sizeof(double) * (size_t)dim * b, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      for (size_t t = 0; t < hC1.size(); t++) hC1[t] += hC2[t];
+    }
+    for (int i = 0; i < dim; i++)
+      for (int c = 0; c < b; c++) Hm[(size_t)i * maxDim + j * b + c] = hC1[(size_t)i * b + c];
+    const bool room = (dim + b <= maxDim);
+    int rc = orth_block();  // next block (also gives the residual coupling R)
+    const bool breakdown = rc != 0;
+    if (breakdown) std::fill(hR.begin(), hR.end(), 0.);
+    if (room)  // T Q_j = Q_{0..j} C_j + Q_{j+1} R : the sub-diagonal block of the projected matrix
+      for (int r = 0; r < b; r++)
+        for (int c = 0; c < b; c++) Hm[(size_t)(dim + r) * maxDim + j * b + c] = hR[(size_t)r * b + c];
+    // Rayleigh-Ritz on the symmetrised leading dim x dim block
+    T.assign((size_t)dim * dim, 0.);
+    for (int i = 0; i < dim; i++)
+      for (int c = 0; c < dim; c++) T[(size_t)i * dim + c] = 0.5 * (Hm[(size_t)i * maxDim + c] + Hm[(size_t)c * maxDim + i]);
+    theta.assign(dim, 0.);
+    sym_eig(dim, T.data(), theta.data());
+    const int want = std::min(nev, dim);
+    ritzVal.assign(want, 0.);
+    ritzRes.assign(want, 0.);
+    int nconv = 0;
+    for (int q = 0; q < want; q++) {
+      const int col = dim - 1 - q;  // largest theta first
+      double s2 = 0.;
+      for (int r = 0; r < b; r++) {
+        double s = 0.;
+        for (int c = 0; c < b; c++) s += hR[(size_t)r * b + c] * T[(size_t)(dim - b + c) * dim + col];
+        s2 += s * s;
+      }
+      ritzVal[q] = theta[col];
+      ritzRes[q] = std::sqrt(s2) / std::max(std::fabs(theta[col]), 1e-300);
+      if (ritzRes[q] <= opt.tol) nconv++;
+    }
+    steps++;
+    res.nconv = nconv;
+    if ((nconv == want && want == nev) || breakdown || !room || dim + b > n) done = true;
+    if (!done) {
+      k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, w, bp, Q.p + (size_t)(j + 1) * b, maxDim, b, b);
+      k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)(j + 1) * b, maxDim, b, b);
+    } else {
+      // Ritz vectors X = Q[:, 0:dim] Y
+      const int got = want;
+      Ysel.assign((size_t)dim * got, 0.);
+      for (int q = 0; q < got; q++)
+        for (int i = 0; i < dim; i++) Ysel[(size_t)i * got + q] = T[(size_t)i * dim + (dim - 1 - q)];
+      CUDA_CHECK(cudaMemcpyAsync(dC.p, Ysel.data(), sizeof(double) * Ysel.size(), cudaMemcpyHostToDevice, st));
+      res.vecs.alloc((size_t)n * got);
+      res.vecs.zero(st);
+      ts_update(n, Q.p, maxDim, dim, dC.p, got, got, res.vecs.p, got, 1., 0., st);
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      res.lambda.resize(got);
+      res.resid = ritzRes;
+      for (int q = 0; q < got; q++) res.lambda[q] = opt.invert ? 1. / ritzVal[q] : ritzVal[q];
+      if (breakdown || dim >= n) res.nconv = got;  // exact invariant subspace
+    }
+  }
+  res.steps = steps;
+  res.dim = dim;
+}
+
+}  // namespace geneo

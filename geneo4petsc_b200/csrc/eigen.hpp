@@ -1,0 +1,36 @@
+// eigen.hpp -- block shift-invert Lanczos for the GenEO pencils, replacing SLEPc EPS(arpack)+STSINVERT
+// (reference: src/geneo.cpp:626-744 eigenLocalSolve, :746-780 buildEigenSolver, :842-893 eigenLocalProblem).
+//
+// Problem:  F x = lambda B x  with F factored (block LDL^T) and B an SPD CSR matrix on the same (permuted) pattern.
+// Operator T = F^-1 B is self-adjoint in the B inner product; its largest eigenvalues theta = 1/lambda are the
+// smallest lambda (tau problem: F = A_neu, B = D A_dir D or A_rob).  For the gamma problem of GenEO-2
+// ((D A_dir D) x = lambda A_rob x, largest lambda) call it with F = A_rob, B = D A_dir D and invert = false.
+// A whole block of right-hand sides goes through the factor per step, so the factor is streamed once per block
+// (ARPACK streams it once per vector).
+#pragma once
+#include <vector>
+#include "kernels.hpp"
+#include "ldlt.hpp"
+
+namespace geneo {
+
+struct EigOptions {
+  int block = 8;
+  double tol = 1e-4;      // ||T x - theta x||_B <= tol * |theta|
+  int maxDim = 0;         // 0: automatic
+  bool invert = true;     // report lambda = 1/theta
+};
+
+struct EigResult {
+  int nconv = 0;               // converged wanted pairs (== nev on success)
+  int steps = 0, dim = 0;
+  std::vector<double> lambda;  // nev values (ascending lambda if invert, else descending)
+  std::vector<double> resid;   // relative residual estimates
+  DevBuf<double> vecs;         // n x nev row-major (ld = nev), permuted (solver) ordering, B-orthonormal
+};
+
+// ptr/idx/valB: device CSR of B in the solver ordering.
+void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* idx, const double* valB, int nev,
+                   const EigOptions& opt, EigResult& res, cudaStream_t st);
+
+}  // namespace geneo

@@ -1,0 +1,836 @@
+// geneo.cu -- see geneo.hpp.
+#include "geneo.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+#include <thread>
+
+#include "dense_host.hpp"
+
+namespace geneo {
+
+// =====================================================================================================================
+// Options
+// =====================================================================================================================
+int GeneoOptions::parse(int argc, const char* const* argv, std::string& err) {
+  auto need = [&](int a, const char* o) -> const char* {
+    if (a + 1 >= argc || !argv[a + 1]) { err = std::string("invalid option ") + o; return nullptr; }
+    return argv[a + 1];
+  };
+  auto num = [&](const char* s, double& v, const char* o) -> bool {
+    std::stringstream ss(s);
+    ss >> v;
+    if (!ss) { err = std::string("invalid option ") + o + ", bad " + s; return false; }
+    return true;
+  };
+  for (int a = 0; a < argc; a++) {
+    if (!argv[a]) continue;
+    const std::string o = argv[a];
+    if (o == "-geneo_lvl") {
+      const char* v = need(a, "-geneo_lvl"); if (!v) return 1;
+      std::string s(v);
+      const size_t c = s.find(',');
+      if (c == std::string::npos) { err = "invalid option -geneo_lvl"; return 1; }
+      const std::string l1 = s.substr(0, c), l2 = s.substr(c + 1);
+      if (l1 == "ASM") lvl1ASM = true;
+      else if (l1 == "RAS") lvl1RAS = true;
+      else if (l1 == "SRAS") lvl1RAS = lvl1SRAS = true;
+      else if (l1 == "ORAS") lvl1RAS = lvl1ORAS = true;
+      else if (l1 == "SORAS") lvl1RAS = lvl1SRAS = lvl1ORAS = true;
+      else { err = "invalid option -geneo_lvl, unknown " + l1; return 1; }
+      if (l2 == "0") lvl2 = 0;
+      else if (l2 == "1") lvl2 = 1;
+      else if (l2 == "H1") { lvl2 = 1; hybrid = true; }
+      else if (l2 == "E1") { lvl2 = 1; hybrid = true; effHybrid = true; }
+      else if (l2 == "2") lvl2 = 2;
+      else if (l2 == "H2") { lvl2 = 2; hybrid = true; }
+      else if (l2 == "E2") { lvl2 = 2; hybrid = true; effHybrid = true; }
+      else { err = "invalid option -geneo_lvl, unknown " + l2; return 1; }
+      a++;
+    } else if (o == "-geneo_optim") { const char* v = need(a, "-geneo_optim"); if (!v || !num(v, optim, "-geneo_optim")) return 1; a++; }
+    else if (o == "-geneo_tau") { const char* v = need(a, "-geneo_tau"); if (!v || !num(v, tau, "-geneo_tau")) return 1; a++; }
+    else if (o == "-geneo_gamma") { const char* v = need(a, "-geneo_gamma"); if (!v || !num(v, gamma, "-geneo_gamma")) return 1; a++; }
+    else if (o == "-geneo_cut") { double c; const char* v = need(a, "-geneo_cut"); if (!v || !num(v, c, "-geneo_cut")) return 1; cut = (int)c; a++; }
+    else if (o == "-geneo_cst") cst = true;
+    else if (o == "-geneo_no_syl") noSyl = true;
+    else if (o == "-geneo_offload") offload = true;
+    else if (o == "-geneo_dbg") {
+      const char* v = need(a, "-geneo_dbg"); if (!v) return 1;
+      std::string s(v);
+      const size_t c = s.find(',');
+      if (c == std::string::npos) { err = "invalid option -geneo_dbg"; return 1; }
+      const std::string f = s.substr(0, c);
+      if (f != "log" && f != "bin" && f != "mat") { err = "invalid option -geneo_dbg, unknown " + f; return 1; }
+      double d; if (!num(s.substr(c + 1).c_str(), d, "-geneo_dbg")) return 1;
+      debug = (int)d; a++;
+    } else if (o == "-geneo_chk") {
+      const char* v = need(a, "-geneo_chk"); if (!v) return 1;
+      std::string f(v);
+      if (f != "log" && f != "bin" && f != "mat") { err = "invalid option -geneo_chk, unknown " + f; return 1; }
+      check = true; a++;
+    } else if (o == "-els2_eps_tol") { const char* v = need(a, "-els2_eps_tol"); if (!v || !num(v, epsTol, "-els2_eps_tol")) return 1; a++; }
+    else if (o == "-els2_eps_ncv") { double c; const char* v = need(a, "-els2_eps_ncv"); if (!v || !num(v, c, "-els2_eps_ncv")) return 1; epsMaxDim = (int)c; a++; }
+    else if (o == "-geneo_nb") { double c; const char* v = need(a, "-geneo_nb"); if (!v || !num(v, c, "-geneo_nb")) return 1; nb = (int)c; a++; }
+    else if (o == "-geneo_ordering") { double c; const char* v = need(a, "-geneo_ordering"); if (!v || !num(v, c, "-geneo_ordering")) return 1; ordering = (int)c; a++; }
+    else if (o == "-geneo_timing") timing = true;
+  }
+  // consistency (src/geneo.cpp:2486-2488)
+  if (lvl2 >= 1 && tau <= 0.) { err = "GenEO preconditioner: tau must be > 0."; return 1; }
+  if (lvl2 >= 1 && tau >= 1.) { err = "GenEO preconditioner: tau must be < 1."; return 1; }
+  if (lvl2 >= 2 && gamma <= 1.) { err = "GenEO preconditioner: gamma must be > 1."; return 1; }
+  if (nb < 8 || nb > 128) { err = "-geneo_nb must be in [8,128]"; return 1; }
+  return 0;
+}
+
+std::string GeneoOptions::name() const {
+  std::string nm = "geneo";
+  nm += (lvl2 == 0) ? "0" : (lvl2 == 1 ? "1" : "2");
+  if (hybrid) nm += effHybrid ? "E" : "H";
+  std::string l1;
+  if (lvl1ASM) l1 = "ASM";
+  if (lvl1RAS) l1 = "RAS";
+  if (lvl1SRAS) l1 = "SRAS";
+  if (lvl1ORAS) l1 = "ORAS";
+  if (lvl1SRAS && lvl1ORAS) l1 = "SORAS";
+  return nm + l1;
+}
+
+const char* ksp_reason_name(int r) {
+  switch (r) {
+    case KSP_CONVERGED_RTOL: return "KSP_CONVERGED_RTOL";
+    case KSP_CONVERGED_ATOL: return "KSP_CONVERGED_ATOL";
+    case KSP_CONVERGED_HAPPY_BREAKDOWN: return "KSP_CONVERGED_HAPPY_BREAKDOWN";
+    case KSP_DIVERGED_ITS: return "KSP_DIVERGED_ITS";
+    case KSP_DIVERGED_DTOL: return "KSP_DIVERGED_DTOL";
+    case KSP_DIVERGED_BREAKDOWN: return "KSP_DIVERGED_BREAKDOWN";
+    case KSP_DIVERGED_INDEFINITE_PC: return "KSP_DIVERGED_INDEFINITE_PC";
+    case KSP_DIVERGED_NANORINF: return "KSP_DIVERGED_NANORINF";
+    case KSP_DIVERGED_INDEFINITE_MAT: return "KSP_DIVERGED_INDEFINITE_MAT";
+    default: return "KSP_CONVERGED_ITERATING";
+  }
+}
+
+// =====================================================================================================================
+// Setup
+// =====================================================================================================================
+namespace {
+
+struct HostPrep {  // everything the host prepares for one subdomain (worker thread)
+  Symbolic sym;
+  CsrHost patP;                 // permuted pattern of A_dir with its values
+  std::vector<double> vNeuP, vRobP, dP;
+  std::vector<int> gidx;
+  double anorm = 0.;
+  int maxMult = 1;
+  std::string err;
+};
+
+void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, HostPrep& H) {
+  const int n = (int)S.nodes.size();
+  SymbolicOptions so;
+  so.nb = opt.nb;
+  so.ordering = opt.ordering;
+  symbolic_analyze(n, S.aDir.ptr.data(), S.aDir.idx.data(), so, H.sym);
+  const std::vector<int>& perm = H.sym.perm;
+  const std::vector<int>& iperm = H.sym.iperm;
+  // A_neu expanded to the A_dir pattern (natural order), then everything permuted to the solver order
+  const int64_t nnz = S.aDir.nnz();
+  std::vector<double> neuExp((size_t)nnz, 0.);
+  for (int r = 0; r < n; r++) {
+    int64_t q = S.aDir.ptr[r];
+    for (int64_t t = S.aNeu.ptr[r]; t < S.aNeu.ptr[r + 1]; t++) {
+      while (q < S.aDir.ptr[r + 1] && S.aDir.idx[q] < S.aNeu.idx[t]) q++;
+      GENEO_CHECK(q < S.aDir.ptr[r + 1] && S.aDir.idx[q] == S.aNeu.idx[t], "A_neu entry outside the A_dir pattern");
+      neuExp[q] = S.aNeu.val[t];
+    }
+  }
+  H.patP.n = H.patP.ncols = n;
+  H.patP.ptr.assign(n + 1, 0);
+  H.patP.idx.resize((size_t)nnz);
+  H.patP.val.resize((size_t)nnz);
+  H.vNeuP.resize((size_t)nnz);
+  std::vector<int64_t> origToPerm((size_t)nnz);
+  std::vector<std::pair<int, int64_t>> row;
+  for (int k = 0; k < n; k++) {
+    const int ro = perm[k];
+    row.clear();
+    for (int64_t t = S.aDir.ptr[ro]; t < S.aDir.ptr[ro + 1]; t++) row.emplace_back(iperm[S.aDir.idx[t]], t);
+    std::sort(row.begin(), row.end());
+    int64_t q = H.patP.ptr[k];
+    for (auto& e : row) {
+      H.patP.idx[q] = e.first;
+      H.patP.val[q] = S.aDir.val[e.second];
+      H.vNeuP[q] = neuExp[e.second];
+      origToPerm[e.second] = q;
+      H.anorm = std::max(H.anorm, std::fabs(S.aDir.val[e.second]));
+      q++;
+    }
+    H.patP.ptr[k + 1] = q;
+  }
+  for (auto& s : H.sym.asmSrc) s = origToPerm[s];
+  H.dP.resize(n);
+  H.gidx.resize(n);
+  for (int k = 0; k < n; k++) {
+    H.dP[k] = 1.0 / ((double)S.mult[perm[k]]);  // createPartitionOfUnity, src/geneo.cpp:977-980
+    H.gidx[k] = S.nodes[perm[k]];
+    H.maxMult = std::max(H.maxMult, S.mult[perm[k]]);
+  }
+  if (opt.lvl1ORAS) {  // createRobinMatrix, src/geneo.cpp:1613-1670 (done sparsely: no dense border x border buffer)
+    H.vRobP = H.patP.val;
+    if (std::fabs(opt.optim) > DBL_EPSILON)
+      for (int k = 0; k < n; k++) {
+        if (S.mult[perm[k]] <= 1) continue;
+        for (int64_t q = H.patP.ptr[k]; q < H.patP.ptr[k + 1]; q++)
+          if (S.mult[perm[H.patP.idx[q]]] > 1) H.vRobP[q] += opt.optim * H.vNeuP[q];
+      }
+  }
+}
+
+}  // namespace
+
+GeneoPC::GeneoPC() {}
+GeneoPC::~GeneoPC() {
+  for (auto s : streams) cudaStreamDestroy(s);
+  for (auto e : events) cudaEventDestroy(e);
+  if (evFork) cudaEventDestroy(evFork);
+}
+
+double GeneoPC::dot(const double* x, const double* y) {
+  vec_dot(nOwn, x, y, scal.p, st);
+  double h = 0.;
+  CUDA_CHECK(cudaMemcpyAsync(&h, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  return h;
+}
+
+void GeneoPC::setup(const Decomposition& dec) {
+  require_device();
+  const double tSetup0 = now_s();
+  nbDof = dec.nbNode;
+  nLoc = nOwn = nbDof;
+  nbPart = dec.nbPart;
+  scal.alloc(1024);
+  std::vector<const Subdomain*> mine;
+  for (auto& S : dec.subs)
+    if (S.aNeu.n > 0) mine.push_back(&S);
+  GENEO_CHECK((int)mine.size() == dec.nbPart, "single-process setup needs every subdomain's matrices");
+  if (opt.lvl2 == 2 && !opt.lvl1ORAS)
+    throw Error("geneo_b200: GenEO-2 needs an optimised level 1 (ORAS/SORAS) -- untested/unsupported in the reference too");
+
+  // ---- operator A = sum_i R_i^T A_neu,i R_i  (MatConvert MATIS->AIJ, src/geneo.cpp:1692), SELL-32 on the device ------
+  double t0 = now_s();
+  {
+    CsrHost g;
+    g.n = g.ncols = nLoc;
+    std::vector<int64_t> cnt(nLoc + 1, 0);
+    for (auto* S : mine)
+      for (int l = 0; l < S->aNeu.n; l++) cnt[S->nodes[l] + 1] += S->aNeu.ptr[l + 1] - S->aNeu.ptr[l];
+    for (int i = 0; i < nLoc; i++) cnt[i + 1] += cnt[i];
+    std::vector<int> ci((size_t)cnt[nLoc]);
+    std::vector<double> cv((size_t)cnt[nLoc]);
+    {
+      std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+      for (auto* S : mine)
+        for (int l = 0; l < S->aNeu.n; l++) {
+          int64_t& p = pos[S->nodes[l]];
+          for (int64_t t = S->aNeu.ptr[l]; t < S->aNeu.ptr[l + 1]; t++) { ci[p] = S->nodes[S->aNeu.idx[t]]; cv[p] = S->aNeu.val[t]; p++; }
+        }
+    }
+    g.ptr.assign(nLoc + 1, 0);
+    g.idx.reserve(ci.size()); g.val.reserve(ci.size());
+    std::vector<std::pair<int, double>> row;
+    for (int i = 0; i < nLoc; i++) {
+      row.clear();
+      for (int64_t t = cnt[i]; t < cnt[i + 1]; t++) row.emplace_back(ci[t], cv[t]);
+      std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+      for (size_t k = 0; k < row.size();) {
+        const int c = row[k].first;
+        double s = 0.;
+        while (k < row.size() && row[k].first == c) { s += row[k].second; k++; }
+        g.idx.push_back(c); g.val.push_back(s);
+      }
+      g.ptr[i + 1] = (int64_t)g.idx.size();
+    }
+    A.build(g, st);
+  }
+  operatorTime = now_s() - t0;
+
+  // ---- host symbolic analysis of every subdomain, in parallel worker threads ---------------------------------------------
+  t0 = now_s();
+  const int P = (int)mine.size();
+  std::vector<HostPrep> prep(P);
+  {
+    unsigned nt = std::max(1u, std::min((unsigned)P, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (unsigned tid = 0; tid < nt; tid++)
+      pool.emplace_back([&, tid]() {
+        for (int p = tid; p < P; p += nt) {
+          try { prepare_subdomain(*mine[p], opt, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
+        }
+      });
+    for (auto& t : pool) t.join();
+    for (auto& h : prep)
+      if (!h.err.empty()) throw Error(h.err);
+  }
+  symbolicTime = now_s() - t0;
+
+  // ---- concatenated subdomain layout, pull-prolong structure ---------------------------------------------------------------
+  subs.resize(P);
+  nAll = 0;
+  for (int p = 0; p < P; p++) { subs[p].id = mine[p]->id; subs[p].n = (int)mine[p]->nodes.size(); subs[p].off = nAll; nAll += subs[p].n; }
+  {
+    std::vector<int> gAll((size_t)nAll);
+    std::vector<double> dA((size_t)nAll);
+    std::vector<int64_t> pp(nLoc + 1, 0);
+    for (int p = 0; p < P; p++)
+      for (int k = 0; k < subs[p].n; k++) { gAll[subs[p].off + k] = prep[p].gidx[k]; dA[subs[p].off + k] = prep[p].dP[k]; pp[prep[p].gidx[k] + 1]++; }
+    for (int i = 0; i < nLoc; i++) pp[i + 1] += pp[i];
+    std::vector<int64_t> ps((size_t)nAll);
+    std::vector<int64_t> cur(pp.begin(), pp.end() - 1);
+    for (int p = 0; p < P; p++)  // ascending subdomain id inside every row: deterministic summation order
+      for (int k = 0; k < subs[p].n; k++) ps[cur[prep[p].gidx[k]]++] = subs[p].off + k;
+    gidxAll.upload(gAll, st);
+    dAll.upload(dA, st);
+    pullPtr.upload(pp, st);
+    pullPos.upload(ps, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  Xall.alloc((size_t)nAll); Yall.alloc((size_t)nAll);
+  t1.alloc(nLoc); t2.alloc(nLoc); t3.alloc(nLoc);
+  const int nstreams = std::min(P, 8);
+  streams.resize(nstreams);
+  events.resize(nstreams);
+  for (int i = 0; i < nstreams; i++) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&events[i], cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+
+  // ---- numeric setup, subdomain by subdomain (each one fills the GPU) -----------------------------------------------------
+  LdltWorkspace ws;
+  for (int p = 0; p < P; p++) {
+    SubdomainState& s = subs[p];
+    HostPrep& H = prep[p];
+    s.maxMult = H.maxMult;
+    s.anorm = H.anorm;
+    s.plan = std::make_shared<LdltPlan>(std::move(H.sym));
+    s.pat.upload_pattern(H.patP, st);
+    s.vNeu.upload(H.vNeuP, st);
+    if (opt.lvl1ORAS) s.vRob.upload(H.vRobP, st);
+    s.gidx.upload(H.gidx, st);
+    s.d.upload(H.dP, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    const double anorm = H.anorm;
+    H = HostPrep();  // free host memory early
+    // pivot threshold
+    const double pivTol = opt.pivRel * std::max(anorm, 1e-300);
+    // level 2 first (its factorizations are transient), then the persistent level-1 factor
+    if (opt.lvl2 >= 1) {
+      std::vector<double> vals;
+      std::vector<DevBuf<double>> vecs;
+      std::vector<int> counts;
+      int cut = opt.cut;
+      if (opt.lvl2 == 2 && cut >= 2) cut = cut / 2;  // src/geneo.cpp:1275
+      const int savedCut = opt.cut;
+      opt.cut = cut;
+      DevBuf<double> vB((size_t)s.pat.nnz);
+      csr_scale_sym(s.n, s.pat.ptr.p, s.pat.idx.p, s.pat.val.p, s.d.p, vB.p, st);  // D A_dir D, src/geneo.cpp:1243-1246
+      if (opt.lvl2 == 1) {
+        eigen_local_problem(s, s.vNeu.p, vB.p, opt.tau, true, ws, vals, vecs, counts);
+      } else {
+        double tl = opt.tau;  // getLocalGenEOTau, src/geneo.cpp:1097-1118
+        if (!opt.cst) { tl = s.maxMult * opt.tau; if (tl >= 1.) tl = 0.9; s.tauLoc = tl; }
+        eigen_local_problem(s, s.vNeu.p, s.vRob.p, tl, true, ws, vals, vecs, counts);
+        double gl = opt.gamma;  // getLocalGenEOGamma, src/geneo.cpp:1120-1232 (connectivity quirk reproduced)
+        if (!opt.cst) {
+          const int NP = dec.nbPart;
+          std::vector<double> C((size_t)NP * NP, 0.), F(NP, 0.), wv(NP);
+          for (int r = 0; r < NP; r++)
+            for (int q = 0; q < NP; q++)
+              C[(size_t)r * NP + q] = (r == q) ? 1. : (dec.subs[r].intersect[q].empty() ? 1. : 0.);
+          for (int r = 0; r < NP; r++) { double sum = 0.; for (int q = 0; q < NP; q++) sum += C[(size_t)r * NP + q]; F[r] = 1. / sum; }
+          for (int r = 0; r < NP; r++) for (int q = 0; q < NP; q++) C[(size_t)r * NP + q] *= F[r] * F[q];
+          sym_eig(NP, C.data(), wv.data());
+          double lam = wv[0];
+          for (int r = 0; r < NP; r++) if (std::fabs(wv[r]) > std::fabs(lam)) lam = wv[r];
+          gl = gl / lam * F[s.id] * F[s.id];
+          if (gl <= 1.) gl = 1.1;
+          s.gammaLoc = gl;
+        }
+        eigen_local_problem(s, vB.p, s.vRob.p, gl, false, ws, vals, vecs, counts);
+      }
+      opt.cut = savedCut;
+      // assemble Z_s = D [v_1 ... v_nev]  (fillZE2L, src/geneo.cpp:249-272); empty => constant vector (:1305-1314)
+      int nev = 0;
+      for (int c : counts) nev += c;
+      const double tz = now_s();
+      if (nev == 0) {
+        s.nev = 1;
+        s.Z.alloc((size_t)s.n);
+        CUDA_CHECK(cudaMemcpyAsync(s.Z.p, s.d.p, sizeof(double) * s.n, cudaMemcpyDeviceToDevice, st));  // D * 1
+        s.eigvals.assign(1, 0.);
+        s.nicolaides += 1;
+      } else {
+        s.nev = nev;
+        s.Z.alloc((size_t)s.n * nev);
+        int c0 = 0;
+        for (size_t b = 0; b < vecs.size(); b++) {
+          const int nc = counts[b];
+          if (nc == 0) continue;
+          // copy block b (n x nc, ld nc) into columns c0.. of Z (ld nev) scaled by d: reuse ts_update with identity? simple 2D copy + scale
+          CUDA_CHECK(cudaMemcpy2DAsync(s.Z.p + c0, sizeof(double) * nev, vecs[b].p, sizeof(double) * nc, sizeof(double) * nc, s.n, cudaMemcpyDeviceToDevice, st));
+          c0 += nc;
+        }
+        rows_scale(s.n, nev, s.d.p, s.Z.p, st);  // Z = D V
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        s.eigvals = vals;
+      }
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      lvl2SetupZTime += now_s() - tz;
+    }
+    // level 1: factor A_dir (or A_rob), src/geneo.cpp:126-148
+    const double tl1 = now_s();
+    s.L1.reset(new LdltFactor(s.plan));
+    FactorStats fs = s.L1->factorize(opt.lvl1ORAS ? s.vRob.p : s.pat.val.p, pivTol, ws, st);
+    s.negL1 = fs.neg;
+    s.perturbed = fs.perturbed;
+    lvl1SetupMinvTime += now_s() - tl1;
+    factorBytes += (int64_t)s.L1->L.bytes();
+    factorNnz += s.plan->sym.lSize;
+    factorFlops += s.plan->sym.flops;
+    estimDimE += s.estim;
+    realDimE += s.nev;
+    nicolaides += s.nicolaides;
+  }
+  ws = LdltWorkspace();
+  if (opt.lvl2 >= 1) {
+    const double te = now_s();
+    build_coarse();
+    lvl2SetupETime = now_s() - te;
+    infoL2 = "blocklanczos ldlt";
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  setupTime = now_s() - tSetup0;
+}
+
+// eigenLocalProblem (src/geneo.cpp:842-963) + estimateNumberOfEigenValues (:502-533) + eigenLocalSolve (:626-722)
+int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb,
+                                 LdltWorkspace& ws, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs,
+                                 std::vector<int>& counts) {
+  const int n = s.n;
+  const int64_t nnz = s.pat.nnz;
+  const double anorm = s.anorm;
+  const double pivTol = opt.pivRel * std::max(anorm, 1e-300);
+  int nev = 1;  // SLEPc default when nothing is requested
+  int est = 0;
+  LdltFactor tmp(s.plan);
+  if (!opt.noSyl) {
+    const double t0 = now_s();
+    DevBuf<double> vS((size_t)nnz);
+    vals_axpby(nnz, vA, param, vB, vS.p, st);  // A - param B, src/geneo.cpp:511-515
+    FactorStats fs = tmp.factorize(vS.p, pivTol, ws, st);
+    est = tauPb ? fs.neg : (n - fs.neg);  // #eigenvalues below tau / above gamma (Sylvester)
+    if (est > n) est = n;
+    if (opt.cut > 0 && est > opt.cut) est = opt.cut;
+    s.estim += est;
+    s.perturbed += fs.perturbed;
+    const double dt = now_s() - t0;
+    lvl2SetupSylTime += dt;
+    (tauPb ? lvl2SetupTauSylTime : lvl2SetupGammaSylTime) += dt;
+    if (est > 0) nev = est;
+  }
+  if (opt.cut > 0 && nev > opt.cut) nev = opt.cut;
+  std::vector<double> lam;
+  DevBuf<double> X;
+  int got = 0;
+  if (opt.noSyl || est > 0) {
+    const double t0 = now_s();
+    EigOptions eo;
+    eo.block = opt.epsBlock; eo.tol = opt.epsTol; eo.maxDim = opt.epsMaxDim; eo.invert = tauPb;
+    EigResult er;
+    if (tauPb) {  // A x = lambda B x, smallest: T = A^-1 B
+      tmp.factorize(vA, pivTol, ws, st);
+      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vB, std::min(nev, n), eo, er, st);
+    } else {      // A x = lambda B x, largest: T = B^-1 A, self-adjoint in the A inner product
+      tmp.factorize(vB, pivTol, ws, st);
+      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vA, std::min(nev, n), eo, er, st);
+    }
+    if (er.nconv < (int)er.lambda.size())
+      fprintf(stderr, "WRNG: geneo_b200: eigen solve of subdomain %d converged %d/%d pairs (dim %d)\n", s.id, er.nconv,
+              (int)er.lambda.size(), er.dim);
+    s.eigSteps += er.steps;
+    s.eigDim = std::max(s.eigDim, er.dim);
+    // keep lambda <= tau (tau) / >= gamma (gamma): src/geneo.cpp:713-714.  Kept pairs are a prefix (sorted).
+    for (size_t i = 0; i < er.lambda.size(); i++) {
+      const bool keep = tauPb ? (er.lambda[i] <= param) : (er.lambda[i] >= param);
+      if (!keep) break;
+      lam.push_back(er.lambda[i]);
+    }
+    got = (int)lam.size();
+    if (got > 0) {
+      X.alloc((size_t)n * got);
+      CUDA_CHECK(cudaMemcpy2DAsync(X.p, sizeof(double) * got, er.vecs.p, sizeof(double) * er.lambda.size(),
+                                   sizeof(double) * got, n, cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const double dt = now_s() - t0;
+    lvl2SetupEigTime += dt;
+    (tauPb ? lvl2SetupTauEigTime : lvl2SetupGammaEigTime) += dt;
+  }
+  tmp.release();
+  // Nicolaides (src/geneo.cpp:897-944): add the constant vector when eigenvalues were kept, none is ~0 and 1 is in ker(A)
+  bool addOne = false;
+  if (tauPb && got > 0 && *std::min_element(lam.begin(), lam.end()) >= DBL_EPSILON) {
+    double num = 0., den = 0.;
+    csr_sum_all(nnz, vA, scal.p, st);
+    CUDA_CHECK(cudaMemcpyAsync(&num, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    csr_sum_all(nnz, vB, scal.p, st);
+    CUDA_CHECK(cudaMemcpyAsync(&den, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (std::fabs(num / den) <= (double)FLT_EPSILON) addOne = true;
+  }
+  if (got > 0) { vals.insert(vals.end(), lam.begin(), lam.end()); vecs.push_back(std::move(X)); counts.push_back(got); }
+  if (addOne) {
+    DevBuf<double> one((size_t)n);
+    vec_set(n, 1., one.p, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    vals.push_back(0.);
+    vecs.push_back(std::move(one));
+    counts.push_back(1);
+    s.nicolaides += 1;
+  }
+  return got;
+}
+
+// Z offsets (all_gather of nev_i, src/geneo.cpp:363-375), E = Z^T A Z (MatPtAP :1033), E^-1 (dcs2_, :1059-1065)
+void GeneoPC::build_coarse() {
+  const int P = (int)subs.size();
+  nE = 0;
+  for (auto& s : subs) { s.zoff = nE; nE += s.nev; }
+  const int nEp = (nE + 7) / 8 * 8;
+  DevBuf<double> dE((size_t)nE * nE);
+  dE.zero(st);
+  DevBuf<double> G((size_t)nLoc * 8), Wg((size_t)nLoc * 8);
+  int nmax = 0;
+  for (auto& s : subs) nmax = std::max(nmax, s.n);
+  DevBuf<double> Gi((size_t)nmax * 8);
+  for (int j = 0; j < P; j++) {
+    SubdomainState& sj = subs[j];
+    for (int c0 = 0; c0 < sj.nev; c0 += 8) {
+      const int nc = std::min(8, sj.nev - c0);
+      G.zero(st);
+      scatter_rows8(sj.n, sj.gidx.p, sj.Z.p, sj.nev, c0, nc, G.p, st);
+      sell_spmm8(A, G.p, Wg.p, st);
+      for (int i = 0; i < P; i++) {
+        SubdomainState& si = subs[i];
+        gather_rows8(si.n, si.gidx.p, Wg.p, Gi.p, st);
+        // E[zoff_i + a, zoff_j + c0 + c] += sum_k Z_i[k,a] * Gi[k,c]
+        ts_gram(si.n, si.Z.p, si.nev, si.nev, Gi.p, 8, nc, dE.p + (size_t)si.zoff * nE + sj.zoff + c0, nE, st);
+      }
+    }
+  }
+  std::vector<double> hE = dE.to_host(st);
+  for (int i = 0; i < nE; i++)
+    for (int j = i + 1; j < nE; j++) hE[(size_t)i * nE + j] = hE[(size_t)j * nE + i] = 0.5 * (hE[(size_t)i * nE + j] + hE[(size_t)j * nE + i]);
+  // dense block LDL^T of E with the same device kernels (one chain of panels), then E^-1 by solving for the identity
+  CsrHost pe;
+  pe.n = pe.ncols = nE;
+  pe.ptr.resize(nE + 1);
+  pe.idx.resize((size_t)nE * nE);
+  for (int i = 0; i <= nE; i++) pe.ptr[i] = (int64_t)i * nE;
+  for (int i = 0; i < nE; i++) for (int j = 0; j < nE; j++) pe.idx[(size_t)i * nE + j] = j;
+  SymbolicOptions so;
+  so.nb = opt.nb; so.ordering = 0; so.amalgamate = false;
+  auto plan = std::make_shared<LdltPlan>(nE, pe.ptr.data(), pe.idx.data(), so);
+  LdltFactor LE(plan);
+  LdltWorkspace ws;
+  dE.upload(hE, st);
+  double emax = 0.;
+  for (int i = 0; i < nE; i++) emax = std::max(emax, std::fabs(hE[(size_t)i * nE + i]));
+  FactorStats fs = LE.factorize(dE.p, opt.pivRel * std::max(emax, 1e-300), ws, st);
+  if (fs.neg > 0 || fs.perturbed > 0)
+    fprintf(stderr, "WRNG: geneo_b200: coarse operator E is not positive definite (neg %d, perturbed %d)\n", fs.neg, fs.perturbed);
+  std::vector<double> hI((size_t)nE * nEp, 0.);
+  for (int i = 0; i < nE; i++) hI[(size_t)i * nEp + i] = 1.;
+  DevBuf<double> dI;
+  dI.upload(hI, st);
+  Einv.alloc((size_t)nE * nEp);
+  Einv.zero(st);
+  for (int j0 = 0; j0 < nEp; j0 += 8) LE.solve_permuted(dI.p, Einv.p, nEp, j0, 8, st);
+  w.alloc(nEp); w2.alloc(nEp);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+// =====================================================================================================================
+// Apply
+// =====================================================================================================================
+void GeneoPC::applyQ(const double* x, double* y) {  // src/geneo.cpp:1435-1517
+  const int P = (int)subs.size();
+  gather_rows(nAll, gidxAll.p, nullptr, x, Xall.p, st);
+  w.zero(st);
+  for (int p = 0; p < P; p++) zt_x(subs[p].n, subs[p].nev, subs[p].Z.p, subs[p].nev, Xall.p + subs[p].off, w.p + subs[p].zoff, st);
+  dense_gemv(nE, nE, Einv.p, (nE + 7) / 8 * 8, w.p, w2.p, st);
+  Yall.zero(st);
+  for (int p = 0; p < P; p++) z_w_add(subs[p].n, subs[p].nev, subs[p].Z.p, subs[p].nev, w2.p + subs[p].zoff, nullptr, Yall.p + subs[p].off, st);
+  pull_sum(nLoc, pullPtr.p, pullPos.p, Yall.p, y, false, st);
+}
+
+// restrict, [D], M^-1, [D], (+ Z E^-1 Z^T fused when addQ), prolong-add.  src/geneo.cpp:1980-2025, 1845-1900.
+void GeneoPC::level1(const double* xin, double* yout, bool addQ) {
+  const int P = (int)subs.size();
+  double tt = 0.;
+  auto tic = [&]() { if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); tt = now_s(); } };
+  auto toc = [&](double& acc) { if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); acc += now_s() - tt; } };
+  tic();
+  gather_rows(nAll, gidxAll.p, nullptr, xin, Xall.p, st);
+  toc(lvl1ApplyScatterTime);
+  if (addQ) {
+    tic();
+    w.zero(st);
+    for (int p = 0; p < P; p++) zt_x(subs[p].n, subs[p].nev, subs[p].Z.p, subs[p].nev, Xall.p + subs[p].off, w.p + subs[p].zoff, st);
+    toc(lvl2ApplyZtTime);
+    tic();
+    dense_gemv(nE, nE, Einv.p, (nE + 7) / 8 * 8, w.p, w2.p, st);
+    toc(lvl2ApplyEinvTime);
+  }
+  tic();
+  if (opt.lvl1RAS) vec_pointwise(nAll, dAll.p, Xall.p, st);  // D before the solve, src/geneo.cpp:1991-1993
+  // local solves: subdomains are independent -> round-robin over side streams
+  CUDA_CHECK(cudaEventRecord(evFork, st));
+  const int ns = (int)streams.size();
+  for (int i = 0; i < ns; i++) CUDA_CHECK(cudaStreamWaitEvent(streams[i], evFork, 0));
+  for (int p = 0; p < P; p++)
+    subs[p].L1->solve_permuted(Xall.p + subs[p].off, Yall.p + subs[p].off, 1, 0, 1, streams[p % ns]);
+  for (int i = 0; i < ns; i++) {
+    CUDA_CHECK(cudaEventRecord(events[i], streams[i]));
+    CUDA_CHECK(cudaStreamWaitEvent(st, events[i], 0));
+  }
+  toc(lvl1ApplyMinvTime);
+  if (addQ || opt.lvl1SRAS) {
+    tic();
+    for (int p = 0; p < P; p++)
+      z_w_add(subs[p].n, addQ ? subs[p].nev : 0, subs[p].Z.p, subs[p].nev, addQ ? w2.p + subs[p].zoff : nullptr,
+              opt.lvl1SRAS ? subs[p].d.p : nullptr, Yall.p + subs[p].off, st);
+    toc(addQ ? lvl2ApplyZTime : lvl1ApplyMinvTime);
+  }
+  tic();
+  pull_sum(nLoc, pullPtr.p, pullPos.p, Yall.p, yout, false, st);
+  toc(lvl1ApplyGatherTime);
+}
+
+void GeneoPC::apply(const double* x, double* y) {  // applyGenEOPC, src/geneo.cpp:2051-2098
+  applyCount++;
+  double t0 = 0.;
+  if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); t0 = now_s(); }
+  if (opt.lvl2 == 0) level1(x, y, false);
+  else if (!opt.hybrid) level1(x, y, true);                         // y = Q x + sum R^T [D] M^-1 [D] R x
+  else if (!opt.effHybrid) {
+    applyQ(x, t1.p);                                                // t1 = Q x
+    sell_spmv_sub(A, t1.p, x, t2.p, st);                            // t2 = x - A Q x = (I - P^T) x
+    level1(t2.p, t3.p, false);
+    sell_spmv(A, t3.p, t2.p, st);
+    applyQ(t2.p, y);                                                // y = Q A t3
+    vec_axpby(nLoc, 1., t3.p, -1., y, st);                          // y = (I - P) t3
+    vec_axpy(nLoc, 1., t1.p, y, st);                                // y += Q x
+  } else {
+    level1(x, t3.p, false);
+    sell_spmv(A, t3.p, t2.p, st);
+    applyQ(t2.p, y);
+    vec_axpby(nLoc, 1., t3.p, -1., y, st);
+  }
+  if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); lvl1ApplyTime += now_s() - t0; }
+}
+
+void GeneoPC::initial_guess(const double* b, double* x0) {
+  if (opt.lvl2 >= 1 && opt.effHybrid) applyQ(b, x0);
+  else CUDA_CHECK(cudaMemsetAsync(x0, 0, sizeof(double) * nLoc, st));
+}
+
+void GeneoPC::copy_einv(double* out) const {
+  const int nEp = (nE + 7) / 8 * 8;
+  std::vector<double> h = Einv.to_host(st);
+  for (int i = 0; i < nE; i++)
+    for (int j = 0; j < nE; j++) out[(size_t)i * nE + j] = h[(size_t)i * nEp + j];
+}
+
+double GeneoPC::trisolve_algo_bytes() const {
+  double b = 0.;
+  for (auto& s : subs)
+    for (auto& F : s.plan->sym.fronts) {
+      const double k = F.k, m = F.m();
+      b += 8. * (2. * m * k + k * k) + 2. * 4. * m + 8. * 4. * (k + m);  // factor once fwd + once bwd, D^-1 once, indices, x/y
+    }
+  return b;
+}
+double GeneoPC::apply_algo_bytes() const {
+  double b = trisolve_algo_bytes();
+  double nz = 0.;
+  for (auto& s : subs) nz += (double)s.n * s.nev;
+  b += 6. * 8. * (double)nAll + 4. * (double)nAll;
+  if (opt.lvl2 >= 1) b += 2. * 8. * nz + 8. * (double)nE * nE;
+  b += 2. * 8. * (double)nLoc;
+  return b;
+}
+
+// =====================================================================================================================
+// Krylov: PETSc-faithful left-preconditioned CG and GMRES(m)
+// =====================================================================================================================
+namespace {
+struct ConvTest {  // KSPConvergedDefault
+  double ttol = 0., rnorm0 = 0., atol = 0., dtol = 0.;
+  int operator()(double rn) const {
+    if (rn != rn) return KSP_DIVERGED_NANORINF;
+    if (rn <= ttol) return rn < atol ? KSP_CONVERGED_ATOL : KSP_CONVERGED_RTOL;
+    if (rn >= dtol * rnorm0) return KSP_DIVERGED_DTOL;
+    return 0;
+  }
+};
+}  // namespace
+
+KspResult GeneoPC::solve_cg(const double* b, double* x, double rtol, double atol, double dtol, int maxIt) {
+  KspResult R;
+  DevBuf<double> r(nLoc), z(nLoc), p(nLoc), wv(nLoc);
+  sell_spmv_sub(A, x, b, r.p, st);  // non-zero initial guess is ALWAYS flagged (src/geneo4PETSc.cpp:1348)
+  apply(r.p, z.p);
+  double dp = norm(z.p);
+  R.history.push_back(dp);
+  ConvTest conv;
+  {  // reference norm ||M^-1 b|| (guess non-zero)
+    apply(b, wv.p);
+    double sn = norm(wv.p);
+    if (sn == 0.) sn = dp;
+    conv.ttol = std::max(rtol * sn, atol); conv.rnorm0 = sn; conv.atol = atol; conv.dtol = dtol;
+  }
+  R.rnorm = dp;
+  R.reason = conv(dp);
+  if (R.reason) return R;
+  double beta = dot(z.p, r.p), betaold = 1.;
+  int i = 0;
+  while (i < maxIt) {
+    if (beta == 0.) { R.reason = KSP_CONVERGED_ATOL; R.its = i; return R; }
+    if (i > 0 && beta * betaold < 0.) { R.reason = KSP_DIVERGED_INDEFINITE_PC; R.its = i; return R; }
+    if (i == 0) CUDA_CHECK(cudaMemcpyAsync(p.p, z.p, sizeof(double) * nLoc, cudaMemcpyDeviceToDevice, st));
+    else vec_aypx(nLoc, beta / betaold, z.p, p.p, st);  // p = z + b p
+    mult(p.p, wv.p);
+    const double dpi = dot(p.p, wv.p);
+    betaold = beta;
+    if (dpi <= 0.) { R.reason = KSP_DIVERGED_INDEFINITE_MAT; R.its = i + 1; return R; }
+    const double a = beta / dpi;
+    vec_cg_update(nLoc, a, p.p, wv.p, x, r.p, st);
+    apply(r.p, z.p);
+    vec_dot2(nOwn, z.p, r.p, z.p, scal.p, st);  // beta = z.r and ||z||^2 in one pass
+    double h[2];
+    CUDA_CHECK(cudaMemcpyAsync(h, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    dp = std::sqrt(h[1]);
+    R.history.push_back(dp);
+    R.rnorm = dp;
+    R.its = i + 1;
+    R.reason = conv(dp);
+    if (R.reason) return R;
+    beta = h[0];
+    i++;
+  }
+  R.reason = KSP_DIVERGED_ITS;
+  R.its = i;
+  return R;
+}
+
+KspResult GeneoPC::solve_gmres(const double* b, double* x, double rtol, double atol, double dtol, int maxIt, int restart) {
+  KspResult R;
+  restart = std::max(1, std::min(restart, maxIt));
+  size_t freeB = 0, totB = 0;
+  CUDA_CHECK(cudaMemGetInfo(&freeB, &totB));
+  const size_t need = (size_t)(restart + 1) * nLoc * sizeof(double);
+  if (need > freeB * 0.9) {  // the reference's test scripts use -ksp_gmres_restart 1000; clamp to what fits
+    restart = (int)std::max<size_t>(2, (size_t)(freeB * 0.9 / ((double)nLoc * sizeof(double))) - 1);
+    fprintf(stderr, "WRNG: geneo_b200: GMRES restart clamped to %d (device memory)\n", restart);
+  }
+  DevBuf<double> V((size_t)(restart + 1) * nLoc), t(nLoc), wv(nLoc), coef(restart + 8);
+  std::vector<double> H((size_t)(restart + 1) * restart, 0.), cs(restart), sn(restart), g(restart + 1), hk(restart + 8), y(restart);
+  ConvTest conv;
+  bool haveTol = false;
+  int its = 0;
+  double res = 0.;
+  int reason = 0;
+  while (true) {
+    sell_spmv_sub(A, x, b, t.p, st);
+    apply(t.p, V.p);  // r = M^-1 (b - A x)
+    res = norm(V.p);
+    if (!haveTol) {
+      apply(b, wv.p);
+      double s0 = norm(wv.p);
+      if (s0 == 0.) s0 = res;
+      conv.ttol = std::max(rtol * s0, atol); conv.rnorm0 = s0; conv.atol = atol; conv.dtol = dtol;
+      haveTol = true;
+      R.history.push_back(res);
+    }
+    reason = conv(res);
+    if (reason || its >= maxIt) break;
+    if (res == 0.) { reason = KSP_CONVERGED_ATOL; break; }
+    vec_scale(nLoc, 1. / res, V.p, st);
+    std::fill(g.begin(), g.end(), 0.);
+    g[0] = res;
+    int k = 0;
+    while (k < restart && its < maxIt) {
+      double* vk = V.p + (size_t)k * nLoc;
+      double* vn = V.p + (size_t)(k + 1) * nLoc;
+      mult(vk, t.p);
+      apply(t.p, vn);  // w = M^-1 A v_k
+      vec_mdot(nOwn, k + 1, V.p, nLoc, vn, coef.p, st);  // classical Gram-Schmidt, no refinement (PETSc default)
+      vec_maxpy(nLoc, k + 1, V.p, nLoc, coef.p, vn, st);
+      CUDA_CHECK(cudaMemcpyAsync(hk.data(), coef.p, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, st));
+      const double tt = norm(vn);
+      for (int j = 0; j <= k; j++) H[(size_t)j * restart + k] = hk[j];
+      double hap = g[k] != 0. ? std::fabs(tt / g[k]) : 1e-30;
+      if (hap > 1e-30) hap = 1e-30;
+      const bool happy = tt < hap;
+      if (!happy) vec_scale(nLoc, 1. / tt, vn, st);
+      H[(size_t)(k + 1) * restart + k] = tt;
+      for (int j = 0; j < k; j++) {
+        const double t1v = H[(size_t)j * restart + k];
+        H[(size_t)j * restart + k] = cs[j] * t1v + sn[j] * H[(size_t)(j + 1) * restart + k];
+        H[(size_t)(j + 1) * restart + k] = -sn[j] * t1v + cs[j] * H[(size_t)(j + 1) * restart + k];
+      }
+      const double den = std::hypot(H[(size_t)k * restart + k], H[(size_t)(k + 1) * restart + k]);
+      if (den == 0.) { reason = KSP_DIVERGED_BREAKDOWN; break; }
+      cs[k] = H[(size_t)k * restart + k] / den;
+      sn[k] = H[(size_t)(k + 1) * restart + k] / den;
+      H[(size_t)k * restart + k] = den;
+      H[(size_t)(k + 1) * restart + k] = 0.;
+      g[k + 1] = -sn[k] * g[k];
+      g[k] = cs[k] * g[k];
+      res = std::fabs(g[k + 1]);
+      k++;
+      its++;
+      R.history.push_back(res);
+      reason = conv(res);
+      if (reason) break;
+      if (happy) { reason = KSP_CONVERGED_HAPPY_BREAKDOWN; break; }
+    }
+    if (k > 0) {  // x += V y,  H y = g
+      for (int i = k - 1; i >= 0; i--) {
+        double s = g[i];
+        for (int j = i + 1; j < k; j++) s -= H[(size_t)i * restart + j] * y[j];
+        y[i] = s / H[(size_t)i * restart + i];
+      }
+      for (int i = 0; i < k; i++) hk[i] = -y[i];
+      CUDA_CHECK(cudaMemcpyAsync(coef.p, hk.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
+      vec_maxpy(nLoc, k, V.p, nLoc, coef.p, x, st);
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (reason) break;
+    if (its >= maxIt) { reason = KSP_DIVERGED_ITS; break; }
+  }
+  if (!reason) reason = KSP_DIVERGED_ITS;
+  R.its = its;
+  R.rnorm = res;
+  R.reason = reason;
+  return R;
+}
+
+}  // namespace geneo

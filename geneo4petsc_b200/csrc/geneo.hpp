@@ -1,0 +1,129 @@
+// geneo.hpp -- the two-level GenEO Schwarz preconditioner and the preconditioned Krylov iteration it drives,
+// device-resident.  Host-side mirror of the reference's plug-in interface (hdr/geneo.hpp:46-138 geneoContext,
+// src/geneo.cpp:1672-1843 setUpGenEOPC, :2051-2098 applyGenEOPC, :2329-2514 options, :2245-2268 name).
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "eigen.hpp"
+#include "kernels.hpp"
+#include "ldlt.hpp"
+#include "mesh.hpp"
+
+namespace geneo {
+
+// Same parameters, names and defaults as geneoContext (hdr/geneo.hpp:54-70; defaults src/geneo.cpp:2649-2662).
+struct GeneoOptions {
+  bool lvl1ASM = true, lvl1RAS = false, lvl1SRAS = false, lvl1ORAS = false;
+  int lvl2 = 1;
+  bool hybrid = false, effHybrid = false;
+  double optim = 0., tau = 0.1, gamma = 10.;
+  bool cst = false;
+  int cut = -1;
+  bool noSyl = false, offload = false;
+  int debug = 0;
+  bool check = false;
+  // knobs of the sub-solvers (stand for the reference's -dls1_/-syl2_/-els2_/-dcs2_ PETSc option prefixes)
+  int nb = 128;          // LDL^T panel width
+  int ordering = 1;      // 1 METIS NodeND, 0 natural
+  double epsTol = 1e-4;  // -els2_eps_tol (block Lanczos residual tolerance; reference default 1e-3, src/geneo.cpp:658)
+  int epsBlock = 8;
+  int epsMaxDim = 0;     // -els2_eps_ncv like bound on the Krylov dimension (0 = automatic)
+  double pivRel = 1e-14; // static pivot threshold relative to max |a_ij| (stands for MUMPS CNTL(1/3), ICNTL(24))
+  bool timing = false;   // synchronise and time every apply phase (reference timers hdr/geneo.hpp:115-123)
+
+  // Parse "-geneo_lvl ASM,1 -geneo_tau 0.1 ..." (grammar of src/geneo.cpp:2338-2481).  Unknown tokens are ignored
+  // (they belong to the caller: PETSc options DB in the reference).  Returns 0, or 1 + message on a bad value.
+  int parse(int argc, const char* const* argv, std::string& err);
+  std::string name() const;  // buildGenEOName
+};
+
+struct SubdomainState {
+  int id = 0, n = 0, nev = 0;
+  int64_t off = 0;   // into the concatenated subdomain vectors
+  int zoff = 0;      // into the coarse vector
+  std::shared_ptr<LdltPlan> plan;
+  std::unique_ptr<LdltFactor> L1;
+  DevBuf<int> gidx;       // rank-local index of solver-order row k
+  DevBuf<double> d;       // partition of unity, solver order
+  DevBuf<double> Z;       // n x nev row-major, solver order, already D-weighted
+  CsrDev pat;             // permuted pattern of A_dir; pat.val = A_dir values
+  DevBuf<double> vNeu, vRob;
+  std::vector<double> eigvals;
+  int estim = 0, nicolaides = 0, eigSteps = 0, eigDim = 0, negL1 = 0, perturbed = 0;
+  double tauLoc = -1., gammaLoc = -1.;
+  int maxMult = 1;
+  double anorm = 0.;  // max |a_ij| of A_dir (scale of the static pivot threshold)
+};
+
+struct KspResult {
+  int its = 0, reason = 0;
+  double rnorm = 0.;
+  std::vector<double> history;
+};
+// PETSc KSPConvergedReason values used here
+enum { KSP_CONVERGED_RTOL = 2, KSP_CONVERGED_ATOL = 3, KSP_CONVERGED_HAPPY_BREAKDOWN = 7, KSP_DIVERGED_ITS = -3,
+       KSP_DIVERGED_DTOL = -4, KSP_DIVERGED_BREAKDOWN = -5, KSP_DIVERGED_INDEFINITE_PC = -8, KSP_DIVERGED_NANORINF = -9,
+       KSP_DIVERGED_INDEFINITE_MAT = -10 };
+const char* ksp_reason_name(int reason);
+
+class GeneoPC {
+ public:
+  GeneoOptions opt;
+  int nbDof = 0;      // global size
+  int nLoc = 0;       // length of the vectors held by this process (== nbDof on one GPU)
+  int nOwn = 0;       // leading entries owned by this process (dots/norms run over these)
+  int nbPart = 0;
+  SellMatrix A;       // operator, sum_i R_i^T A_neu,i R_i
+  std::vector<SubdomainState> subs;
+  int nE = 0;
+  cudaStream_t st = 0;
+
+  // reference timers (hdr/geneo.hpp:115-123), seconds
+  double lvl1SetupMinvTime = 0., lvl2SetupSylTime = 0., lvl2SetupEigTime = 0., lvl2SetupZTime = 0., lvl2SetupETime = 0.;
+  double lvl2SetupTauLocTime = 0., lvl2SetupTauSylTime = 0., lvl2SetupTauEigTime = 0.;
+  double lvl2SetupGammaLocTime = 0., lvl2SetupGammaSylTime = 0., lvl2SetupGammaEigTime = 0.;
+  double lvl1ApplyTime = 0., lvl1ApplyScatterTime = 0., lvl1ApplyMinvTime = 0., lvl1ApplyGatherTime = 0.;
+  double lvl1ApplyPrjFSTime = 0., lvl2ApplyTime = 0., lvl2ApplyZtTime = 0., lvl2ApplyEinvTime = 0., lvl2ApplyZTime = 0.;
+  double symbolicTime = 0., operatorTime = 0., setupTime = 0.;
+  int estimDimE = 0, realDimE = 0, nicolaides = 0;
+  int64_t factorBytes = 0, factorNnz = 0, applyCount = 0;
+  double factorFlops = 0.;
+  std::string infoL2;
+
+  GeneoPC();
+  ~GeneoPC();
+  // All subdomains of `dec` whose matrices are present are local to this process (single-GPU path).
+  void setup(const Decomposition& dec);
+  void apply(const double* x, double* y);                 // device pointers, length nLoc; x is not modified
+  void applyQ(const double* x, double* y);                // y = Z E^-1 Z^T x
+  void mult(const double* x, double* y) { sell_spmv(A, x, y, st); }
+  void initial_guess(const double* b, double* x0);        // x0 = Q b (efficient hybrid) or 0 (src/geneo.cpp:1601-1607)
+  KspResult solve_cg(const double* b, double* x, double rtol, double atol, double dtol, int maxIt);
+  KspResult solve_gmres(const double* b, double* x, double rtol, double atol, double dtol, int maxIt, int restart);
+  double dot(const double* x, const double* y);
+  double norm(const double* x) { return std::sqrt(dot(x, x)); }
+  // algorithmic bytes of one PC apply and of its dominant kernel family (factor sweeps)
+  double apply_algo_bytes() const;
+  double trisolve_algo_bytes() const;
+  void copy_einv(double* out) const;  // nE x nE row-major E^-1 to the host
+
+ private:
+  void setup_subdomain_numeric(const Subdomain& S, SubdomainState& s, LdltWorkspace& ws);
+  int eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb,
+                          LdltWorkspace& ws, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs,
+                          std::vector<int>& counts);
+  void build_coarse();
+  void level1(const double* xin, double* yout, bool addQ);
+  DevBuf<double> Xall, Yall, w, w2, Einv, t1, t2, t3, scal;
+  DevBuf<int> gidxAll;
+  DevBuf<double> dAll;
+  DevBuf<int64_t> pullPtr, pullPos;
+  int64_t nAll = 0;
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t evFork = nullptr;
+};
+
+}  // namespace geneo

@@ -1,0 +1,522 @@
+// kernels.cu -- see kernels.hpp.  sm_100a.  Everything here is HBM-bound: coalesced, vectorised where alignment is
+// known, grid sized as a multiple of the 148 SMs, warp-shuffle reductions.
+#include "kernels.hpp"
+
+#include <algorithm>
+
+namespace geneo {
+namespace {
+
+constexpr int NSM = 148;
+
+inline int grid_for(int64_t n, int threads, int perSm = 8) {
+  int64_t g = (n + threads - 1) / threads;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)NSM * perSm));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block reduction of NV values per thread, result atomically added to out[0..NV)
+template <int NV>
+__device__ __forceinline__ void block_reduce_atomic(double (&v)[NV], double* out) {
+  __shared__ double sh[NV][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    v[q] = warp_sum(v[q]);
+    if (lane == 0) sh[q][warp] = v[q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      double s = lane < nw ? sh[q][lane] : 0.;
+      s = warp_sum(s);
+      if (lane == 0) atomicAdd(out + q, s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SELL-32 SpMV
+// ---------------------------------------------------------------------------------------------------------------
+template <bool SUB>
+__global__ void __launch_bounds__(256) k_sell_spmv(int n, int nslices, const int64_t* __restrict__ sliceOff,
+                                                   const int* __restrict__ col, const double* __restrict__ val,
+                                                   const double* __restrict__ x, const double* __restrict__ b,
+                                                   double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < nslices; s += gridDim.x * wpb) {
+    const int64_t o0 = sliceOff[s], o1 = sliceOff[s + 1];
+    const int width = (int)((o1 - o0) >> 5);
+    const int* c = col + o0 + lane;
+    const double* v = val + o0 + lane;
+    double a0 = 0., a1 = 0.;
+    int j = 0;
+    for (; j + 4 <= width; j += 4) {
+      const int c0 = c[(j + 0) * 32], c1 = c[(j + 1) * 32], c2 = c[(j + 2) * 32], c3 = c[(j + 3) * 32];
+      const double v0 = v[(j + 0) * 32], v1 = v[(j + 1) * 32], v2 = v[(j + 2) * 32], v3 = v[(j + 3) * 32];
+      a0 += v0 * __ldg(x + c0);
+      a1 += v1 * __ldg(x + c1);
+      a0 += v2 * __ldg(x + c2);
+      a1 += v3 * __ldg(x + c3);
+    }
+    for (; j < width; j++) a0 += v[j * 32] * __ldg(x + c[j * 32]);
+    const int row = s * 32 + lane;
+    if (row < n) y[row] = SUB ? (b[row] - (a0 + a1)) : (a0 + a1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sell_spmm8(int n, int nslices, const int64_t* __restrict__ sliceOff,
+                                                    const int* __restrict__ col, const double* __restrict__ val,
+                                                    const double* __restrict__ X, double* __restrict__ Y) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < nslices; s += gridDim.x * wpb) {
+    const int64_t o0 = sliceOff[s], o1 = sliceOff[s + 1];
+    const int width = (int)((o1 - o0) >> 5);
+    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    for (int j = 0; j < width; j++) {
+      const int c = col[o0 + j * 32 + lane];
+      const double v = val[o0 + j * 32 + lane];
+      const double2* xr = reinterpret_cast<const double2*>(X + (size_t)c * 8);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double2 xv = __ldg(xr + q);
+        acc[2 * q] += v * xv.x;
+        acc[2 * q + 1] += v * xv.y;
+      }
+    }
+    const int row = s * 32 + lane;
+    if (row < n) {
+      double2* yr = reinterpret_cast<double2*>(Y + (size_t)row * 8);
+#pragma unroll
+      for (int q = 0; q < 4; q++) yr[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
+    }
+  }
+}
+__global__ void k_scatter_rows8(int n, const int* __restrict__ idx, const double* __restrict__ Z, int ldz, int c0, int nc,
+                                double* __restrict__ G) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)n * 8; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = t >> 3;
+    const int c = (int)(t & 7);
+    G[(size_t)idx[k] * 8 + c] = c < nc ? Z[(size_t)k * ldz + c0 + c] : 0.;
+  }
+}
+__global__ void k_gather_rows8(int n, const int* __restrict__ idx, const double* __restrict__ G, double* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)n * 8; t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = G[(size_t)idx[t >> 3] * 8 + (t & 7)];
+}
+
+template <int NRT>
+__global__ void __launch_bounds__(256) k_csr_spmm(int n, const int64_t* __restrict__ ptr, const int* __restrict__ idx,
+                                                  const double* __restrict__ val, const double* __restrict__ X, int ldx,
+                                                  double* __restrict__ Y, int ldy) {
+  // NRT threads per row (one per right-hand side)
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = t / NRT;
+  const int j = (int)(t % NRT);
+  if (row >= n) return;
+  double acc = 0.;
+  for (int64_t q = ptr[row]; q < ptr[row + 1]; q++) acc += val[q] * X[(size_t)idx[q] * ldx + j];
+  Y[(size_t)row * ldy + j] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BLAS-1
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dot(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                             double* out) {
+  double v[1] = {0.};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[0] += x[i] * y[i];
+  block_reduce_atomic<1>(v, out);
+}
+__global__ void __launch_bounds__(256) k_dot2(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                              const double* __restrict__ z, double* out) {
+  double v[2] = {0., 0.};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    v[0] += x[i] * y[i];
+    const double zz = z[i];
+    v[1] += zz * zz;
+  }
+  block_reduce_atomic<2>(v, out);
+}
+__global__ void k_axpby(int n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + b * y[i];
+}
+__global__ void k_axpy(int n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+__global__ void k_cg_update(int n, double a, const double* __restrict__ p, const double* __restrict__ w,
+                            double* __restrict__ x, double* __restrict__ r) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += a * p[i];
+    r[i] -= a * w[i];
+  }
+}
+__global__ void k_scale(int n, double a, double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= a;
+}
+__global__ void k_set(int n, double a, double step, double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = a + step * (double)i;
+}
+// out[j] = V_j . w for j < nv : every CTA streams w once and all basis vectors (VecMDot)
+__global__ void __launch_bounds__(256) k_mdot(int n, int nv, const double* __restrict__ V, int64_t ldv,
+                                              const double* __restrict__ w, double* out) {
+  for (int j0 = 0; j0 < nv; j0 += 4) {
+    double v[4] = {0., 0., 0., 0.};
+    const int nj = min(4, nv - j0);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double wi = w[i];
+      for (int q = 0; q < nj; q++) v[q] += V[(j0 + q) * ldv + i] * wi;
+    }
+    __syncthreads();
+    block_reduce_atomic<4>(v, out + j0);  // out has room for nv rounded up to 4
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_maxpy(int n, int nv, const double* __restrict__ V, int64_t ldv,
+                                               const double* __restrict__ coef, double* __restrict__ w) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double s = w[i];
+    for (int j = 0; j < nv; j++) s -= coef[j] * V[j * ldv + i];
+    w[i] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// restrict / prolong
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_gather(int64_t cnt, const int* __restrict__ idx, const double* __restrict__ scale,
+                         const double* __restrict__ x, double* __restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < cnt; k += (int64_t)gridDim.x * blockDim.x) {
+    double v = __ldg(x + idx[k]);
+    if (scale) v *= scale[k];
+    out[k] = v;
+  }
+}
+__global__ void k_pull_sum(int n, const int64_t* __restrict__ ptr, const int64_t* __restrict__ pos,
+                           const double* __restrict__ t, double* __restrict__ y, bool accumulate) {
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+    double s = accumulate ? y[g] : 0.;
+    for (int64_t e = ptr[g]; e < ptr[g + 1]; e++) s += __ldg(t + pos[e]);
+    y[g] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tall-skinny dense
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GR = 64;  // rows per smem tile
+__global__ void __launch_bounds__(256) k_ts_gram(int n, const double* __restrict__ X, int ldx, int p,
+                                                 const double* __restrict__ Y, int ldy, int q, double* G, int ldg,
+                                                 int rowsPerCta) {
+  __shared__ double sx[GR][33], sy[GR][33];
+  const int p0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+  const int pi = threadIdx.x & 31, qg = threadIdx.x >> 5;  // 8 groups x 4 columns
+  const int64_t r0 = (int64_t)blockIdx.z * rowsPerCta;
+  const int64_t r1 = min((int64_t)n, r0 + rowsPerCta);
+  double acc[4] = {0., 0., 0., 0.};
+  for (int64_t rb = r0; rb < r1; rb += GR) {
+    for (int e = threadIdx.x; e < GR * 32; e += 256) {
+      const int rr = e >> 5, cc = e & 31;
+      const int64_t r = rb + rr;
+      sx[rr][cc] = (r < r1 && p0 + cc < p) ? X[(size_t)r * ldx + p0 + cc] : 0.;
+      sy[rr][cc] = (r < r1 && q0 + cc < q) ? Y[(size_t)r * ldy + q0 + cc] : 0.;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < GR; rr++) {
+      const double xv = sx[rr][pi];
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[e] += xv * sy[rr][qg * 4 + e];
+    }
+    __syncthreads();
+  }
+  if (p0 + pi < p)
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+      if (q0 + qg * 4 + e < q) atomicAdd(&G[(size_t)(p0 + pi) * ldg + q0 + qg * 4 + e], acc[e]);
+}
+
+// W[r, j] = beta W[r,j] + alpha sum_p Q[r,p] C[p,j] ; thread per (row, j), j fastest; C tiles of 64 rows in smem
+__global__ void __launch_bounds__(256) k_ts_update(int n, const double* __restrict__ Q, int ldq, int p,
+                                                   const double* __restrict__ C, int ldc, int q, double* __restrict__ W,
+                                                   int ldw, double alpha, double beta, int qpad) {
+  extern __shared__ double sc[];  // [64][qpad]
+  const int rowsPerCta = 256 / qpad;
+  const int j = threadIdx.x % qpad;
+  const int64_t r = (int64_t)blockIdx.x * rowsPerCta + threadIdx.x / qpad;
+  const bool ok = (threadIdx.x / qpad) < rowsPerCta && r < n && j < q;
+  double acc = 0.;
+  for (int pb = 0; pb < p; pb += 64) {
+    const int pc = min(64, p - pb);
+    for (int e = threadIdx.x; e < pc * qpad; e += 256) {
+      const int pp = e / qpad, jj = e % qpad;
+      sc[e] = jj < q ? C[(size_t)(pb + pp) * ldc + jj] : 0.;
+    }
+    __syncthreads();
+    if (ok) {
+      const double* qr = Q + (size_t)r * ldq + pb;
+      for (int pp = 0; pp < pc; pp++) acc += qr[pp] * sc[pp * qpad + j];
+    }
+    __syncthreads();
+  }
+  if (ok) {
+    double* w = W + (size_t)r * ldw + j;
+    *w = (beta == 0. ? 0. : beta * *w) + alpha * acc;
+  }
+}
+
+// w[c] += sum_k Z[k,c] x[k]  : block handles a row chunk; thread (c lanes within a row) ; nev <= 32*? generic loop
+__global__ void __launch_bounds__(256) k_zt_x(int n, int nev, const double* __restrict__ Z, int ldz,
+                                              const double* __restrict__ x, double* w) {
+  // thread t handles column c = t % nevPad for rows r = t / nevPad + stride
+  __shared__ double sh[256];
+  int nevPad = 1;
+  while (nevPad < nev) nevPad <<= 1;
+  if (nevPad > 256) nevPad = 256;
+  for (int c0 = 0; c0 < nev; c0 += nevPad) {
+    const int c = c0 + (threadIdx.x % nevPad);
+    const int rlane = threadIdx.x / nevPad, rstride = 256 / nevPad;
+    double acc = 0.;
+    if (c < nev)
+      for (int64_t r = (int64_t)blockIdx.x * rstride + rlane; r < n; r += (int64_t)gridDim.x * rstride)
+        acc += Z[(size_t)r * ldz + c] * x[r];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < nevPad) {
+      double s = 0.;
+      for (int q = 0; q < rstride; q++) s += sh[q * nevPad + threadIdx.x];
+      if (c0 + threadIdx.x < nev) atomicAdd(&w[c0 + threadIdx.x], s);
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_z_w_add(int n, int nev, const double* __restrict__ Z, int ldz,
+                                                 const double* __restrict__ w, const double* __restrict__ d,
+                                                 double* __restrict__ t) {
+  // one warp per 32/nevGroup rows would be ideal; simple version: warp per row group, lanes over columns
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    double acc = 0.;
+    for (int c = lane; c < nev; c += 32) acc += Z[(size_t)r * ldz + c] * w[c];
+    acc = warp_sum(acc);
+    if (lane == 0) t[r] = t[r] * (d ? d[r] : 1.) + acc;
+  }
+}
+__global__ void __launch_bounds__(256) k_dense_gemv(int m, int n, const double* __restrict__ A, int lda,
+                                                    const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= m) return;
+  double acc = 0.;
+  for (int c = lane; c < n; c += 32) acc += A[(size_t)row * lda + c] * x[c];
+  acc = warp_sum(acc);
+  if (lane == 0) y[row] = acc;
+}
+__global__ void k_pointwise(int64_t n, const double* __restrict__ d, double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= d[i];
+}
+__global__ void k_rows_scale(int64_t tot, int ld, const double* __restrict__ d, double* __restrict__ Z) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) Z[i] *= d[i / ld];
+}
+__global__ void k_csr_scale_sym(int n, const int64_t* __restrict__ ptr, const int* __restrict__ idx,
+                                const double* __restrict__ val, const double* __restrict__ d, double* __restrict__ out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const double dr = d[r];
+    for (int64_t q = ptr[r]; q < ptr[r + 1]; q++) out[q] = dr * val[q] * d[idx[q]];
+  }
+}
+__global__ void k_vals_axpby(int64_t nnz, const double* __restrict__ a, double tau, const double* __restrict__ b,
+                             double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a[i] - tau * b[i];
+}
+__global__ void __launch_bounds__(256) k_sum_all(int64_t nnz, const double* __restrict__ v, double* out) {
+  double s[1] = {0.};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) s[0] += v[i];
+  block_reduce_atomic<1>(s, out);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+void SellMatrix::build(const CsrHost& a, cudaStream_t st) {
+  n = a.n;
+  nnz = a.nnz();
+  nslices = (n + 31) / 32;
+  std::vector<int64_t> off(nslices + 1, 0);
+  for (int s = 0; s < nslices; s++) {
+    int64_t w = 0;
+    for (int r = s * 32; r < std::min(n, s * 32 + 32); r++) w = std::max<int64_t>(w, a.ptr[r + 1] - a.ptr[r]);
+    off[s + 1] = off[s] + w * 32;
+  }
+  stored = off[nslices];
+  std::vector<int> c((size_t)stored);
+  std::vector<double> v((size_t)stored, 0.);
+  for (int s = 0; s < nslices; s++) {
+    const int64_t w = (off[s + 1] - off[s]) / 32;
+    for (int l = 0; l < 32; l++) {
+      const int r = s * 32 + l;
+      const int64_t len = r < n ? a.ptr[r + 1] - a.ptr[r] : 0;
+      for (int64_t j = 0; j < w; j++) {
+        const int64_t o = off[s] + j * 32 + l;
+        if (j < len) { c[o] = a.idx[a.ptr[r] + j]; v[o] = a.val[a.ptr[r] + j]; }
+        else { c[o] = r < n ? r : 0; v[o] = 0.; }
+      }
+    }
+  }
+  sliceOff.upload(off, st);
+  col.upload(c, st);
+  val.upload(v, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void sell_spmv(const SellMatrix& A, const double* x, double* y, cudaStream_t st) {
+  const int grid = std::max(1, std::min((A.nslices + 7) / 8, NSM * 8));
+  k_sell_spmv<false><<<grid, 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, x, nullptr, y);
+  CUDA_CHECK(cudaGetLastError());
+}
+void sell_spmv_sub(const SellMatrix& A, const double* x, const double* b, double* y, cudaStream_t st) {
+  const int grid = std::max(1, std::min((A.nslices + 7) / 8, NSM * 8));
+  k_sell_spmv<true><<<grid, 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, x, b, y);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void sell_spmm8(const SellMatrix& A, const double* X, double* Y, cudaStream_t st) {
+  const int grid = std::max(1, std::min((A.nslices + 7) / 8, NSM * 8));
+  k_sell_spmm8<<<grid, 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, X, Y);
+  CUDA_CHECK(cudaGetLastError());
+}
+void scatter_rows8(int n, const int* idx, const double* Z, int ldz, int c0, int nc, double* G, cudaStream_t st) {
+  if (n) k_scatter_rows8<<<grid_for((int64_t)n * 8, 256), 256, 0, st>>>(n, idx, Z, ldz, c0, nc, G);
+}
+void gather_rows8(int n, const int* idx, const double* G, double* out, cudaStream_t st) {
+  if (n) k_gather_rows8<<<grid_for((int64_t)n * 8, 256), 256, 0, st>>>(n, idx, G, out);
+}
+
+void CsrDev::upload_pattern(const CsrHost& a, cudaStream_t st) {
+  n = a.n;
+  nnz = a.nnz();
+  ptr.upload(a.ptr, st);
+  idx.upload(a.idx, st);
+  val.upload(a.val, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void csr_spmm(int n, const int64_t* ptr, const int* idx, const double* val, const double* X, int ldx, double* Y, int ldy,
+              int nr, cudaStream_t st) {
+  const int64_t tot = (int64_t)n * nr;
+  const int grid = (int)((tot + 255) / 256);
+  switch (nr) {
+    case 1: k_csr_spmm<1><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 2: k_csr_spmm<2><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 4: k_csr_spmm<4><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 8: k_csr_spmm<8><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 16: k_csr_spmm<16><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 32: k_csr_spmm<32><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    default: GENEO_CHECK(false, "csr_spmm: nr must be a power of two <= 32");
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void vec_dot(int n, const double* x, const double* y, double* out, cudaStream_t st) {
+  CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double), st));
+  k_dot<<<grid_for(n, 256, 4), 256, 0, st>>>(n, x, y, out);
+}
+void vec_dot2(int n, const double* x, const double* y, const double* z, double* out, cudaStream_t st) {
+  CUDA_CHECK(cudaMemsetAsync(out, 0, 2 * sizeof(double), st));
+  k_dot2<<<grid_for(n, 256, 4), 256, 0, st>>>(n, x, y, z, out);
+}
+void vec_axpy(int n, double a, const double* x, double* y, cudaStream_t st) { k_axpy<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, y); }
+void vec_aypx(int n, double a, const double* x, double* y, cudaStream_t st) { k_axpby<<<grid_for(n, 256), 256, 0, st>>>(n, 1., x, a, y); }
+void vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st) { k_axpby<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, b, y); }
+void vec_cg_update(int n, double a, const double* p, const double* w, double* x, double* r, cudaStream_t st) {
+  k_cg_update<<<grid_for(n, 256), 256, 0, st>>>(n, a, p, w, x, r);
+}
+void vec_scale(int n, double a, double* x, cudaStream_t st) { k_scale<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); }
+void vec_set(int n, double a, double* x, cudaStream_t st) { k_set<<<grid_for(n, 256), 256, 0, st>>>(n, a, 0., x); }
+void vec_iota(int n, double first, double* x, cudaStream_t st) { k_set<<<grid_for(n, 256), 256, 0, st>>>(n, first, 1., x); }
+void vec_mdot(int n, int nv, const double* V, int64_t ldv, const double* w, double* out, cudaStream_t st) {
+  CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)((nv + 3) / 4 * 4), st));
+  k_mdot<<<grid_for(n, 256, 4), 256, 0, st>>>(n, nv, V, ldv, w, out);
+}
+void vec_maxpy(int n, int nv, const double* V, int64_t ldv, const double* coef, double* w, cudaStream_t st) {
+  k_maxpy<<<grid_for(n, 256), 256, 0, st>>>(n, nv, V, ldv, coef, w);
+}
+void gather_rows(int64_t cnt, const int* idx, const double* scale, const double* x, double* out, cudaStream_t st) {
+  if (cnt) k_gather<<<grid_for(cnt, 256), 256, 0, st>>>(cnt, idx, scale, x, out);
+}
+void pull_sum(int n, const int64_t* ptr, const int64_t* pos, const double* t, double* y, bool accumulate, cudaStream_t st) {
+  k_pull_sum<<<grid_for(n, 256), 256, 0, st>>>(n, ptr, pos, t, y, accumulate);
+}
+void ts_gram(int n, const double* X, int ldx, int p, const double* Y, int ldy, int q, double* G, int ldg, cudaStream_t st) {
+  const int tp = (p + 31) / 32, tq = (q + 31) / 32;
+  int nz = std::max(1, std::min((n + 4 * GR - 1) / (4 * GR), std::max(1, NSM * 4 / (tp * tq))));
+  int rowsPerCta = ((n + nz - 1) / nz + GR - 1) / GR * GR;
+  nz = (n + rowsPerCta - 1) / rowsPerCta;
+  dim3 grid(tp, tq, nz);
+  k_ts_gram<<<grid, 256, 0, st>>>(n, X, ldx, p, Y, ldy, q, G, ldg, rowsPerCta);
+  CUDA_CHECK(cudaGetLastError());
+}
+void ts_update(int n, const double* Q, int ldq, int p, const double* C, int ldc, int q, double* W, int ldw, double alpha,
+               double beta, cudaStream_t st) {
+  for (int j0 = 0; j0 < q; j0 += 32) {  // column chunks of <= 32 keep the C tile (64 x 32 doubles) in 16 KB of smem
+    const int qc = std::min(32, q - j0);
+    int qpad = 1;
+    while (qpad < qc) qpad <<= 1;
+    const int rowsPerCta = 256 / qpad;
+    const int grid = (n + rowsPerCta - 1) / rowsPerCta;
+    k_ts_update<<<grid, 256, 64 * qpad * sizeof(double), st>>>(n, Q, ldq, p, C + j0, ldc, qc, W + j0, ldw, alpha, beta, qpad);
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+void zt_x(int n, int nev, const double* Z, int ldz, const double* x, double* w, cudaStream_t st) {
+  if (nev == 0) return;
+  int nevPad = 1;
+  while (nevPad < nev) nevPad <<= 1;
+  nevPad = std::min(nevPad, 256);
+  const int rstride = 256 / nevPad;
+  const int grid = std::max(1, std::min((n + rstride * 8 - 1) / (rstride * 8), NSM * 4));
+  k_zt_x<<<grid, 256, 0, st>>>(n, nev, Z, ldz, x, w);
+  CUDA_CHECK(cudaGetLastError());
+}
+void z_w_add(int n, int nev, const double* Z, int ldz, const double* w, const double* d, double* t, cudaStream_t st) {
+  const int grid = std::max(1, std::min((n + 7) / 8, NSM * 8));
+  k_z_w_add<<<grid, 256, 0, st>>>(n, nev, Z, ldz, w, d, t);
+  CUDA_CHECK(cudaGetLastError());
+}
+void dense_gemv(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t st) {
+  if (m == 0) return;
+  k_dense_gemv<<<(m + 7) / 8, 256, 0, st>>>(m, n, A, lda, x, y);
+  CUDA_CHECK(cudaGetLastError());
+}
+void vec_pointwise(int64_t n, const double* d, double* x, cudaStream_t st) { k_pointwise<<<grid_for(n, 256), 256, 0, st>>>(n, d, x); }
+void rows_scale(int n, int ld, const double* d, double* Z, cudaStream_t st) {
+  const int64_t tot = (int64_t)n * ld;
+  if (tot) k_rows_scale<<<grid_for(tot, 256), 256, 0, st>>>(tot, ld, d, Z);
+}
+void csr_scale_sym(int n, const int64_t* ptr, const int* idx, const double* val, const double* d, double* out, cudaStream_t st) {
+  k_csr_scale_sym<<<grid_for(n, 256), 256, 0, st>>>(n, ptr, idx, val, d, out);
+}
+void vals_axpby(int64_t nnz, const double* a, double tau, const double* b, double* out, cudaStream_t st) {
+  k_vals_axpby<<<grid_for(nnz, 256), 256, 0, st>>>(nnz, a, tau, b, out);
+}
+void csr_sum_all(int64_t nnz, const double* val, double* out, cudaStream_t st) {
+  CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double), st));
+  k_sum_all<<<grid_for(nnz, 256, 4), 256, 0, st>>>(nnz, val, out);
+}
+
+}  // namespace geneo

@@ -1,0 +1,70 @@
+// ldlt.hpp -- device-resident block LDL^T multifrontal factorization + solves (replaces MUMPS LU/Cholesky:
+// reference call sites src/geneo.cpp:94-124, 452-500, 766-776, 1044-1066; solve phase :1995, :1486-1493).
+#pragma once
+#include <memory>
+#include "common.hpp"
+#include "symbolic.hpp"
+
+namespace geneo {
+
+struct FrontDev {  // device copy of what the kernels need from symbolic.hpp:Front
+  int64_t lOff, uOff, wOff, rowOff, relOff;
+  int k, h, parent, nchild;
+};
+
+struct WorkItem { int f, a, b; };
+
+// Pattern-level object: symbolic analysis + device work lists.  Shared by every numeric factorization that uses
+// the same sparsity pattern (A_dir, A_neu expanded to the A_dir pattern, A_neu - tau*B).
+class LdltPlan {
+ public:
+  LdltPlan(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt);
+  explicit LdltPlan(Symbolic&& s);  // symbolic analysis done elsewhere (e.g. on a host worker thread)
+  Symbolic sym;
+  // device-resident schedule
+  DevBuf<FrontDev> dFronts;
+  DevBuf<int> dRowIdx, dRel;
+  DevBuf<int64_t> dAsmSrc, dAsmDst;
+  DevBuf<WorkItem> dItems;  // all item lists, concatenated
+  struct Range { int64_t off = 0; int cnt = 0; };
+  std::vector<Range> eaddItems, diagItems, copyItems, panelItems, schurItems;  // per level (factor)
+  std::vector<Range> fwdItems, bwdItems;                                       // per level (solve)
+  Range dsolveItems;                                                           // all fronts (diagonal solve)
+  std::vector<int64_t> levelU;                                                 // doubles of update arena used per level
+  DevBuf<int> dPerm;                                                           // new -> old
+  size_t plan_bytes() const;
+ private:
+  void build_device();
+ public:
+};
+
+struct FactorStats { int neg = 0, perturbed = 0; double seconds = 0.; };
+
+// Shared scratch for numeric factorizations (two ping-pong update arenas + the per-level panel scratch).
+struct LdltWorkspace {
+  DevBuf<double> u0, u1, w;
+  DevBuf<int> counters;  // [0] negative pivots, [1] perturbed pivots
+  void ensure(const Symbolic& s);
+};
+
+class LdltFactor {
+ public:
+  explicit LdltFactor(std::shared_ptr<LdltPlan> plan) : plan_(plan) {}
+  // vals: device array aligned with the plan's input CSR pattern.  pivTol: |pivot| below it is replaced by +-pivTol.
+  FactorStats factorize(const double* dVals, double pivTol, LdltWorkspace& ws, cudaStream_t st);
+  // Solve in the PERMUTED ordering: X (n x ldx row-major block, columns j0..j0+nr-1) is overwritten by the forward
+  // sweep, the result lands in Y (same layout).  nr in {1,2,4,8}.
+  void solve_permuted(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const;
+  const LdltPlan& plan() const { return *plan_; }
+  std::shared_ptr<LdltPlan> plan_ptr() const { return plan_; }
+  DevBuf<double> L;
+  void release() { L.release(); }
+ private:
+  std::shared_ptr<LdltPlan> plan_;
+};
+
+// DGEMM self-test hooks (microbenchmarks / parity tests of the DMMA tile kernel).
+void dgemm_nt_device(int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                     int mode /*0: C=AB^T, 1: C-=AB^T*/, cudaStream_t st);
+
+}  // namespace geneo

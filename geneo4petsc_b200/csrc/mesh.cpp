@@ -1,0 +1,431 @@
+// mesh.cpp -- see mesh.hpp.  Host only.
+#include "mesh.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <set>
+#include <sstream>
+#include <thread>
+
+namespace geneo {
+
+void Mesh::finalize() {
+  const int ne = nbElem();
+  matPtr.assign(ne + 1, 0);
+  for (int e = 0; e < ne; e++) {
+    int64_t k = elemPtr[e + 1] - elemPtr[e];
+    matPtr[e + 1] = matPtr[e] + k * k;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generators
+// ---------------------------------------------------------------------------------------------------------------
+int parse_gen_args(const std::string& args, GridGenOptions& o) {
+  std::stringstream ss(args);
+  while (ss) {
+    std::string opt;
+    ss >> opt;
+    if (opt == "--size") { ss >> o.size; if (!ss) return 1; }
+    if (opt == "--weakScaling") { ss >> o.weakScaling; if (!ss) return 1; }
+    if (opt == "--dim") { ss >> o.dim; if (!ss || o.dim < 1 || o.dim > 3) return 1; }
+    if (opt == "--inpEps") { ss >> o.inpEps; if (!ss) return 1; }
+    if (opt == "--kappa") {
+      ss >> o.kappaMax; if (!ss || o.kappaMax < 1.) return 1;
+      ss >> o.kappaInterp; if (!ss) return 1;
+      if (o.kappaInterp != "quad" && o.kappaInterp != "lin" && o.kappaInterp != "minmax") return 1;
+    }
+    if (opt == "--lbd") { ss >> o.lbd; if (!ss) return 1; }
+    if (opt == "--dt") { ss >> o.dt; if (!ss) return 1; }
+  }
+  return 0;
+}
+
+static inline double kappa1d(int mode, double alpha, double beta, double x) {
+  switch (mode) {
+    case 1: return alpha * x * x + beta;  // quad
+    case 2: return alpha * x + beta;      // lin
+    case 3: {                             // minmax: a layer of alpha in the middle third
+      double k = 1.;
+      if (x >= beta) k = alpha;
+      if (x >= 2. * beta) k = 1.;
+      return k;
+    }
+    default: return 1.;
+  }
+}
+
+void generate_grid(const GridGenOptions& o, Mesh& m) {
+  int n = 0;  // grid edge, with the reference's float truncation (laplacian.cpp:101-105)
+  if (o.dim == 1) n = o.size * o.weakScaling;
+  if (o.dim == 2) n = (int)std::sqrt((double)(o.size * o.size * o.weakScaling));
+  if (o.dim == 3) n = (int)std::cbrt((double)(o.size * o.size * o.size * o.weakScaling));
+  const int n1 = n, n2 = (o.dim >= 2) ? n : 1, n3 = (o.dim >= 3) ? n : 1;
+  int mode = 0;
+  double alpha = 0., beta = 1.;
+  const double xMax = (double)(n - 1);
+  if (o.kappaInterp == "quad") { mode = 1; alpha = (o.kappaMax - beta) / (xMax * xMax); }
+  else if (o.kappaInterp == "lin") { mode = 2; alpha = (o.kappaMax - beta) / xMax; }
+  else if (o.kappaInterp == "minmax") { mode = 3; alpha = o.kappaMax; beta = xMax / 3.; }
+
+  const int64_t npts = (int64_t)n1 * n2 * n3;
+  GENEO_CHECK(npts < (int64_t)2147483647, "grid too large for 32-bit node ids");
+  m.nbNode = (int)npts;
+  m.elemPtr.clear(); m.elemIdx.clear(); m.matVal.clear();
+  m.elemPtr.reserve(npts * (o.dim + 0) + n1 * n2 + 1);
+  m.elemIdx.reserve(npts * 2 * o.dim);
+  m.matVal.reserve(npts * 4 * o.dim);
+  m.elemPtr.push_back(0);
+  std::vector<double> k1(n1), k2(n2), k3(n3);
+  for (int i = 0; i < n1; i++) k1[i] = kappa1d(mode, alpha, beta, (double)i);
+  for (int i = 0; i < n2; i++) k2[i] = kappa1d(mode, alpha, beta, (double)i);
+  for (int i = 0; i < n3; i++) k3[i] = kappa1d(mode, alpha, beta, (double)i);
+
+  auto add = [&](int c, int nb, double kappa) {
+    double dg = (1. + o.inpEps), og = -1.;
+    if (nb >= 0) {
+      // transform(elemMat *= kappa) then (heat) lbd*lap + inertia/dt -- same operation order as the reference
+      double d = dg * kappa, f = og * kappa;
+      if (o.heat) { d = o.lbd * d + (1. / 3.) / o.dt; f = o.lbd * f + (1. / 6.) / o.dt; }
+      m.elemIdx.push_back(c); m.elemIdx.push_back(nb);
+      m.matVal.push_back(d); m.matVal.push_back(f); m.matVal.push_back(f); m.matVal.push_back(d);
+    } else {
+      double d = dg * kappa;
+      if (o.heat) d = o.lbd * d + (1. / 3.) / o.dt;
+      m.elemIdx.push_back(c);
+      m.matVal.push_back(d);
+    }
+    m.elemPtr.push_back((int64_t)m.elemIdx.size());
+  };
+  for (int d3 = 0; d3 < n3; d3++)
+    for (int d2 = 0; d2 < n2; d2++)
+      for (int d1 = 0; d1 < n1; d1++) {
+        const int c = d1 + n1 * d2 + n1 * n2 * d3;
+        const double kappa = k1[d1] * k2[d2] * k3[d3];
+        if (o.dim == 1 && d1 == 0) add(c, -1, kappa);
+        if (d1 + 1 < n1) add(c, c + 1, kappa);
+        if (o.dim == 2 && d2 == 0) add(c, -1, kappa);
+        if (d2 + 1 < n2) add(c, c + n1, kappa);
+        if (o.dim == 3 && d3 == 0) add(c, -1, kappa);
+        if (d3 + 1 < n3) add(c, c + n1 * n2, kappa);
+      }
+  m.finalize();
+}
+
+int read_input_file(const std::string& path, double inpEps, Mesh& m) {
+  std::ifstream inp(path);
+  if (!inp) { std::cerr << "Error: can not open " << path << std::endl; return 1; }
+  m = Mesh();
+  m.elemPtr.push_back(0);
+  std::set<int> nodes;
+  std::string line;
+  while (std::getline(inp, line)) {
+    size_t s = 0;
+    while (s < line.size() && isspace((unsigned char)line[s])) s++;
+    line = line.substr(s);
+    if (line.empty() || line[0] == '%' || line[0] == '#') continue;
+    std::stringstream ss(line);
+    std::string tok;
+    bool fillDof = true;
+    std::vector<int> dofs;
+    std::vector<double> vals;
+    while (ss >> tok) {
+      if (tok == "-") { fillDof = false; continue; }
+      std::stringstream ts(tok);
+      if (fillDof) { int d = 0; ts >> d; if (ts) dofs.push_back(d); }
+      else { double a = 0.; ts >> a; if (ts) vals.push_back(a); }
+    }
+    const int nd = (int)dofs.size();
+    if (vals.empty())
+      for (int i = 0; i < nd; i++)
+        for (int j = 0; j < nd; j++) vals.push_back(i == j ? 1. + inpEps : -1. / ((double)(nd - 1)));
+    if ((int)vals.size() != nd * nd) { std::cerr << "Error: bad matrix (" << m.nbElem() + 1 << ") in file " << std::endl; return 1; }
+    for (int d : dofs) { m.elemIdx.push_back(d); nodes.insert(d); }
+    m.elemPtr.push_back((int64_t)m.elemIdx.size());
+    m.matVal.insert(m.matVal.end(), vals.begin(), vals.end());
+  }
+  if (nodes.empty()) { std::cerr << "Error: empty input" << std::endl; return 1; }
+  m.nbNode = (int)nodes.size();
+  if (*nodes.rbegin() + 1 != m.nbNode || *nodes.begin() < 0) {
+    std::cerr << "Error: bad node set (" << *nodes.rbegin() + 1 << "/" << m.nbNode << ") in file " << std::endl;
+    return 1;
+  }
+  m.finalize();
+  return 0;
+}
+
+int read_rhs_file(const std::string& path, int n, std::vector<double>& b) {
+  std::ifstream inp(path);
+  if (!inp) { std::cerr << "Error: can not open " << path << std::endl; return 1; }
+  b.assign(n, 0.);
+  std::string line;
+  while (std::getline(inp, line)) {
+    size_t s = 0;
+    while (s < line.size() && isspace((unsigned char)line[s])) s++;
+    line = line.substr(s);
+    if (line.empty() || line[0] == '%' || line[0] == '#') continue;
+    std::stringstream ss(line);
+    long idx; double v;
+    ss >> idx;
+    if (!ss) { std::cerr << "Error: can not read " << path << std::endl; return 1; }
+    ss >> v;
+    if (!ss) v = 1.;
+    if (idx < 0 || idx >= n) { std::cerr << "Error: bad index in " << path << std::endl; return 1; }
+    b[idx] = v;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// METIS (CUDA-toolkit libmetis_static.a: 64-bit idx_t, 32-bit real_t, no header shipped)
+// ---------------------------------------------------------------------------------------------------------------
+typedef int64_t midx_t;
+extern "C" {
+int METIS_SetDefaultOptions(midx_t* options);
+int METIS_PartMeshDual(midx_t* ne, midx_t* nn, midx_t* eptr, midx_t* eind, midx_t* vwgt, midx_t* vsize, midx_t* ncommon,
+                       midx_t* nparts, float* tpwgts, midx_t* options, midx_t* objval, midx_t* epart, midx_t* npart);
+int METIS_PartMeshNodal(midx_t* ne, midx_t* nn, midx_t* eptr, midx_t* eind, midx_t* vwgt, midx_t* vsize, midx_t* nparts,
+                        float* tpwgts, midx_t* options, midx_t* objval, midx_t* epart, midx_t* npart);
+}
+
+int metis_partition(const Mesh& m, int nbPart, bool dual, std::vector<int>& elemPart, std::vector<int>& nodePart) {
+  const int ne = m.nbElem(), nn = m.nbNode;
+  elemPart.assign(ne, 0);
+  nodePart.assign(nn, 0);
+  if (nbPart == 1) return 0;  // the reference does not call METIS for one partition
+  midx_t options[40];
+  METIS_SetDefaultOptions(options);
+  options[10] = 1;  // METIS_OPTION_MINCONN
+  options[0] = 1;   // METIS_OPTION_PTYPE  = METIS_PTYPE_KWAY
+  options[1] = 0;   // METIS_OPTION_OBJTYPE = METIS_OBJTYPE_CUT
+  midx_t obj = 0, ncommon = 1, NE = ne, NN = nn, NP = nbPart;
+  std::vector<midx_t> eptr(m.elemPtr.begin(), m.elemPtr.end()), eind(m.elemIdx.begin(), m.elemIdx.end());
+  std::vector<midx_t> ep(ne), np(nn);
+  int rc;
+  if (dual) rc = METIS_PartMeshDual(&NE, &NN, eptr.data(), eind.data(), NULL, NULL, &ncommon, &NP, NULL, options, &obj, ep.data(), np.data());
+  else      rc = METIS_PartMeshNodal(&NE, &NN, eptr.data(), eind.data(), NULL, NULL, &NP, NULL, options, &obj, ep.data(), np.data());
+  if (rc != 1) { std::cerr << "Error: METIS partition KO" << std::endl; return 1; }
+  for (int e = 0; e < ne; e++) elemPart[e] = (int)ep[e];
+  for (int i = 0; i < nn; i++) nodePart[i] = (int)np[i];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Decomposition
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+// Sum-duplicate COO -> CSR with sorted columns.  rows/cols are local indices < n.
+void coo_to_csr(int n, std::vector<int>& rows, std::vector<int>& cols, std::vector<double>& vals, CsrHost& a) {
+  const size_t nz = rows.size();
+  std::vector<int64_t> cnt(n + 1, 0);
+  for (size_t t = 0; t < nz; t++) cnt[rows[t] + 1]++;
+  for (int i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+  std::vector<int> c2(nz);
+  std::vector<double> v2(nz);
+  {
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (size_t t = 0; t < nz; t++) {
+      int64_t q = pos[rows[t]]++;
+      c2[q] = cols[t];
+      v2[q] = vals[t];
+    }
+  }
+  a.n = a.ncols = n;
+  a.ptr.assign(n + 1, 0);
+  a.idx.clear(); a.val.clear();
+  a.idx.reserve(nz / 2 + n); a.val.reserve(nz / 2 + n);
+  std::vector<std::pair<int, double>> tmp;
+  for (int i = 0; i < n; i++) {
+    tmp.clear();
+    for (int64_t q = cnt[i]; q < cnt[i + 1]; q++) tmp.emplace_back(c2[q], v2[q]);
+    std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, double>& x, const std::pair<int, double>& y) { return x.first < y.first; });
+    for (size_t k = 0; k < tmp.size();) {
+      int c = tmp[k].first;
+      double s = 0.;
+      while (k < tmp.size() && tmp[k].first == c) { s += tmp[k].second; k++; }  // insertion order, like ADD_VALUES
+      a.idx.push_back(c);
+      a.val.push_back(s);
+    }
+    a.ptr[i + 1] = (int64_t)a.idx.size();
+  }
+}
+
+}  // namespace
+
+void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, const std::vector<int>& nodePart,
+               bool dual, int overlap, const std::vector<char>& owner, Decomposition& d) {
+  const int ne = m.nbElem(), nn = m.nbNode;
+  d = Decomposition();
+  d.nbPart = nbPart; d.nbNode = nn; d.nbElem = ne;
+  d.nodeMult.assign(nn, 0);
+  d.elemMult.assign(ne, 0);
+  d.subs.resize(nbPart);
+
+  // inverse topology node -> elements (always needed here: nodal mode, overlap and aDir use it)
+  std::vector<int64_t> n2ePtr(nn + 1, 0);
+  for (size_t t = 0; t < m.elemIdx.size(); t++) n2ePtr[m.elemIdx[t] + 1]++;
+  for (int i = 0; i < nn; i++) n2ePtr[i + 1] += n2ePtr[i];
+  std::vector<int> n2e(m.elemIdx.size());
+  {
+    std::vector<int64_t> pos(n2ePtr.begin(), n2ePtr.end() - 1);
+    for (int e = 0; e < ne; e++)
+      for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) n2e[pos[m.elemIdx[t]]++] = e;
+  }
+
+  // -- element / node sets -----------------------------------------------------------------------------------------
+  std::vector<std::vector<int>> partElems(nbPart);
+  if (dual) {
+    for (int e = 0; e < ne; e++) {
+      GENEO_CHECK(elemPart[e] >= 0 && elemPart[e] < nbPart, "bad element partition");
+      partElems[elemPart[e]].push_back(e);
+    }
+  } else {
+    std::vector<std::vector<int>> partNodes(nbPart);
+    for (int i = 0; i < nn; i++) {
+      GENEO_CHECK(nodePart[i] >= 0 && nodePart[i] < nbPart, "bad node partition");
+      partNodes[nodePart[i]].push_back(i);
+    }
+    std::vector<int> stamp(ne, -1);
+    for (int p = 0; p < nbPart; p++)  // an element belongs to p if one of its nodes does
+      for (int g : partNodes[p])
+        for (int64_t t = n2ePtr[g]; t < n2ePtr[g + 1]; t++) {
+          int e = n2e[t];
+          if (stamp[e] != p) { stamp[e] = p; partElems[p].push_back(e); }
+        }
+  }
+  {
+    std::vector<int> estamp(ne, -1), nstamp(nn, -1);
+    for (int p = 0; p < nbPart; p++) {
+      std::vector<int>& el = partElems[p];
+      for (int e : el) estamp[e] = p;
+      size_t layerBegin = 0;
+      for (int l = 0; l < overlap; l++) {  // one layer = every element sharing a node with the current set
+        // (the reference rescans the whole set each time; scanning only the last layer + first pass is equivalent
+        //  because older elements' neighbours were already added)
+        size_t cur = el.size();
+        size_t from = (l == 0) ? 0 : layerBegin;
+        for (size_t q = from; q < cur; q++) {
+          int e = el[q];
+          for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) {
+            int g = m.elemIdx[t];
+            for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
+              int e2 = n2e[u];
+              if (estamp[e2] != p) { estamp[e2] = p; el.push_back(e2); }
+            }
+          }
+        }
+        layerBegin = cur;
+      }
+      std::sort(el.begin(), el.end());
+      Subdomain& s = d.subs[p];
+      s.id = p;
+      s.elems = el;
+      for (int e : el) {
+        d.elemMult[e]++;
+        for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) {
+          int g = m.elemIdx[t];
+          if (nstamp[g] != p) { nstamp[g] = p; s.nodes.push_back(g); }
+        }
+      }
+      std::sort(s.nodes.begin(), s.nodes.end());
+      for (int g : s.nodes) d.nodeMult[g]++;
+      std::vector<int>().swap(partElems[p]);
+    }
+  }
+
+  // -- multiplicities + intersections (local indices, ascending) -----------------------------------------------------
+  std::vector<int64_t> n2dPtr(nn + 1, 0);
+  for (int i = 0; i < nn; i++) n2dPtr[i + 1] = n2dPtr[i] + d.nodeMult[i];
+  std::vector<int> n2d(n2dPtr[nn]);
+  {
+    std::vector<int64_t> pos(n2dPtr.begin(), n2dPtr.end() - 1);
+    for (int p = 0; p < nbPart; p++)
+      for (int g : d.subs[p].nodes) n2d[pos[g]++] = p;
+  }
+  for (int p = 0; p < nbPart; p++) {
+    Subdomain& s = d.subs[p];
+    const int nl = (int)s.nodes.size();
+    s.mult.resize(nl);
+    s.intersect.assign(nbPart, std::vector<int>());
+    for (int l = 0; l < nl; l++) {
+      int g = s.nodes[l];
+      s.mult[l] = d.nodeMult[g];
+      if (d.nodeMult[g] > 1)
+        for (int64_t t = n2dPtr[g]; t < n2dPtr[g + 1]; t++)
+          if (n2d[t] != p) s.intersect[n2d[t]].push_back(l);
+    }
+  }
+
+  // -- local matrices for owned subdomains ---------------------------------------------------------------------------
+  std::vector<int> mine;
+  for (int p = 0; p < nbPart; p++)
+    if (owner.empty() || owner[p]) mine.push_back(p);
+  unsigned nthreads = std::max(1u, std::min((unsigned)mine.size(), std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  std::vector<std::string> errs(nthreads);
+  for (unsigned tid = 0; tid < nthreads; tid++) {
+    pool.emplace_back([&, tid]() {
+      try {
+        std::vector<int> g2l(nn, -1), estamp(ne, -1);
+        for (size_t w = tid; w < mine.size(); w += nthreads) {
+          const int p = mine[w];
+          Subdomain& s = d.subs[p];
+          const int nl = (int)s.nodes.size();
+          for (int l = 0; l < nl; l++) g2l[s.nodes[l]] = l;
+          std::vector<int> rows, cols;
+          std::vector<double> vals;
+          // Neumann: own elements weighted by 1/elemMult (buildDomain :473-476, fillALoc :688-708)
+          size_t cap = 0;
+          for (int e : s.elems) { int64_t k = m.elemPtr[e + 1] - m.elemPtr[e]; cap += (size_t)(k * k); }
+          rows.reserve(cap); cols.reserve(cap); vals.reserve(cap);
+          for (int e : s.elems) {
+            const int64_t b = m.elemPtr[e];
+            const int k = (int)(m.elemPtr[e + 1] - b);
+            const double w8 = 1. / ((double)d.elemMult[e]);
+            const double* K = &m.matVal[m.matPtr[e]];
+            for (int i = 0; i < k; i++)
+              for (int j = 0; j < k; j++) {
+                rows.push_back(g2l[m.elemIdx[b + i]]);
+                cols.push_back(g2l[m.elemIdx[b + j]]);
+                vals.push_back(K[i * k + j] * w8);
+              }
+          }
+          coo_to_csr(nl, rows, cols, vals, s.aNeu);
+          // Dirichlet R A R^T: every element touching the subdomain, restricted to its nodes, full weight
+          rows.clear(); cols.clear(); vals.clear();
+          for (int l = 0; l < nl; l++) {
+            const int g = s.nodes[l];
+            for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
+              const int e = n2e[u];
+              if (estamp[e] == p) continue;
+              estamp[e] = p;
+              const int64_t b = m.elemPtr[e];
+              const int k = (int)(m.elemPtr[e + 1] - b);
+              const double* K = &m.matVal[m.matPtr[e]];
+              for (int i = 0; i < k; i++) {
+                const int li = g2l[m.elemIdx[b + i]];
+                if (li < 0) continue;
+                for (int j = 0; j < k; j++) {
+                  const int lj = g2l[m.elemIdx[b + j]];
+                  if (lj < 0) continue;
+                  rows.push_back(li); cols.push_back(lj); vals.push_back(K[i * k + j]);
+                }
+              }
+            }
+          }
+          coo_to_csr(nl, rows, cols, vals, s.aDir);
+          for (int l = 0; l < nl; l++) g2l[s.nodes[l]] = -1;
+        }
+      } catch (std::exception& ex) { errs[tid] = ex.what(); }
+    });
+  }
+  for (auto& t : pool) t.join();
+  for (auto& e : errs) GENEO_CHECK(e.empty(), e);
+  d.nnzNeuTotal = 0;
+  for (int p : mine) d.nnzNeuTotal += d.subs[p].aNeu.nnz();
+}
+
+}  // namespace geneo

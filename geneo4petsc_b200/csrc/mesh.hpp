@@ -1,0 +1,65 @@
+// mesh.hpp -- host side of the driver path: input mesh, METIS partition, overlapping decomposition,
+// weighted Neumann / Dirichlet local matrices.  Mirrors (re-designed, not translated) the driver half of the
+// reference: src/geneo4PETSc.cpp:98-194 (text input), :196-379 (decomposition), :381-445 (METIS),
+// :447-494 (element weighting), :643-715 (local matrix assembly).  All of this stays on the host.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "common.hpp"
+
+namespace geneo {
+
+// Element mesh: elements in CSR form + one dense row-major n_e x n_e matrix per element
+// (the reference's getInput() plug-in ABI, src/geneo4PETSc.cpp:81-85, flattened).
+struct Mesh {
+  int nbNode = 0;
+  std::vector<int64_t> elemPtr;  // [nbElem+1]
+  std::vector<int> elemIdx;
+  std::vector<int64_t> matPtr;   // [nbElem+1]
+  std::vector<double> matVal;
+  int nbElem() const { return (int)elemPtr.size() - 1; }
+  void finalize();               // (re)build matPtr from elemPtr
+};
+
+// Structured generators producing EXACTLY the element sequence of the reference's tst/laplacian and tst/heat
+// plug-ins (tst/laplacian/laplacian.cpp:56-188, tst/laplacian/laplacianServices.cpp:7-94, tst/heat/heat.cpp:24-261)
+// without the multimap/set bookkeeping (O(N) time and memory).
+struct GridGenOptions {
+  int dim = 3, size = 4, weakScaling = 1;
+  double inpEps = 1e-4, kappaMax = 1.0;
+  std::string kappaInterp;  // "", "lin", "quad", "minmax"
+  bool heat = false;
+  double lbd = 1.0, dt = 0.1;
+};
+int parse_gen_args(const std::string& args, GridGenOptions& o);  // same "--size S --dim D ..." grammar
+void generate_grid(const GridGenOptions& o, Mesh& m);
+int read_input_file(const std::string& path, double inpEps, Mesh& m);             // text format A
+int read_rhs_file(const std::string& path, int n, std::vector<double>& b);        // text format B
+
+// METIS_PartMeshDual / METIS_PartMeshNodal with the reference's options (MINCONN=1, KWAY, CUT, ncommon=1).
+int metis_partition(const Mesh& m, int nbPart, bool dual, std::vector<int>& elemPart, std::vector<int>& nodePart);
+
+struct Subdomain {
+  int id = 0;
+  std::vector<int> nodes;  // sorted global node ids == local numbering (rank in the sorted set)
+  std::vector<int> elems;  // sorted global element ids
+  std::vector<int> mult;   // node multiplicity, local order
+  CsrHost aNeu;            // sum_e (1/elemMult[e]) K_e
+  CsrHost aDir;            // (R A R^T): every element coupling between two nodes of the subdomain, full weight
+  std::vector<std::vector<int>> intersect;  // [q] -> local indices shared with subdomain q (ascending)
+};
+
+struct Decomposition {
+  int nbPart = 0, nbNode = 0, nbElem = 0;
+  std::vector<int> nodeMult, elemMult;
+  std::vector<Subdomain> subs;  // ALL subdomains' index sets; matrices only for the ones in `mine`
+  int64_t nnzNeuTotal = 0;      // "nnz coefs" of the INFO line (sum over all local matrices)
+};
+
+// Build node/element sets, multiplicities, intersections for every subdomain; assemble aNeu/aDir for
+// subdomains p with owner[p] == true (all when owner is empty).
+void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, const std::vector<int>& nodePart,
+               bool dual, int overlap, const std::vector<char>& owner, Decomposition& d);
+
+}  // namespace geneo

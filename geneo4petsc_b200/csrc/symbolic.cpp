@@ -1,0 +1,340 @@
+// symbolic.cpp -- see symbolic.hpp.  Host only.
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "common.hpp"
+
+namespace geneo {
+
+typedef int64_t midx_t;
+extern "C" int METIS_SetDefaultOptions(midx_t* options);
+extern "C" int METIS_NodeND(midx_t* nvtxs, midx_t* xadj, midx_t* adjncy, midx_t* vwgt, midx_t* options, midx_t* perm,
+                            midx_t* iperm);
+
+namespace {
+
+// Elimination tree of P A P^T (Liu, path compression).  Row j of the permuted matrix = row perm[j] of the input.
+void etree(int n, const int64_t* ptr, const int* idx, const std::vector<int>& perm, const std::vector<int>& iperm,
+           std::vector<int>& parent) {
+  parent.assign(n, -1);
+  std::vector<int> anc(n, -1);
+  for (int j = 0; j < n; j++) {
+    const int jo = perm[j];
+    for (int64_t t = ptr[jo]; t < ptr[jo + 1]; t++) {
+      int i = iperm[idx[t]];
+      while (i != -1 && i < j) {
+        int next = anc[i];
+        anc[i] = j;
+        if (next == -1) parent[i] = j;
+        i = next;
+      }
+    }
+  }
+}
+
+void postorder(int n, const std::vector<int>& parent, std::vector<int>& post) {
+  std::vector<int> head(n, -1), next(n, -1), stack;
+  for (int j = n - 1; j >= 0; j--)
+    if (parent[j] != -1) { next[j] = head[parent[j]]; head[parent[j]] = j; }
+  post.clear();
+  post.reserve(n);
+  stack.reserve(64);
+  for (int r = 0; r < n; r++) {
+    if (parent[r] != -1) continue;
+    stack.push_back(r);
+    while (!stack.empty()) {
+      int p = stack.back();
+      int c = head[p];
+      if (c == -1) { post.push_back(p); stack.pop_back(); }
+      else { head[p] = next[c]; stack.push_back(c); }
+    }
+  }
+}
+
+// Column counts of the Cholesky factor (Gilbert, Ng, Peyton 1994), skeleton-matrix / row-subtree leaves.
+void colcounts(int n, const int64_t* ptr, const int* idx, const std::vector<int>& perm, const std::vector<int>& iperm,
+               const std::vector<int>& parent, const std::vector<int>& post, std::vector<int>& cc) {
+  std::vector<int> first(n, -1), maxfirst(n, -1), prevleaf(n, -1), anc(n);
+  std::vector<int64_t> delta(n, 0);
+  for (int k = 0; k < n; k++) {
+    int j = post[k];
+    delta[j] = (first[j] == -1) ? 1 : 0;  // j is a leaf of the etree
+    for (; j != -1 && first[j] == -1; j = parent[j]) first[j] = k;
+  }
+  for (int i = 0; i < n; i++) anc[i] = i;
+  for (int k = 0; k < n; k++) {
+    const int j = post[k];
+    if (parent[j] != -1) delta[parent[j]]--;
+    const int jo = perm[j];
+    for (int64_t t = ptr[jo]; t < ptr[jo + 1]; t++) {
+      const int i = iperm[idx[t]];
+      if (i <= j || first[j] <= maxfirst[i]) continue;  // j is not a leaf of the i-th row subtree
+      maxfirst[i] = first[j];
+      const int jprev = prevleaf[i];
+      prevleaf[i] = j;
+      if (jprev == -1) { delta[j]++; continue; }  // first leaf
+      int q = jprev;
+      while (q != anc[q]) q = anc[q];
+      for (int s = jprev; s != q;) { int sp = anc[s]; anc[s] = q; s = sp; }
+      delta[j]++;
+      delta[q]--;  // q = least common ancestor of jprev and j
+    }
+    if (parent[j] != -1) anc[j] = parent[j];
+  }
+  for (int k = 0; k < n; k++) {  // accumulate up the tree in postorder (children before parents)
+    const int j = post[k];
+    if (parent[j] != -1) delta[parent[j]] += delta[j];
+  }
+  cc.resize(n);
+  for (int j = 0; j < n; j++) cc[j] = (int)delta[j];
+}
+
+}  // namespace
+
+void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt, Symbolic& S) {
+  S = Symbolic();
+  S.n = n;
+  S.nb = opt.nb;
+  GENEO_CHECK(n > 0, "empty matrix");
+  GENEO_CHECK(opt.nb >= 1 && opt.nb <= 128, "panel width must be in [1,128]");
+
+  // ---- 1. fill-reducing ordering ------------------------------------------------------------------------------------
+  std::vector<int> perm(n), iperm(n);
+  bool useMetis = (opt.ordering == 1 && n > 32);
+  if (useMetis) {
+    std::vector<midx_t> xadj(n + 1, 0), adj;
+    adj.reserve(ptr[n]);
+    for (int i = 0; i < n; i++) {
+      for (int64_t t = ptr[i]; t < ptr[i + 1]; t++)
+        if (idx[t] != i) adj.push_back(idx[t]);
+      xadj[i + 1] = (midx_t)adj.size();
+    }
+    if (adj.empty()) useMetis = false;
+    else {
+      midx_t nv = n, options[40];
+      METIS_SetDefaultOptions(options);
+      std::vector<midx_t> p(n), ip(n);
+      int rc = METIS_NodeND(&nv, xadj.data(), adj.data(), NULL, options, p.data(), ip.data());
+      GENEO_CHECK(rc == 1, "METIS_NodeND failed");
+      for (int i = 0; i < n; i++) { perm[i] = (int)p[i]; iperm[i] = (int)ip[i]; }
+    }
+  }
+  if (!useMetis) { std::iota(perm.begin(), perm.end(), 0); std::iota(iperm.begin(), iperm.end(), 0); }
+
+  // ---- 2. etree, postorder, column counts; relabel so that the ordering IS a postorder -----------------------------
+  std::vector<int> parent, post, cc;
+  etree(n, ptr, idx, perm, iperm, parent);
+  postorder(n, parent, post);
+  GENEO_CHECK((int)post.size() == n, "postorder failed");
+  colcounts(n, ptr, idx, perm, iperm, parent, post, cc);
+  {
+    std::vector<int> ipost(n), perm2(n), parent2(n), cc2(n);
+    for (int k = 0; k < n; k++) ipost[post[k]] = k;
+    for (int k = 0; k < n; k++) {
+      perm2[k] = perm[post[k]];
+      parent2[k] = parent[post[k]] == -1 ? -1 : ipost[parent[post[k]]];
+      cc2[k] = cc[post[k]];
+    }
+    perm.swap(perm2); parent.swap(parent2); cc.swap(cc2);
+    for (int k = 0; k < n; k++) iperm[perm[k]] = k;
+  }
+
+  // ---- 3. supernodes (maximal: same structure as the next column) + relaxed amalgamation ----------------------------
+  std::vector<int> snFirst, snK, snH;
+  for (int j = 0; j < n; j++) {
+    bool join = j > 0 && parent[j - 1] == j && cc[j] == cc[j - 1] - 1;
+    if (join) snK.back()++;
+    else { snFirst.push_back(j); snK.push_back(1); snH.push_back(cc[j]); }
+  }
+  int ns = (int)snFirst.size();
+  std::vector<int> snOf(n);
+  for (int s = 0; s < ns; s++)
+    for (int j = snFirst[s]; j < snFirst[s] + snK[s]; j++) snOf[j] = s;
+  std::vector<int> snParent(ns);
+  for (int s = 0; s < ns; s++) {
+    int last = snFirst[s] + snK[s] - 1;
+    snParent[s] = parent[last] == -1 ? -1 : snOf[parent[last]];
+  }
+  std::vector<int> alive(ns, 1);
+  if (opt.amalgamate) {
+    std::vector<int> prev(ns), mergedInto(ns, -1);
+    std::vector<double> zeros(ns, 0.);
+    for (int s = 0; s < ns; s++) prev[s] = s - 1;
+    auto rootOf = [&](int s) { while (s != -1 && mergedInto[s] != -1) s = mergedInto[s]; return s; };
+    for (int s = 0; s < ns; s++) {
+      while (true) {
+        int c = prev[s];
+        if (c < 0) break;
+        if (rootOf(snParent[c]) != s) break;  // the supernode just before s is not one of its children
+        const double kc = snK[c], hc = snH[c], ks = snK[s], hs = snH[s];
+        const double newk = kc + ks, newh = kc + hs;
+        const double z = zeros[c] + zeros[s] + kc * (newh - hc);
+        const double total = newk * newh - newk * (newk - 1.) / 2.;
+        const double frac = z / total;
+        bool merge = (newk <= 4) || (newk <= 16 && frac < 0.8) || (newk <= 48 && frac < 0.1) || (frac < 0.05);
+        if (!merge) break;
+        snFirst[s] = snFirst[c]; snK[s] = (int)newk; snH[s] = (int)newh; zeros[s] = z;
+        alive[c] = 0; mergedInto[c] = s; prev[s] = prev[c];
+      }
+    }
+    for (int s = 0; s < ns; s++)
+      if (alive[s]) snParent[s] = rootOf(snParent[s]);
+  }
+  // compact
+  std::vector<int> newId(ns, -1), fFirst, fK, fPar;
+  for (int s = 0; s < ns; s++)
+    if (alive[s]) { newId[s] = (int)fFirst.size(); fFirst.push_back(snFirst[s]); fK.push_back(snK[s]); }
+  for (int s = 0; s < ns; s++)
+    if (alive[s]) fPar.push_back(snParent[s] == -1 ? -1 : newId[snParent[s]]);
+  ns = (int)fFirst.size();
+  S.nsuper = ns;
+  for (int s = 0; s < ns; s++)
+    for (int j = fFirst[s]; j < fFirst[s] + fK[s]; j++) snOf[j] = s;
+
+  // ---- 4. row structure of every supernode (own columns, then the sorted union of A-entries and children rows) -------
+  std::vector<int64_t> snRowOff(ns + 1, 0);
+  std::vector<int>& rowIdx = S.rowIdx;
+  {
+    std::vector<int> chHead(ns, -1), chNext(ns, -1), mark(n, -1);
+    for (int s = ns - 1; s >= 0; s--)
+      if (fPar[s] != -1) { chNext[s] = chHead[fPar[s]]; chHead[fPar[s]] = s; }
+    std::vector<int> below;
+    for (int s = 0; s < ns; s++) {
+      const int c0 = fFirst[s], c1 = c0 + fK[s];
+      below.clear();
+      for (int j = c0; j < c1; j++) {
+        const int jo = perm[j];
+        for (int64_t t = ptr[jo]; t < ptr[jo + 1]; t++) {
+          const int i = iperm[idx[t]];
+          if (i >= c1 && mark[i] != s) { mark[i] = s; below.push_back(i); }
+        }
+      }
+      for (int c = chHead[s]; c != -1; c = chNext[c]) {
+        for (int64_t t = snRowOff[c] + fK[c]; t < snRowOff[c + 1]; t++) {
+          const int i = rowIdx[t];
+          if (i >= c1 && mark[i] != s) { mark[i] = s; below.push_back(i); }
+        }
+      }
+      std::sort(below.begin(), below.end());
+      for (int j = c0; j < c1; j++) rowIdx.push_back(j);
+      rowIdx.insert(rowIdx.end(), below.begin(), below.end());
+      snRowOff[s + 1] = (int64_t)rowIdx.size();
+    }
+  }
+  S.nnzRowIdx = (int64_t)rowIdx.size();
+
+  // ---- 5. cut supernodes into panels (fronts) ------------------------------------------------------------------------
+  const int NB = opt.nb;
+  std::vector<int> firstFrontOfSn(ns), lastFrontOfSn(ns);
+  S.frontOfCol.assign(n, -1);
+  for (int s = 0; s < ns; s++) {
+    const int hs = (int)(snRowOff[s + 1] - snRowOff[s]);
+    const int np = (fK[s] + NB - 1) / NB;
+    firstFrontOfSn[s] = (int)S.fronts.size();
+    for (int p = 0; p < np; p++) {
+      Front f;
+      const int off = p * NB;
+      f.col0 = fFirst[s] + off;
+      f.k = std::min(NB, fK[s] - off);
+      f.h = hs - off;
+      f.rowOff = snRowOff[s] + off;
+      f.chain = (p + 1 < np) ? 1 : 0;
+      const int id = (int)S.fronts.size();
+      for (int j = f.col0; j < f.col0 + f.k; j++) S.frontOfCol[j] = id;
+      S.fronts.push_back(f);
+    }
+    lastFrontOfSn[s] = (int)S.fronts.size() - 1;
+  }
+  const int nf = (int)S.fronts.size();
+  for (int s = 0; s < ns; s++) {
+    for (int f = firstFrontOfSn[s]; f < lastFrontOfSn[s]; f++) S.fronts[f].parent = f + 1;
+    S.fronts[lastFrontOfSn[s]].parent = (fPar[s] == -1) ? -1 : firstFrontOfSn[fPar[s]];
+  }
+  // relative indices of the last panel of every supernode into the first panel of the parent supernode
+  for (int f = 0; f < nf; f++) {
+    Front& F = S.fronts[f];
+    if (F.parent == -1 || F.chain) { if (F.parent == -1) GENEO_CHECK(F.m() == 0, "root front with update rows"); continue; }
+    const Front& P = S.fronts[F.parent];
+    F.relOff = (int64_t)S.rel.size();
+    const int* mine = &rowIdx[F.rowOff + F.k];
+    const int* par = &rowIdx[P.rowOff];
+    int q = 0;
+    for (int i = 0; i < F.m(); i++) {
+      while (q < P.h && par[q] < mine[i]) q++;
+      GENEO_CHECK(q < P.h && par[q] == mine[i], "symbolic: child row missing in parent front");
+      S.rel.push_back(q);
+    }
+  }
+  for (int f = 0; f < nf; f++)
+    if (S.fronts[f].parent != -1) S.fronts[S.fronts[f].parent].nchild++;
+
+  // ---- 6. top-down levels, arenas, offsets ---------------------------------------------------------------------------
+  std::vector<int> depth(nf, 0);
+  int maxDepth = 0;
+  for (int f = nf - 1; f >= 0; f--) {
+    if (S.fronts[f].parent != -1) depth[f] = depth[S.fronts[f].parent] + 1;
+    maxDepth = std::max(maxDepth, depth[f]);
+  }
+  S.nlevels = maxDepth + 1;
+  S.levelPtr.assign(S.nlevels + 1, 0);
+  for (int f = 0; f < nf; f++) { S.fronts[f].level = maxDepth - depth[f]; S.levelPtr[S.fronts[f].level + 1]++; }
+  for (int l = 0; l < S.nlevels; l++) S.levelPtr[l + 1] += S.levelPtr[l];
+  S.levelFronts.resize(nf);
+  {
+    std::vector<int> pos(S.levelPtr.begin(), S.levelPtr.end() - 1);
+    for (int f = 0; f < nf; f++) S.levelFronts[pos[S.fronts[f].level]++] = f;
+  }
+  int64_t lOff = 0;
+  for (int f = 0; f < nf; f++) {
+    Front& F = S.fronts[f];
+    F.lOff = lOff;
+    lOff += (int64_t)F.h * F.k;
+    const double k = F.k, m = F.m();
+    S.flops += k * k * k / 3. + m * k * k + m * m * k;
+    S.maxK = std::max(S.maxK, F.k);
+    S.maxH = std::max(S.maxH, F.h);
+  }
+  S.lSize = lOff;
+  for (int l = 0; l < S.nlevels; l++) {
+    int64_t u = 0, w = 0;
+    for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
+      Front& F = S.fronts[S.levelFronts[t]];
+      const int64_t m = F.m();
+      if (m > 0) { F.uOff = u; u += m * m; F.wOff = w; w += m * F.k; }
+      u = (u + 15) & ~(int64_t)15;  // 128-byte alignment of every update matrix / scratch panel
+      w = (w + 15) & ~(int64_t)15;
+    }
+    S.uArena = std::max(S.uArena, u);
+    S.wArena = std::max(S.wArena, w);
+  }
+
+  // ---- 7. scatter map of the input values (lower triangle of P A P^T) into the panels --------------------------------
+  S.perm = perm;
+  S.iperm = iperm;
+  S.asmSrc.reserve(ptr[n] / 2 + n);
+  S.asmDst.reserve(ptr[n] / 2 + n);
+  for (int ro = 0; ro < n; ro++) {
+    const int i = iperm[ro];
+    for (int64_t t = ptr[ro]; t < ptr[ro + 1]; t++) {
+      const int j = iperm[idx[t]];
+      if (i < j) continue;  // entry (i,j) with i >= j goes to column j
+      const Front& F = S.fronts[S.frontOfCol[j]];
+      int pos;
+      if (i < F.col0 + F.k) pos = i - F.col0;
+      else {
+        const int* b = &rowIdx[F.rowOff + F.k];
+        const int* e = &rowIdx[F.rowOff + F.h];
+        const int* it = std::lower_bound(b, e, i);
+        GENEO_CHECK(it != e && *it == i, "symbolic: matrix entry outside the predicted structure");
+        pos = F.k + (int)(it - b);
+      }
+      S.asmSrc.push_back(t);
+      S.asmDst.push_back(F.lOff + pos + (int64_t)(j - F.col0) * F.h);
+    }
+  }
+}
+
+}  // namespace geneo

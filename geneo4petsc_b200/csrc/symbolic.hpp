@@ -1,0 +1,69 @@
+// symbolic.hpp -- host symbolic analysis for the block LDL^T multifrontal solver that replaces MUMPS
+// (reference call sites: src/geneo.cpp:94-124 directLocalSolve, :452-500 getInertia, :746-780 buildEigenSolver).
+//
+// Design (B200-first, see DESIGN.md "Sparse LDL^T"):
+//   * fill-reducing ordering: METIS NodeND on the host;
+//   * elimination tree, postorder, Gilbert-Ng-Peyton column counts, supernodes with relaxed amalgamation;
+//   * every supernode is cut into PANELS ("fronts") of at most NB pivot columns, chained in the assembly tree, so that
+//     each front needs exactly one dense NBxNB pivot-block inversion, one panel product and one Schur GEMM;
+//   * fronts are levelled top-down (level = height - depth): a child is always exactly one level below its parent, so
+//     update matrices live in two ping-pong arenas and every level is ONE batched launch per kernel;
+//   * the factor is stored as block LDL^T:  panel f (h x k, column-major, ld = h) holds D_f^{-1} (k x k, full) on top
+//     of the unit-lower block L21 = F21 D_f^{-1} (m x k).  Triangular solves then contain no triangular kernel at all:
+//     forward = rectangular GEMV scatter, diagonal = dense k x k GEMV, backward = transposed GEMV gather.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace geneo {
+
+struct Front {
+  int col0 = 0;        // first pivot column (permuted numbering)
+  int k = 0;           // pivot columns (<= NB)
+  int h = 0;           // rows of the panel = k + m
+  int parent = -1;     // parent front, -1 for a root
+  int level = 0;       // schedule level (children are at level-1)
+  int chain = 0;       // 1 if the parent is the next panel of the same supernode (identity relative indices)
+  int nchild = 0;
+  int64_t rowOff = 0;  // into Symbolic::rowIdx (h entries, ascending, first k = own columns)
+  int64_t lOff = 0;    // into the factor value array (h*k doubles)
+  int64_t uOff = -1;   // into the ping-pong update arena of parity (level & 1); m*m doubles, ld = m
+  int64_t wOff = -1;   // into the per-level scratch holding the unscaled panel F21 (m*k doubles, ld = m)
+  int64_t relOff = -1; // into Symbolic::rel (m entries: position of update row i in the parent's row list); -1 if chain
+  int m() const { return h - k; }
+};
+
+struct Symbolic {
+  int n = 0, nb = 128;
+  std::vector<int> perm;   // new -> old
+  std::vector<int> iperm;  // old -> new
+  std::vector<Front> fronts;
+  std::vector<int> rowIdx;
+  std::vector<int> rel;
+  std::vector<int> frontOfCol;  // permuted column -> front
+  int nlevels = 0;
+  std::vector<int> levelPtr;    // [nlevels+1] into levelFronts
+  std::vector<int> levelFronts; // fronts sorted by level
+  int64_t lSize = 0;            // doubles in the factor
+  int64_t uArena = 0;           // doubles in EACH of the two update arenas
+  int64_t wArena = 0;           // doubles in the per-level panel scratch
+  // scatter of the input values into the factor array: for t < asmSrc.size(): L[asmDst[t]] = val[asmSrc[t]]
+  std::vector<int64_t> asmSrc;  // index into the input CSR value array (lower triangle entries after permutation)
+  std::vector<int64_t> asmDst;
+  // statistics
+  int nsuper = 0;
+  double flops = 0.;            // sum_f k^3/3 + m k^2 + m^2 k
+  int64_t nnzRowIdx = 0;
+  int maxK = 0, maxH = 0;
+};
+
+struct SymbolicOptions {
+  int nb = 128;        // panel width
+  int ordering = 1;    // 0 natural, 1 METIS NodeND
+  bool amalgamate = true;
+};
+
+// ptr/idx: CSR pattern of a structurally symmetric n x n matrix (both triangles; column order irrelevant).
+void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt, Symbolic& s);
+
+}  // namespace geneo

@@ -1,0 +1,123 @@
+/*
+ * geneo_b200.h -- C ABI of libgeneob200.so: a B200-native (sm_100a) drop-in for the data-parallel hot path of
+ * geneo4PETSc (two-level GenEO Schwarz preconditioner + the preconditioned Krylov iteration it drives).
+ *
+ * Plain pointers and sizes only (no PETSc, no torch, no C++ types).  Every entry point returns 0 on success and a
+ * non-zero code on failure; geneo_last_error() then holds the message (the reference returns PetscErrorCode through
+ * CHKERRQ and aborts through SETERRABT, src/geneo.cpp:74).  There is NO CPU fallback: every numeric entry point fails
+ * loudly when no CUDA device is present.  Entry points are NOT re-entrant (same as the reference).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
+ * The PETSc-facing adapter that re-exports createGenEOPC / PCGenEOSetup / initGenEOPC on top of this ABI is in
+ * geneo4petsc_b200/csrc/petsc_adapter/ (compiled only where petsc.h exists) and described in INTEGRATION.md.
+ */
+#ifndef GENEO_B200_H
+#define GENEO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct geneo_problem_s* geneo_problem_t; /* mesh + partition + decomposition (driver half, src/geneo4PETSc.cpp) */
+typedef struct geneo_pc_s* geneo_pc_t;           /* geneoContext (hdr/geneo.hpp:46-138)                                  */
+
+const char* geneo_last_error(void);
+int geneo_version(void);
+int geneo_device_count(void); /* number of visible CUDA devices (0 on a CPU-only host) */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Driver half: input, partition, decomposition            (src/geneo4PETSc.cpp:571-641 partitionAndDecompose)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int geneo_problem_create(geneo_problem_t* out);
+int geneo_problem_destroy(geneo_problem_t p);
+/* The getInput() plug-in ABI (src/geneo4PETSc.cpp:81-85, :1522-1543) flattened: elemPtr[nbElem+1], elemIdx[elemPtr[nbElem]],
+ * elemMat = the dense row-major n_e x n_e matrices of all elements back to back. */
+int geneo_problem_set_mesh(geneo_problem_t p, uint32_t nbNode, uint32_t nbElem, const uint32_t* elemPtr,
+                           const uint32_t* elemIdx, const double* elemMat);
+/* --inpLibA replacement for the reference's own generators: kind = "laplacian" (tst/laplacian/laplacian.cpp:56-188) or
+ * "heat" (tst/heat/heat.cpp:117-261); args uses the same "--size S --dim D --kappa K interp ..." grammar. */
+int geneo_problem_generate(geneo_problem_t p, const char* kind, const char* args);
+/* --inpFileA (src/geneo4PETSc.cpp:144-194). */
+int geneo_problem_read_file(geneo_problem_t p, const char* path, double inpEps);
+/* METIS partition (src/geneo4PETSc.cpp:381-445) unless elemPart/nodePart are given, then decompose (:292-379) with
+ * `overlap` layers (:238-290) and assemble the weighted Neumann matrices (:447-494, :643-715) and the Dirichlet
+ * matrices R_i A R_i^T (src/geneo.cpp:1699).  nbPart replaces "mpirun -n" (src/geneo4PETSc.cpp:604). */
+int geneo_problem_decompose(geneo_problem_t p, int nbPart, int metisDual, int overlap, const int32_t* elemPart,
+                            const int32_t* nodePart);
+int geneo_problem_sizes(geneo_problem_t p, int64_t* nbNode, int64_t* nbElem, int64_t* nbPart, int64_t* nnzNeuTotal);
+int geneo_problem_get_mesh(geneo_problem_t p, int64_t* elemPtr, int32_t* elemIdx, double* elemMat); /* sizes from _mesh_sizes */
+int geneo_problem_mesh_sizes(geneo_problem_t p, int64_t* nIdx, int64_t* nMat);
+int geneo_problem_get_partition(geneo_problem_t p, int32_t* elemPart, int32_t* nodePart);
+/* subdomain s: sizes = {nbNodeLoc, nbElemLoc, nnz(A_neu), nnz(A_dir)} */
+int geneo_problem_sub_sizes(geneo_problem_t p, int s, int64_t sizes[4]);
+int geneo_problem_sub_nodes(geneo_problem_t p, int s, int32_t* nodes, int32_t* mult);
+int geneo_problem_sub_intersect(geneo_problem_t p, int s, int q, int32_t* idx, int64_t cap, int64_t* count);
+/* which = 0: A_neu (MatISGetLocalMat, src/geneo.cpp:1714), 1: A_dir (:1699) */
+int geneo_problem_sub_matrix(geneo_problem_t p, int s, int which, int64_t* ptr, int32_t* idx, double* val);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Preconditioner                                             (hdr/geneo_c.h:9-10, hdr/geneo.hpp:30-41)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int geneo_pc_create(geneo_pc_t* out);                                        /* createGenEOPC, src/geneo.cpp:2639-2728    */
+int geneo_pc_set_from_options(geneo_pc_t pc, int argc, const char* const* argv); /* setUpGenEOPCFromOptions, :2329-2514  */
+/* initGenEOPC (:2591-2632) + setUpGenEOPC (:1672-1843) for every subdomain of a decomposed problem held by this process */
+int geneo_pc_setup(geneo_pc_t pc, geneo_problem_t p);
+/* applyGenEOPC (:2051-2098).  Host buffers of length nbDof (copied in and out); x is not modified. */
+int geneo_pc_apply(geneo_pc_t pc, const double* x, double* y);
+int geneo_pc_apply_device(geneo_pc_t pc, const double* dx, double* dy);     /* same with device pointers            */
+int geneo_pc_apply_q_device(geneo_pc_t pc, const double* dx, double* dy);   /* applyQ, :1435-1542                   */
+int geneo_pc_destroy(geneo_pc_t pc);                                         /* destroyGenEOPC, :2217-2243           */
+/* geneoContext fields the driver reads (src/geneo4PETSc.cpp:928-986, 1123-1225) */
+int geneo_pc_name(geneo_pc_t pc, char* buf, int cap);                        /* gCtx->name                           */
+/* ints = {nbDof, nbPart, lvl2, hybrid, effHybrid, lvl1ORAS, offload, noSyl, estimDimE, estimMin, estimMax, realDimE,
+ *         realMin, realMax, nicolaides, nE}                                                                          */
+int geneo_pc_info(geneo_pc_t pc, int64_t ints[16], double reals[4] /* tau, gamma, optim, reserved */);
+/* timers (seconds), same order as hdr/geneo.hpp:115-123 then extras; see abi.cpp for the index list */
+int geneo_pc_timers(geneo_pc_t pc, double* t, int cap);
+/* stats = {factor bytes, factor nnz, factor flops, tri-solve algorithmic bytes per apply, apply algorithmic bytes,
+ *          SpMV algorithmic bytes, number of applies so far, sum n_i} */
+int geneo_pc_stats(geneo_pc_t pc, double stats[8]);
+int geneo_pc_sub_info(geneo_pc_t pc, int s, int64_t ints[8] /* n, nev, estim, nicolaides, eigSteps, eigDim, neg, perturbed */,
+                      double reals[2] /* tauLoc, gammaLoc */);
+int geneo_pc_sub_eigenvalues(geneo_pc_t pc, int s, double* vals, int cap, int* count);
+/* Z_s in the subdomain's natural local numbering, row-major n x nev (for parity checks of span(Z)) */
+int geneo_pc_sub_z(geneo_pc_t pc, int s, double* z);
+int geneo_pc_coarse_matrix(geneo_pc_t pc, double* einv /* nE x nE row-major, E^-1 */);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Operator and Krylov solve                                   (src/geneo4PETSc.cpp:807-835 createB, :1233-1281)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int geneo_mult(geneo_pc_t pc, const double* x, double* y);                   /* MatMult(MATIS), host buffers          */
+int geneo_mult_device(geneo_pc_t pc, const double* dx, double* dy);
+int geneo_make_rhs(geneo_pc_t pc, double* b);                                /* b = A (1,2,...,N)^T, :820-831         */
+/* KSPSolve with left preconditioning, preconditioned-norm convergence test, non-zero initial guess flagged
+ * (x0 = Q b for the efficient hybrid variants, 0 otherwise: src/geneo.cpp:1601-1607, src/geneo4PETSc.cpp:1348).
+ * ksp = "cg" | "gmres".  Host buffers.  out = {iterations, reason (PETSc KSPConvergedReason values), nb history} */
+int geneo_ksp_solve(geneo_pc_t pc, const char* ksp, const double* b, double* x, double rtol, double atol, double dtol,
+                    int maxIt, int restart, int64_t out[3], double* rnorm, double* history, int histCap);
+int geneo_ksp_solve_device(geneo_pc_t pc, const char* ksp, const double* db, double* dx, double rtol, double atol,
+                           double dtol, int maxIt, int restart, int64_t out[3], double* rnorm, double* history, int histCap);
+const char* geneo_ksp_reason_name(int reason);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Host-only test hooks (no device needed): symbolic analysis of a CSR pattern, dense symmetric eigen-solver
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct geneo_symbolic_s* geneo_symbolic_t;
+int geneo_symbolic_create(int n, const int64_t* ptr, const int32_t* idx, int nb, int ordering, int amalgamate,
+                          geneo_symbolic_t* out);
+int geneo_symbolic_destroy(geneo_symbolic_t s);
+/* ints = {n, nfronts, nlevels, lSize, uArena, wArena, nRowIdx, nRel, nAsm, nsuper} ; reals = {flops} */
+int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[10], double reals[1]);
+/* fronts: 12 int64 per front = {col0,k,h,parent,level,chain,nchild,rowOff,lOff,uOff,wOff,relOff} */
+int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32_t* rowIdx, int32_t* rel, int64_t* asmSrc,
+                       int64_t* asmDst);
+int geneo_host_sym_eig(int n, double* a /* row-major in, eigenvectors (columns) out */, double* w);
+/* microbenchmarks on the device (first-run calibration): kind 0 = DMMA 64x64-tile GEMM C=AB^T (M=N=K=n) TFLOP/s,
+ * kind 1 = device copy GB/s over n doubles.  result[0] = rate, result[1] = max abs error vs a reference (kind 0). */
+int geneo_microbench(int kind, int n, int reps, double result[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,99 @@
+"""numpy emulation of the device numeric phase of the block LDL^T solver, driven by the EXACT host symbolic structures
+the CUDA kernels consume (geneo4petsc_b200/csrc/symbolic.cpp).  Test infrastructure: it validates scatter maps,
+relative indices, levels and arena offsets on a CPU-only box."""
+import numpy as np
+
+F_COL0, F_K, F_H, F_PARENT, F_LEVEL, F_CHAIN, F_NCHILD, F_ROWOFF, F_LOFF, F_UOFF, F_WOFF, F_RELOFF = range(12)
+
+
+def factorize(sym, vals):
+    """vals: CSR values of the input matrix (same pattern/order as given to Symbolic).  Returns (L, neg)."""
+    fr = sym.fronts
+    L = np.zeros(sym.info["lSize"])
+    L[sym.asm_dst] = vals[sym.asm_src]
+    arenas = [np.zeros(max(1, sym.info["uArena"])), np.zeros(max(1, sym.info["uArena"]))]
+    neg = 0
+    order = np.argsort(fr[:, F_LEVEL], kind="stable")
+    levels = fr[:, F_LEVEL]
+    for lvl in range(sym.info["nlevels"]):
+        cur, prev = arenas[lvl & 1], arenas[(lvl & 1) ^ 1]
+        cur[:] = 0.0
+        W = np.zeros(max(1, sym.info["wArena"]))
+        if lvl > 0:  # extend-add children (level lvl-1) into their parents
+            for c in order[levels[order] == lvl - 1]:
+                k, h, par = fr[c, F_K], fr[c, F_H], fr[c, F_PARENT]
+                m = h - k
+                if m == 0:
+                    continue
+                assert par >= 0 and fr[par, F_LEVEL] == lvl
+                pk, ph = fr[par, F_K], fr[par, F_H]
+                pm = ph - pk
+                U = prev[fr[c, F_UOFF]: fr[c, F_UOFF] + m * m].reshape(m, m, order="F")
+                rel = np.arange(m) if fr[c, F_RELOFF] < 0 else sym.rel[fr[c, F_RELOFF]: fr[c, F_RELOFF] + m]
+                Pp = L[fr[par, F_LOFF]: fr[par, F_LOFF] + ph * pk].reshape(ph, pk, order="F")
+                Up = cur[fr[par, F_UOFF]: fr[par, F_UOFF] + pm * pm].reshape(pm, pm, order="F") if pm > 0 else None
+                for cc in range(m):
+                    pc = rel[cc]
+                    rr = np.arange(cc, m)
+                    pr = rel[rr]
+                    if pc < pk:
+                        Pp[pr, pc] += U[rr, cc]
+                    else:
+                        Up[pr - pk, pc - pk] += U[rr, cc]
+        for f in order[levels[order] == lvl]:
+            k, h = fr[f, F_K], fr[f, F_H]
+            m = h - k
+            P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+            F11 = np.tril(P[:k, :k]) + np.tril(P[:k, :k], -1).T
+            # symmetric sweep (pivot signs = inertia)
+            a = F11.copy()
+            for p in range(k):
+                d = a[p, p]
+                if d < 0:
+                    neg += 1
+                col = a[:, p].copy()
+                a -= np.outer(col, col) / d
+                a[:, p] = col / d
+                a[p, :] = col / d
+                a[p, p] = -1.0 / d
+            Dinv = -a
+            P[:k, :k] = Dinv
+            if m > 0:
+                F21 = P[k:, :].copy()
+                Wf = W[fr[f, F_WOFF]: fr[f, F_WOFF] + m * k].reshape(m, k, order="F")
+                Wf[:, :] = F21
+                P[k:, :] = F21 @ Dinv
+                U = cur[fr[f, F_UOFF]: fr[f, F_UOFF] + m * m].reshape(m, m, order="F")
+                U -= P[k:, :] @ F21.T
+    return L, neg
+
+
+def solve(sym, L, b):
+    """Solve in the ORIGINAL ordering using the permuted block LDL^T factor."""
+    fr = sym.fronts
+    x = b[sym.perm].astype(float).copy()
+    order = np.argsort(fr[:, F_LEVEL], kind="stable")
+    for f in order:  # forward (levels ascending)
+        k, h = fr[f, F_K], fr[f, F_H]
+        if h == k:
+            continue
+        P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+        rows = sym.row_idx[fr[f, F_ROWOFF]: fr[f, F_ROWOFF] + h]
+        np.subtract.at(x, rows[k:], P[k:, :] @ x[rows[:k]])
+    y = np.zeros_like(x)
+    for f in range(len(fr)):
+        k, h = fr[f, F_K], fr[f, F_H]
+        P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+        rows = sym.row_idx[fr[f, F_ROWOFF]: fr[f, F_ROWOFF] + k]
+        assert np.array_equal(rows, np.arange(fr[f, F_COL0], fr[f, F_COL0] + k))
+        y[rows] = P[:k, :] @ x[rows]
+    for f in order[::-1]:  # backward (levels descending)
+        k, h = fr[f, F_K], fr[f, F_H]
+        if h == k:
+            continue
+        P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+        rows = sym.row_idx[fr[f, F_ROWOFF]: fr[f, F_ROWOFF] + h]
+        y[rows[:k]] -= P[k:, :].T @ y[rows[k:]]
+    out = np.zeros_like(y)
+    out[sym.perm] = y
+    return out

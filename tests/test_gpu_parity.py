@@ -1,0 +1,144 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/geneo_b200.h) against the oracle on the same seeded
+inputs, against the reference's tst/dummy goldens (tests/golden/dummy_goldens.json) and through size-independent
+properties.  Tolerances: partition / eigen-counts / dim E identical; eigenvalues 1e-6 relative; iteration counts +-1;
+final true relative residual <= 10 x rtol (the KSP tests the PRECONDITIONED norm, like the reference)."""
+import numpy as np
+import pytest
+
+import geneo4petsc_b200 as g
+from oracle import geneo_oracle as go
+from tests._cases import golden_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(mesh, nparts, dual=True, overlap=0):
+    return g.Problem().set_mesh(mesh.nb_node, mesh.elem_ptr, mesh.elem_idx, mesh.mat_val).decompose(nparts, dual, overlap)
+
+
+def _oracle(mesh, p, nparts, opt, dual=True, overlap=0, **kw):
+    return go.run_case(mesh, nparts, opt, dual=dual, overlap=overlap, part=p.partition(), **kw)
+
+
+def test_dmma_tile_gemm_is_correct():
+    for n in (64, 200, 513):
+        rate, err = g.microbench(0, n, 1)
+        assert err < 1e-10 * n, (n, err)
+
+
+@pytest.fixture(scope="module")
+def lap3d():
+    return go.gen_grid(3, 12, 1e-4, 2.0, "lin")
+
+
+@pytest.mark.parametrize("lvl", ["ASM,0", "ASM,1", "RAS,1", "SRAS,1", "ASM,H1", "ASM,E1", "SORAS,0", "SORAS,2", "SORAS,H2", "SORAS,E2", "ORAS,1"])
+def test_apply_matches_oracle(lap3d, lvl):
+    mesh, nparts = lap3d, 4
+    p = _problem(mesh, nparts)
+    l1, l2 = lvl.split(",")
+    tau = 0.3
+    pc = g.GeneoPC(["-geneo_lvl", lvl, "-geneo_tau", str(tau), "-geneo_optim", "0.5", "-els2_eps_tol", "1e-8"]).setup(p)
+    rep = _oracle(mesh, p, nparts, go.GenEOOptions(lvl1=l1, lvl2=l2, tau=tau, optim=0.5), ksp="cg", rtol=1e-6)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(mesh.nb_node)
+    np.testing.assert_allclose(pc.mult(x), rep.a @ x, rtol=1e-12, atol=1e-12)
+    info = pc.info()
+    if l2 != "0":
+        assert info["nE"] == rep.pc.e.shape[0]
+        for s in range(nparts):
+            si = pc.sub_info(s)
+            assert si["nev"] == rep.pc.sub[s].z.shape[1] and si["estim"] == rep.pc.sub[s].estim
+            mine, ref = np.sort(pc.sub_eigenvalues(s)), np.sort(np.array(rep.pc.sub[s].eigvals))
+            np.testing.assert_allclose(mine, ref, rtol=1e-6, atol=1e-12)
+    y, yo = pc.apply(x), rep.pc.apply(x)
+    assert np.linalg.norm(y - yo) <= 1e-6 * np.linalg.norm(yo)
+
+
+@pytest.mark.parametrize("ksp", ["cg", "gmres"])
+@pytest.mark.parametrize("lvl,dual,overlap", [("ASM,1", True, 0), ("ASM,1", False, 1), ("ASM,H1", True, 1), ("ASM,E1", True, 0),
+                                              ("SORAS,2", True, 0), ("ASM,0", True, 0)])
+def test_ksp_iterations_match_oracle(lap3d, ksp, lvl, dual, overlap):
+    if ksp == "cg" and lvl.startswith("ASM,E"):
+        pytest.skip("efficient hybrid is not symmetric: GMRES only")
+    mesh, nparts = lap3d, 4
+    p = _problem(mesh, nparts, dual, overlap)
+    l1, l2 = lvl.split(",")
+    pc = g.GeneoPC(["-geneo_lvl", lvl]).setup(p)
+    b = pc.make_rhs()
+    rep = _oracle(mesh, p, nparts, go.GenEOOptions(lvl1=l1, lvl2=l2), dual=dual, overlap=overlap, ksp=ksp, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(b, rep.b, rtol=1e-12)
+    r = pc.ksp_solve(b, ksp=ksp, rtol=1e-6, atol=1e-6)
+    assert r["reason"] > 0 and rep.ksp.converged
+    assert abs(r["its"] - rep.ksp.its) <= 1, (r["its"], rep.ksp.its)
+    true_res = np.linalg.norm(rep.a @ r["x"] - b) / np.linalg.norm(b)
+    assert true_res <= max(10 * rep.true_rel_res, 1e-5)
+    np.testing.assert_allclose(r["history"][0], rep.ksp.history[0], rtol=1e-6)
+
+
+def test_coarse_space_identities(lap3d):
+    """Q A Z = Z  and  symmetric PC (size-independent properties)."""
+    mesh, nparts = lap3d, 4
+    p = _problem(mesh, nparts)
+    pc = g.GeneoPC(["-geneo_lvl", "ASM,1", "-geneo_tau", "0.3"]).setup(p)
+    nodes0, _ = p.sub_nodes(0)
+    z0 = pc.sub_z(0)
+    v = np.zeros(mesh.nb_node)
+    v[nodes0] = z0[:, 0]
+    import torch
+    dv = torch.tensor(pc.mult(v), device="cuda")
+    out = torch.zeros_like(dv)
+    pc.apply_q_device(dv.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), v, atol=1e-8 * np.abs(v).max())
+    rng = np.random.default_rng(1)
+    a, b = rng.standard_normal(mesh.nb_node), rng.standard_normal(mesh.nb_node)
+    assert abs(a @ pc.apply(b) - b @ pc.apply(a)) <= 1e-9 * abs(a @ pc.apply(b))
+
+
+def test_dummy_goldens_through_the_cuda_path(dummy_goldens, dummy_inputs):
+    """The reference's own 8-DOF goldens: b, converged x, nnz count, PC name -- every geneo configuration."""
+    n_ok = 0
+    for name, gd in sorted(dummy_goldens["goldens"].items()):
+        cfg = golden_config(gd)
+        if cfg is None:
+            continue
+        eps = 1.0 if gd["input"] == "tridiag" else 1e-4
+        p = g.Problem().read_file(dummy_inputs / (gd["input"] + ".inp"), eps).decompose(2, cfg["dual"], cfg["overlap"])
+        argv = ["-geneo_lvl", "%s,%s" % (cfg["lvl1"], cfg["lvl2"])] + (["-geneo_cut", "10"] if gd["input"] == "tridiag" else [])
+        if cfg["offload"]:
+            argv.append("-geneo_offload")
+        pc = g.GeneoPC(argv).setup(p)
+        b = go.read_rhs_file(str(dummy_inputs / "B.inp"), 8) if gd["input"] == "identity" else pc.make_rhs()
+        np.testing.assert_allclose(b, gd["b"], atol=1e-12)
+        r = pc.ksp_solve(b, ksp="gmres", rtol=1e-12, atol=1e-12)
+        assert r["reason"] > 0, name
+        np.testing.assert_allclose(r["x"], gd["x"], atol=2e-5)
+        assert gd["info"][2].startswith("INFO: %s pc" % pc.name)
+        assert ("nnz coefs %d," % p.sizes()["nnz"]) in gd["info"][0]
+        n_ok += 1
+    assert n_ok == 80
+
+
+def test_heat_high_contrast(lap3d):
+    mesh = go.gen_grid(3, 12, 1e-4, 100.0, "minmax", heat=True)
+    p = _problem(mesh, 4)
+    pc = g.GeneoPC(["-geneo_lvl", "ASM,1"]).setup(p)
+    rep = _oracle(mesh, p, 4, go.GenEOOptions(), ksp="cg", rtol=1e-6, atol=1e-6)
+    r = pc.ksp_solve(pc.make_rhs(), ksp="cg", rtol=1e-6, atol=1e-6)
+    assert r["reason"] > 0
+    assert abs(r["its"] - rep.ksp.its) <= max(1, int(0.1 * rep.ksp.its))
+    assert pc.info()["nE"] == rep.pc.e.shape[0]
+
+
+def test_larger_case_roundtrip():
+    """64k DOFs, 8 subdomains: solution of A x = A (1..N) is (1..N); eigen-counts equal the oracle's inertia counts."""
+    mesh = go.gen_grid(3, 40, 1e-4)
+    p = _problem(mesh, 8)
+    pc = g.GeneoPC(["-geneo_lvl", "ASM,1", "-geneo_tau", "0.2"]).setup(p)
+    b = pc.make_rhs()
+    r = pc.ksp_solve(b, ksp="cg", rtol=1e-8, atol=1e-50)
+    assert r["reason"] > 0
+    np.testing.assert_allclose(r["x"], np.arange(1, mesh.nb_node + 1.0), rtol=1e-5)
+    rep = _oracle(mesh, p, 8, go.GenEOOptions(tau=0.2), ksp="cg", rtol=1e-8, atol=1e-50)
+    assert [pc.sub_info(s)["nev"] for s in range(8)] == [s.z.shape[1] for s in rep.pc.sub]
+    assert abs(r["its"] - rep.ksp.its) <= 1

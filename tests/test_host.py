@@ -1,0 +1,148 @@
+"""CPU-side tests of the product's HOST logic (no device needed): C-ABI exports, generators, decomposition parity with
+the oracle, symbolic analysis (validated by a numpy emulation of the device numeric phase), small dense eigen-solver."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.linalg as sla
+
+import geneo4petsc_b200 as g
+from geneo4petsc_b200._lib import header_functions
+from oracle import geneo_oracle as go
+from tests import _emul
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 40
+    for f in names:
+        assert hasattr(g.lib, f), "missing export " + f
+
+
+def test_no_cpu_fallback_without_device():
+    if g.device_count() > 0:
+        pytest.skip("a device is present")
+    p = g.Problem().generate("laplacian", "--dim 2 --size 6").decompose(2)
+    with pytest.raises(g.GeneoError, match="no CUDA device"):
+        g.GeneoPC().setup(p)
+    with pytest.raises(g.GeneoError):
+        g.microbench(1, 1024)
+
+
+@pytest.mark.parametrize("kind,args,kw", [
+    ("laplacian", "--dim 3 --size 9 --kappa 2. lin --inpEps 0.0001", dict(dim=3, size=9, inp_eps=1e-4, kappa_max=2.0, interp="lin")),
+    ("laplacian", "--dim 2 --size 11 --weakScaling 3 --kappa 5. quad", dict(dim=2, size=11, weak=3, kappa_max=5.0, interp="quad")),
+    ("laplacian", "--dim 1 --size 7", dict(dim=1, size=7)),
+    ("heat", "--dim 3 --size 7 --kappa 100. minmax --lbd 1. --dt 0.1", dict(dim=3, size=7, kappa_max=100.0, interp="minmax", heat=True)),
+])
+def test_structured_generator_matches_reference_element_sequence(kind, args, kw):
+    p = g.Problem().generate(kind, args)
+    ep, ei, em = p.mesh()
+    m = go.gen_grid(**kw)  # itself checked bit-exact against the reference's own generator (test_oracle_props.py)
+    assert p.sizes()["nb_node"] == m.nb_node and p.sizes()["nb_elem"] == m.nb_elem
+    assert np.array_equal(ep, m.elem_ptr) and np.array_equal(ei, m.elem_idx) and np.array_equal(em, m.mat_val)
+
+
+def test_bad_options_are_rejected():
+    for bad in (["-geneo_lvl", "FOO,1"], ["-geneo_lvl", "ASM,9"], ["-geneo_tau", "1.5"], ["-geneo_tau", "abc"],
+                ["-geneo_lvl", "SORAS,2", "-geneo_gamma", "0.5"], ["-geneo_lvl"]):
+        with pytest.raises(g.GeneoError):
+            g.GeneoPC(bad)
+    assert g.GeneoPC(["-geneo_lvl", "SORAS,H2"]).name == "geneo2HSORAS"
+    assert g.GeneoPC().name == "geneo1ASM"
+    assert g.GeneoPC(["-geneo_lvl", "RAS,E1"]).name == "geneo1ERAS"
+    assert g.GeneoPC(["-geneo_lvl", "ASM,0"]).name == "geneo0ASM"
+
+
+@pytest.mark.parametrize("dual,overlap,nparts", [(True, 0, 4), (False, 0, 3), (True, 1, 4), (False, 2, 2), (True, 0, 1)])
+def test_decomposition_matches_oracle(dual, overlap, nparts):
+    mesh = go.gen_grid(3, 8, 1e-4, 3.0, "lin")
+    p = g.Problem().set_mesh(mesh.nb_node, mesh.elem_ptr, mesh.elem_idx, mesh.mat_val).decompose(nparts, dual, overlap)
+    ep, npart = p.partition()
+    oe, on = go.metis_partition(mesh, nparts, dual)
+    assert np.array_equal(ep, oe) and np.array_equal(npart, on)  # same METIS build, same options => identical partition
+    dec = go.decompose(mesh, nparts, oe, on, dual, overlap)
+    nnz = 0
+    for s in range(nparts):
+        nodes, mult = p.sub_nodes(s)
+        assert np.array_equal(nodes, dec.nodes[s])
+        assert np.array_equal(mult, dec.node_mult[dec.nodes[s]])
+        for q in range(nparts):
+            assert np.array_equal(p.sub_intersect(s, q), dec.intersect[s][q])
+        a_neu = go.local_neumann(mesh, dec, s)
+        mine = p.sub_matrix(s, 0)
+        assert abs(mine - a_neu).max() < 1e-13
+        nnz += mine.nnz
+    a = go.assemble_global(mesh.nb_node, dec, [go.local_neumann(mesh, dec, s) for s in range(nparts)])
+    for s in range(nparts):
+        nodes = dec.nodes[s]
+        a_dir = a[nodes][:, nodes]
+        assert abs(p.sub_matrix(s, 1) - a_dir).max() < 1e-12
+    assert p.sizes()["nnz"] == nnz
+
+
+def test_explicit_partition_is_honoured():
+    mesh = go.gen_grid(2, 8)
+    epart = (np.arange(mesh.nb_elem) % 3).astype(np.int32)
+    p = g.Problem().set_mesh(mesh.nb_node, mesh.elem_ptr, mesh.elem_idx, mesh.mat_val).decompose(3, True, 0, elem_part=epart)
+    assert np.array_equal(p.partition()[0], epart)
+    dec = go.decompose(mesh, 3, epart, np.zeros(mesh.nb_node, dtype=int), True, 0)
+    for s in range(3):
+        assert np.array_equal(p.sub_nodes(s)[0], dec.nodes[s])
+
+
+def _grid_matrix(n, dim):
+    mesh = go.gen_grid(dim, n, 1e-2)
+    part = go.metis_partition(mesh, 1, True)
+    dec = go.decompose(mesh, 1, part[0], part[1], True, 0)
+    return go.local_neumann(mesh, dec, 0)
+
+
+@pytest.mark.parametrize("n,dim,nb,ordering,amalg", [(6, 3, 8, 1, True), (9, 3, 16, 1, True), (12, 2, 128, 1, True),
+                                                     (7, 3, 8, 0, False), (10, 3, 32, 1, False), (30, 1, 8, 1, True)])
+def test_symbolic_structures_drive_a_correct_factorization(n, dim, nb, ordering, amalg):
+    a = _grid_matrix(n, dim).tocsr()
+    a.sort_indices()
+    sym = g.Symbolic(a, nb=nb, ordering=ordering, amalgamate=amalg)
+    fr = sym.fronts
+    assert sorted(sym.perm.tolist()) == list(range(a.shape[0]))
+    assert fr[:, _emul.F_K].sum() == a.shape[0] and fr[:, _emul.F_K].max() <= nb
+    par = fr[:, _emul.F_PARENT]
+    has_par = par >= 0
+    assert np.all(fr[has_par, _emul.F_LEVEL] + 1 == fr[par[has_par], _emul.F_LEVEL])  # children exactly one level below
+    L, neg = _emul.factorize(sym, a.data)
+    assert neg == 0
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(a.shape[0])
+    x = _emul.solve(sym, L, b)
+    assert np.linalg.norm(a @ x - b) <= 1e-9 * np.linalg.norm(b)
+    # inertia of an indefinite shift (Sylvester): compare with the exact eigenvalue count
+    w = sla.eigvalsh(a.toarray())
+    shift = 0.5 * (w[len(w) // 3] + w[len(w) // 3 + 1])
+    s = (a - shift * sp.identity(a.shape[0])).tocsr()
+    s.sort_indices()
+    assert np.array_equal(s.indices, a.indices)
+    _, neg = _emul.factorize(sym, s.data)
+    assert neg == int(np.sum(w < shift))
+
+
+def test_symbolic_dense_matrix_is_one_chain():
+    n = 70
+    rng = np.random.default_rng(1)
+    m = rng.standard_normal((n, n))
+    e = m @ m.T + n * np.eye(n)
+    a = sp.csr_matrix(e)
+    sym = g.Symbolic(a, nb=16, ordering=0, amalgamate=False)
+    assert sym.info["nsuper"] == 1 and sym.info["nfronts"] == 5 and sym.info["nlevels"] == 5
+    L, neg = _emul.factorize(sym, a.data)
+    x = _emul.solve(sym, L, np.ones(n))
+    np.testing.assert_allclose(e @ x, np.ones(n), rtol=1e-10)
+
+
+def test_host_sym_eig_matches_lapack():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 5, 40, 130):
+        a = rng.standard_normal((n, n))
+        a = a + a.T
+        w, v = g.host_sym_eig(a)
+        np.testing.assert_allclose(w, np.linalg.eigvalsh(a), atol=1e-11 * max(1, n))
+        np.testing.assert_allclose(a @ v, v * w, atol=1e-10 * max(1, n))
