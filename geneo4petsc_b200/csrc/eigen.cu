@@ -19,6 +19,19 @@ __global__ void k_fill_random(int64_t n, int ld, int ncols, uint64_t seed, doubl
     x[t] = j < ncols ? ((double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5) : 0.;
   }
 }
+// x[r*ld + j] = random for c0 <= j < c1 (other columns untouched)
+__global__ void k_fill_random_cols(int64_t n, int ld, int c0, int c1, uint64_t seed, double* __restrict__ x) {
+  const int nc = c1 - c0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * nc; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / nc;
+    const int j = c0 + (int)(t % nc);
+    uint64_t z = (uint64_t)(r * ld + j) * 0x9E3779B97F4A7C15ull + seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    x[r * ld + j] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+  }
+}
 // dst[r*ldd + j] = src[r*lds + j], j < ncols ; zero-fills dst columns ncols..ldfill-1
 __global__ void k_copy_block(int64_t n, const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd,
                              int ncols, int ldfill) {
@@ -40,7 +53,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
   if (n <= 64) { b = n; maxDim = n; }
   else {
     b = std::max(1, opt.block);
-    maxDim = opt.maxDim > 0 ? opt.maxDim : std::max(3 * nev + 4 * b, 64);
+    maxDim = opt.maxDim > 0 ? opt.maxDim : std::max(6 * nev + 8 * b, 128);
     maxDim = std::min(maxDim, n);
     maxDim = std::max(b, maxDim / b * b);
   }
@@ -109,8 +122,76 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     for (int i = 0; i < dim; i++)
       for (int c = 0; c < b; c++) Hm[(size_t)i * maxDim + j * b + c] = hC1[(size_t)i * b + c];
     const bool room = (dim + b <= maxDim);
-    int rc = orth_block();  // next block (also gives the residual coupling R)
-    const bool breakdown = rc != 0;
+    // ---- next block: rank-revealing B-orthonormalisation of W (SVQB + random completion + CholQR) -----------------------
+    // As Ritz pairs converge the residual block W loses numerical rank; plain CholQR would break down.  Directions
+    // below the threshold are replaced by random vectors (orthogonalised against the basis); the coupling block is
+    // then R = Q_{j+1}^T B W_orig, which is what the projected matrix and the residual estimates need.
+    bool breakdown = false;
+    {
+      spmmB(w, bw);  // B W_orig (kept in bw for R)
+      CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * b * b, st));
+      ts_gram(n, w, bp, b, bw, bp, b, dC.p, b, st);
+      std::vector<double> G((size_t)b * b), Gs((size_t)b * b), sv(b), dsc(b), M((size_t)b * b, 0.);
+      CUDA_CHECK(cudaMemcpyAsync(G.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      // a column whose B-norm fell below 1e-12 of its norm before the Gram-Schmidt sweep carries no information
+      for (int i = 0; i < b; i++) {
+        double ref = G[(size_t)i * b + i];
+        for (int q = 0; q < dim; q++) ref += hC1[(size_t)q * b + i] * hC1[(size_t)q * b + i];
+        const double gii = G[(size_t)i * b + i];
+        dsc[i] = (gii > 1e-24 * ref && gii > 0.) ? 1. / std::sqrt(gii) : 0.;
+      }
+      for (int i = 0; i < b; i++)
+        for (int c = 0; c < b; c++) Gs[(size_t)i * b + c] = 0.5 * (G[(size_t)i * b + c] + G[(size_t)c * b + i]) * dsc[i] * dsc[c];
+      sym_eig(b, Gs.data(), sv.data());  // ascending
+      int r = 0;
+      for (int q = b - 1; q >= 0; q--) {  // keep directions with a significant scaled singular value
+        if (!(sv[q] > 1e-10)) break;
+        for (int i = 0; i < b; i++) M[(size_t)i * b + r] = dsc[i] * Gs[(size_t)i * b + q] / std::sqrt(sv[q]);
+        r++;
+      }
+      CUDA_CHECK(cudaMemcpyAsync(dC.p, M.data(), sizeof(double) * b * b, cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaMemsetAsync(w2, 0, sizeof(double) * (size_t)n * bp, st));
+      ts_update(n, w, bp, b, dC.p, b, b, w2, bp, 1., 0., st);  // w2 = W M (columns >= r are zero)
+      if (r < b) k_fill_random_cols<<<gridn((int64_t)n * (b - r)), 256, 0, st>>>(n, bp, r, b, 0xabcdef12ull + (uint64_t)steps * 7919ull, w2);
+      // re-orthogonalise against the basis (the 1/sqrt(s) scaling amplifies the loss of orthogonality)
+      for (int pass = 0; pass < (r < b ? 2 : 1); pass++) {
+        CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * (size_t)dim * b, st));
+        ts_gram(n, BQ.p, maxDim, dim, w2, bp, b, dC.p, b, st);
+        ts_update(n, Q.p, maxDim, dim, dC.p, b, b, w2, bp, -1., 1., st);
+      }
+      // CholQR on the (now well-conditioned) block
+      double* worig_bw = bw;  // B W_orig
+      double* wn = w2;        // new block
+      int rc = 0;
+      for (int pass = 0; pass < 2 && rc == 0; pass++) {
+        spmmB(wn, bw2);
+        CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * b * b, st));
+        ts_gram(n, wn, bp, b, bw2, bp, b, dC.p, b, st);
+        CUDA_CHECK(cudaMemcpyAsync(hR.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int i = 0; i < b; i++)
+          for (int c = i + 1; c < b; c++) hR[i * b + c] = hR[c * b + i] = 0.5 * (hR[i * b + c] + hR[c * b + i]);
+        if (chol_upper(b, hR.data(), 1e-13) >= 0) { rc = 1; break; }
+        triu_inverse(b, hR.data(), hRinv.data());
+        CUDA_CHECK(cudaMemcpyAsync(dC.p, hRinv.data(), sizeof(double) * b * b, cudaMemcpyHostToDevice, st));
+        double* tmp = (wn == w2) ? w : w2;  // out-of-place target (w is free: W_orig only survives through bw)
+        CUDA_CHECK(cudaMemsetAsync(tmp, 0, sizeof(double) * (size_t)n * bp, st));
+        ts_update(n, wn, bp, b, dC.p, b, b, tmp, bp, 1., 0., st);
+        wn = tmp;
+      }
+      if (rc != 0) breakdown = true;
+      else {
+        // R = Q_{j+1}^T B W_orig
+        CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * b * b, st));
+        ts_gram(n, wn, bp, b, worig_bw, bp, b, dC.p, b, st);
+        CUDA_CHECK(cudaMemcpyAsync(hR.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        // final block and its B image
+        if (wn != w) std::swap(w, w2);  // make w point at the new block
+        spmmB(w, bw);
+      }
+    }
     if (breakdown) std::fill(hR.begin(), hR.end(), 0.);
     if (room)  // T Q_j = Q_{0..j} C_j + Q_{j+1} R : the sub-diagonal block of the projected matrix
       for (int r = 0; r < b; r++)

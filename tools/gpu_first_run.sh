@@ -18,7 +18,7 @@ for _ in range(5): torch.matmul(a, b)
 e1.record(); torch.cuda.synchronize()
 print("cublas dgemm 8192 TFLOP/s", 5 * 2 * 8192**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
 PY
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/pytest_gpu.log
+tail -120 gpurun_out/pytest_gpu.log | cut -c1-200
 cat gpurun_out/microbench.log
