@@ -406,6 +406,14 @@ void GeneoPC::setup(const Decomposition& dec) {
     nicolaides += s.nicolaides;
   }
   ws = LdltWorkspace();
+  {  // the forest of all level-1 factors
+    std::vector<const LdltPlan*> plans;
+    std::vector<int64_t> xoff;
+    std::vector<const double*> Ls;
+    for (auto& s : subs) { plans.push_back(s.plan.get()); xoff.push_back(s.off); Ls.push_back(s.L1->L.p); }
+    forest.build(plans, xoff);
+    forest.set_factors(Ls, st);
+  }
   if (opt.lvl2 >= 1) {
     const double te = now_s();
     build_coarse();
@@ -599,16 +607,7 @@ void GeneoPC::level1(const double* xin, double* yout, bool addQ) {
   }
   tic();
   if (opt.lvl1RAS) vec_pointwise(nAll, dAll.p, Xall.p, st);  // D before the solve, src/geneo.cpp:1991-1993
-  // local solves: subdomains are independent -> round-robin over side streams
-  CUDA_CHECK(cudaEventRecord(evFork, st));
-  const int ns = (int)streams.size();
-  for (int i = 0; i < ns; i++) CUDA_CHECK(cudaStreamWaitEvent(streams[i], evFork, 0));
-  for (int p = 0; p < P; p++)
-    subs[p].L1->solve_permuted(Xall.p + subs[p].off, Yall.p + subs[p].off, 1, 0, 1, streams[p % ns]);
-  for (int i = 0; i < ns; i++) {
-    CUDA_CHECK(cudaEventRecord(events[i], streams[i]));
-    CUDA_CHECK(cudaStreamWaitEvent(st, events[i], 0));
-  }
+  forest.solve(Xall.p, Yall.p, 1, 0, 1, st);  // every local subdomain in ONE persistent cooperative kernel
   toc(lvl1ApplyMinvTime);
   if (addQ || opt.lvl1SRAS) {
     tic();

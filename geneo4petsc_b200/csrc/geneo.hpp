@@ -116,6 +116,7 @@ class GeneoPC {
                           std::vector<int>& counts);
   void build_coarse();
   void level1(const double* xin, double* yout, bool addQ);
+  SolveForest forest;
   DevBuf<double> Xall, Yall, w, w2, Einv, t1, t2, t3, scal;
   DevBuf<int> gidxAll;
   DevBuf<double> dAll;

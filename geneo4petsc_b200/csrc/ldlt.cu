@@ -12,9 +12,12 @@
 //                   once per sweep with fully coalesced 256-byte warp loads (HBM-bound by design)
 #include "ldlt.hpp"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 namespace geneo {
+namespace cg = cooperative_groups;
 
 // =====================================================================================================================
 // DMMA 64x64 tile:  C (+)= A * B^T,  A: M x K (col-major, lda), B: N x K (col-major, ldb), C: M x N (col-major, ldc)
@@ -268,30 +271,30 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_schur(const WorkItem* __restri
 }
 
 // =====================================================================================================================
-// Solve kernels: one warp per (front, row block).
+// Solve: ONE persistent cooperative kernel per solve over a FOREST of factors (all local subdomains at once).
+// Work items are (subdomain, front, 32-row block, 32-column chunk); a warp streams its 8 KB (fwd / diag) or 32 KB (bwd)
+// tile of the factor with coalesced 256-byte loads; levels are separated by grid-wide barriers instead of kernel
+// launches, so a whole preconditioner application costs one launch and 2*levels+2 barriers.
 // =====================================================================================================================
+constexpr int SOLVE_COLS = 32;
 constexpr int BWD_ROWS = 128;
 
 template <int NR>
-__global__ void __launch_bounds__(256) k_fwd(int nitems, const WorkItem* __restrict__ items,
-                                             const FrontDev* __restrict__ fr, const int* __restrict__ rowIdx,
-                                             const double* __restrict__ L, double* __restrict__ X, int ldx) {
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (w >= nitems) return;
-  const WorkItem it = items[w];
-  const FrontDev F = fr[it.f];
+__device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it, double* __restrict__ X, int ldx, int lane) {
+  const FrontDev F = S.fronts[it.f];
   const int k = F.k, h = F.h, m = h - k;
-  const int r = it.a * 32 + lane;
+  const int r = it.rb * 32 + lane;
   const bool ok = r < m;
-  const double* Lp = L + F.lOff + k + (ok ? r : 0);
-  const int col0 = rowIdx[F.rowOff];
-  const double* x1 = X + (size_t)col0 * ldx;
+  const int c0 = it.cb * SOLVE_COLS, c1 = min(k, c0 + SOLVE_COLS);
+  const double* Lp = S.L + F.lOff + k + (ok ? r : 0);
+  const int col0 = S.rowIdx[F.rowOff];
+  const double* x1 = X + (size_t)(S.xoff + col0) * ldx;
   double acc[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) acc[j] = 0.;
-  int c = 0;
-  for (; c + 4 <= k; c += 4) {
-    double l0 = Lp[(size_t)c * h], l1 = Lp[(size_t)(c + 1) * h], l2 = Lp[(size_t)(c + 2) * h], l3 = Lp[(size_t)(c + 3) * h];
+  int c = c0;
+  for (; c + 4 <= c1; c += 4) {
+    const double l0 = Lp[(size_t)c * h], l1 = Lp[(size_t)(c + 1) * h], l2 = Lp[(size_t)(c + 2) * h], l3 = Lp[(size_t)(c + 3) * h];
 #pragma unroll
     for (int j = 0; j < NR; j++) {
       acc[j] += l0 * x1[(size_t)c * ldx + j];
@@ -300,69 +303,72 @@ __global__ void __launch_bounds__(256) k_fwd(int nitems, const WorkItem* __restr
       acc[j] += l3 * x1[(size_t)(c + 3) * ldx + j];
     }
   }
-  for (; c < k; c++) {
+  for (; c < c1; c++) {
     const double l0 = Lp[(size_t)c * h];
 #pragma unroll
     for (int j = 0; j < NR; j++) acc[j] += l0 * x1[(size_t)c * ldx + j];
   }
   if (ok) {
-    const int row = rowIdx[F.rowOff + k + r];
+    const int row = S.rowIdx[F.rowOff + k + r];
 #pragma unroll
-    for (int j = 0; j < NR; j++) atomicAdd(&X[(size_t)row * ldx + j], -acc[j]);
+    for (int j = 0; j < NR; j++) atomicAdd(&X[(size_t)(S.xoff + row) * ldx + j], -acc[j]);
   }
 }
 
 template <int NR>
-__global__ void __launch_bounds__(256) k_dsolve(int nitems, const WorkItem* __restrict__ items,
-                                                const FrontDev* __restrict__ fr, const int* __restrict__ rowIdx,
-                                                const double* __restrict__ L, const double* __restrict__ X,
-                                                double* __restrict__ Y, int ldx) {
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (w >= nitems) return;
-  const WorkItem it = items[w];
-  const FrontDev F = fr[it.f];
+__device__ __forceinline__ void dsolve_item(const ForestSub& S, const ForestItem it, const double* __restrict__ X,
+                                            double* __restrict__ Y, int ldx, int lane) {
+  const FrontDev F = S.fronts[it.f];
   const int k = F.k, h = F.h;
-  const int r = it.a * 32 + lane;
+  const int r = it.rb * 32 + lane;
   const bool ok = r < k;
-  const double* Dp = L + F.lOff + (ok ? r : 0);
-  const int col0 = rowIdx[F.rowOff];
-  const double* x1 = X + (size_t)col0 * ldx;
+  const int c0 = it.cb * SOLVE_COLS, c1 = min(k, c0 + SOLVE_COLS);
+  const double* Dp = S.L + F.lOff + (ok ? r : 0);
+  const int col0 = S.rowIdx[F.rowOff];
+  const double* x1 = X + (size_t)(S.xoff + col0) * ldx;
   double acc[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) acc[j] = 0.;
-  for (int c = 0; c < k; c++) {
+  int c = c0;
+  for (; c + 4 <= c1; c += 4) {
+    const double l0 = Dp[(size_t)c * h], l1 = Dp[(size_t)(c + 1) * h], l2 = Dp[(size_t)(c + 2) * h], l3 = Dp[(size_t)(c + 3) * h];
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+      acc[j] += l0 * x1[(size_t)c * ldx + j];
+      acc[j] += l1 * x1[(size_t)(c + 1) * ldx + j];
+      acc[j] += l2 * x1[(size_t)(c + 2) * ldx + j];
+      acc[j] += l3 * x1[(size_t)(c + 3) * ldx + j];
+    }
+  }
+  for (; c < c1; c++) {
     const double l0 = Dp[(size_t)c * h];
 #pragma unroll
     for (int j = 0; j < NR; j++) acc[j] += l0 * x1[(size_t)c * ldx + j];
   }
   if (ok) {
 #pragma unroll
-    for (int j = 0; j < NR; j++) Y[(size_t)(col0 + r) * ldx + j] = acc[j];
+    for (int j = 0; j < NR; j++) atomicAdd(&Y[(size_t)(S.xoff + col0 + r) * ldx + j], acc[j]);
   }
 }
 
 template <int NR>
-__global__ void __launch_bounds__(256) k_bwd(int nitems, const WorkItem* __restrict__ items,
-                                             const FrontDev* __restrict__ fr, const int* __restrict__ rowIdx,
-                                             const double* __restrict__ L, double* __restrict__ Y, int ldx) {
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (w >= nitems) return;
-  const WorkItem it = items[w];
-  const FrontDev F = fr[it.f];
+__device__ __forceinline__ void bwd_item(const ForestSub& S, const ForestItem it, double* __restrict__ Y, int ldx, int lane) {
+  const FrontDev F = S.fronts[it.f];
   const int k = F.k, h = F.h, m = h - k;
-  const int col0 = rowIdx[F.rowOff];
-  const double* Lp = L + F.lOff + k;
+  const int col0 = S.rowIdx[F.rowOff];
+  const int c0 = it.cb * SOLVE_COLS, c1 = min(k, c0 + SOLVE_COLS);
+  const double* Lp = S.L + F.lOff + k;
   double xb[4][NR];
   int rr[4];
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    const int r = it.a * BWD_ROWS + q * 32 + lane;
+    const int r = it.rb * BWD_ROWS + q * 32 + lane;
     rr[q] = r < m ? r : -1;
-    const int row = r < m ? rowIdx[F.rowOff + k + r] : 0;
+    const int row = r < m ? S.rowIdx[F.rowOff + k + r] : 0;
 #pragma unroll
-    for (int j = 0; j < NR; j++) xb[q][j] = r < m ? Y[(size_t)row * ldx + j] : 0.;
+    for (int j = 0; j < NR; j++) xb[q][j] = r < m ? Y[(size_t)(S.xoff + row) * ldx + j] : 0.;
   }
-  for (int c = 0; c < k; c++) {
+  for (int c = c0; c < c1; c++) {
     double p[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) p[j] = 0.;
@@ -379,8 +385,49 @@ __global__ void __launch_bounds__(256) k_bwd(int nitems, const WorkItem* __restr
     }
     if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < NR; j++) atomicAdd(&Y[(size_t)(col0 + c) * ldx + j], -p[j]);
+      for (int j = 0; j < NR; j++) atomicAdd(&Y[(size_t)(S.xoff + col0 + c) * ldx + j], -p[j]);
     }
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(NR <= 2 ? 1024 : 512) k_solve_forest(const ForestSub* __restrict__ subs, const ForestItem* __restrict__ items,
+                                                      const int64_t* __restrict__ ranges, int nlev, int64_t ntot,
+                                                      double* __restrict__ X, double* __restrict__ Y, int ldx) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // Y = 0 (the diagonal solve accumulates into it); visible to everyone after the first barrier
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntot * NR; t += (int64_t)gridDim.x * blockDim.x)
+    Y[(t / NR) * ldx + (t % NR)] = 0.;
+  const int64_t* fwdOff = ranges;
+  const int64_t* fwdCnt = ranges + nlev;
+  const int64_t* bwdOff = ranges + 2 * nlev;
+  const int64_t* bwdCnt = ranges + 3 * nlev;
+  for (int l = 0; l < nlev; l++) {
+    const int64_t off = fwdOff[l], cnt = fwdCnt[l];
+    for (int64_t i = gw; i < cnt; i += nw) {
+      const ForestItem it = items[off + i];
+      fwd_item<NR>(subs[it.sub], it, X, ldx, lane);
+    }
+    grid.sync();
+  }
+  {
+    const int64_t off = ranges[4 * nlev], cnt = ranges[4 * nlev + 1];
+    for (int64_t i = gw; i < cnt; i += nw) {
+      const ForestItem it = items[off + i];
+      dsolve_item<NR>(subs[it.sub], it, X, Y, ldx, lane);
+    }
+    grid.sync();
+  }
+  for (int l = nlev - 1; l >= 0; l--) {
+    const int64_t off = bwdOff[l], cnt = bwdCnt[l];
+    for (int64_t i = gw; i < cnt; i += nw) {
+      const ForestItem it = items[off + i];
+      bwd_item<NR>(subs[it.sub], it, Y, ldx, lane);
+    }
+    if (l > 0) grid.sync();
   }
 }
 
@@ -414,7 +461,6 @@ void LdltPlan::build_device() {
   auto end = [&](Range& r) { r.cnt = (int)((int64_t)items.size() - r.off); };
   const int nl = sym.nlevels;
   eaddItems.resize(nl); diagItems.resize(nl); copyItems.resize(nl); panelItems.resize(nl); schurItems.resize(nl);
-  fwdItems.resize(nl); bwdItems.resize(nl);
   levelU.assign(nl, 0);
   for (int l = 0; l < nl; l++) {
     const int* lf = &sym.levelFronts[sym.levelPtr[l]];
@@ -456,19 +502,7 @@ void LdltPlan::build_device() {
         for (int tj = 0; tj <= ti; tj++) items.push_back(WorkItem{lf[t], ti, tj});
     }
     end(schurItems[l]);
-    begin(fwdItems[l]);
-    for (int t = 0; t < cnt; t++)
-      for (int rb = 0; rb * 32 < sym.fronts[lf[t]].m(); rb++) items.push_back(WorkItem{lf[t], rb, 0});
-    end(fwdItems[l]);
-    begin(bwdItems[l]);
-    for (int t = 0; t < cnt; t++)
-      for (int rb = 0; rb * BWD_ROWS < sym.fronts[lf[t]].m(); rb++) items.push_back(WorkItem{lf[t], rb, 0});
-    end(bwdItems[l]);
   }
-  begin(dsolveItems);
-  for (int f = 0; f < nf; f++)
-    for (int rb = 0; rb * 32 < sym.fronts[f].k; rb++) items.push_back(WorkItem{f, rb, 0});
-  end(dsolveItems);
 
   dFronts.upload(fd);
   dRowIdx.upload(sym.rowIdx);
@@ -535,34 +569,108 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   return stats;
 }
 
-template <int NR>
-static void solve_impl(const LdltPlan& P, const double* L, double* X, double* Y, int ldx, cudaStream_t st) {
-  const Symbolic& S = P.sym;
-  const WorkItem* items = P.dItems.p;
-  for (int l = 0; l < S.nlevels; l++) {
-    const int cnt = P.fwdItems[l].cnt;
-    if (cnt) k_fwd<NR><<<(cnt + 7) / 8, 256, 0, st>>>(cnt, items + P.fwdItems[l].off, P.dFronts.p, P.dRowIdx.p, L, X, ldx);
+// =====================================================================================================================
+// SolveForest
+// =====================================================================================================================
+void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::vector<int64_t>& xoff) {
+  const int ns = (int)plans.size();
+  plans_ = plans;
+  xoff_ = xoff;
+  nlev = 0;
+  ntot = 0;
+  for (int s = 0; s < ns; s++) { nlev = std::max(nlev, plans[s]->sym.nlevels); ntot = std::max<int64_t>(ntot, xoff[s] + plans[s]->sym.n); }
+  std::vector<ForestItem> items;
+  std::vector<int64_t> ranges(4 * (size_t)nlev + 2, 0);
+  for (int l = 0; l < nlev; l++) {
+    ranges[l] = (int64_t)items.size();
+    for (int s = 0; s < ns; s++) {
+      const Symbolic& S = plans[s]->sym;
+      if (l >= S.nlevels) continue;
+      for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
+        const int f = S.levelFronts[t];
+        const Front& F = S.fronts[f];
+        for (int rb = 0; rb * 32 < F.m(); rb++)
+          for (int cb = 0; cb * SOLVE_COLS < F.k; cb++) items.push_back(ForestItem{s, f, rb, cb});
+      }
+    }
+    ranges[nlev + l] = (int64_t)items.size() - ranges[l];
   }
-  {
-    const int cnt = P.dsolveItems.cnt;
-    k_dsolve<NR><<<(cnt + 7) / 8, 256, 0, st>>>(cnt, items + P.dsolveItems.off, P.dFronts.p, P.dRowIdx.p, L, X, Y, ldx);
+  for (int l = 0; l < nlev; l++) {
+    ranges[2 * nlev + l] = (int64_t)items.size();
+    for (int s = 0; s < ns; s++) {
+      const Symbolic& S = plans[s]->sym;
+      if (l >= S.nlevels) continue;
+      for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
+        const int f = S.levelFronts[t];
+        const Front& F = S.fronts[f];
+        for (int rb = 0; rb * BWD_ROWS < F.m(); rb++)
+          for (int cb = 0; cb * SOLVE_COLS < F.k; cb++) items.push_back(ForestItem{s, f, rb, cb});
+      }
+    }
+    ranges[3 * nlev + l] = (int64_t)items.size() - ranges[2 * nlev + l];
   }
-  for (int l = S.nlevels - 1; l >= 0; l--) {
-    const int cnt = P.bwdItems[l].cnt;
-    if (cnt) k_bwd<NR><<<(cnt + 7) / 8, 256, 0, st>>>(cnt, items + P.bwdItems[l].off, P.dFronts.p, P.dRowIdx.p, L, Y, ldx);
+  ranges[4 * nlev] = (int64_t)items.size();
+  for (int s = 0; s < ns; s++) {
+    const Symbolic& S = plans[s]->sym;
+    for (int f = 0; f < (int)S.fronts.size(); f++)
+      for (int rb = 0; rb * 32 < S.fronts[f].k; rb++)
+        for (int cb = 0; cb * SOLVE_COLS < S.fronts[f].k; cb++) items.push_back(ForestItem{s, f, rb, cb});
   }
-  CUDA_CHECK(cudaGetLastError());
+  ranges[4 * nlev + 1] = (int64_t)items.size() - ranges[4 * nlev];
+  dItems.upload(items);
+  dRanges.upload(ranges);
+  hSubs.assign(ns, ForestSub{nullptr, nullptr, nullptr, 0});
+  for (int s = 0; s < ns; s++) { hSubs[s].fronts = plans[s]->dFronts.p; hSubs[s].rowIdx = plans[s]->dRowIdx.p; hSubs[s].xoff = xoff[s]; }
+  dSubs.alloc(ns);
+  CUDA_CHECK(cudaStreamSynchronize(0));
+  int dev = 0, nsm = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const void* fns[4] = {(const void*)k_solve_forest<1>, (const void*)k_solve_forest<2>, (const void*)k_solve_forest<4>, (const void*)k_solve_forest<8>};
+  for (int q = 0; q < 4; q++) {
+    int nb = 0;
+    const int threads = q <= 1 ? 1024 : 512;  // few, fat CTAs: the grid barrier cost grows with the number of CTAs
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fns[q], threads, 0));
+    gridBlocks[q] = std::max(1, nb) * nsm;
+  }
+}
+
+void SolveForest::set_factors(const std::vector<const double*>& L, cudaStream_t st) {
+  GENEO_CHECK(L.size() == hSubs.size(), "forest: wrong number of factors");
+  for (size_t s = 0; s < L.size(); s++) hSubs[s].L = L[s];
+  CUDA_CHECK(cudaMemcpyAsync(dSubs.p, hSubs.data(), sizeof(ForestSub) * hSubs.size(), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const {
+  double* Xp = X + j0;
+  double* Yp = Y + j0;
+  const ForestSub* subs = dSubs.p;
+  const ForestItem* items = dItems.p;
+  const int64_t* ranges = dRanges.p;
+  int nl = nlev;
+  int64_t nt = ntot;
+  void* args[] = {(void*)&subs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ldx};
+  const void* fn = nullptr;
+  int q = 0;
+  switch (nr) {
+    case 1: fn = (const void*)k_solve_forest<1>; q = 0; break;
+    case 2: fn = (const void*)k_solve_forest<2>; q = 1; break;
+    case 4: fn = (const void*)k_solve_forest<4>; q = 2; break;
+    case 8: fn = (const void*)k_solve_forest<8>; q = 3; break;
+    default: GENEO_CHECK(false, "nrhs chunk must be 1, 2, 4 or 8");
+  }
+  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(q <= 1 ? 1024 : 512), args, 0, st));
 }
 
 void LdltFactor::solve_permuted(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const {
   GENEO_CHECK(L.p != nullptr, "solve before factorize");
-  switch (nr) {
-    case 1: solve_impl<1>(*plan_, L.p, X + j0, Y + j0, ldx, st); break;
-    case 2: solve_impl<2>(*plan_, L.p, X + j0, Y + j0, ldx, st); break;
-    case 4: solve_impl<4>(*plan_, L.p, X + j0, Y + j0, ldx, st); break;
-    case 8: solve_impl<8>(*plan_, L.p, X + j0, Y + j0, ldx, st); break;
-    default: GENEO_CHECK(false, "nrhs chunk must be 1, 2, 4 or 8");
+  if (!self_) {
+    self_.reset(new SolveForest());
+    self_->build({plan_.get()}, {0});
   }
+  if (selfL_ != L.p) { self_->set_factors({L.p}, st); selfL_ = L.p; }
+  self_->solve(X, Y, ldx, j0, nr, st);
 }
 
 }  // namespace geneo

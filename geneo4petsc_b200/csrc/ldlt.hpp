@@ -28,14 +28,34 @@ class LdltPlan {
   DevBuf<WorkItem> dItems;  // all item lists, concatenated
   struct Range { int64_t off = 0; int cnt = 0; };
   std::vector<Range> eaddItems, diagItems, copyItems, panelItems, schurItems;  // per level (factor)
-  std::vector<Range> fwdItems, bwdItems;                                       // per level (solve)
-  Range dsolveItems;                                                           // all fronts (diagonal solve)
   std::vector<int64_t> levelU;                                                 // doubles of update arena used per level
   DevBuf<int> dPerm;                                                           // new -> old
   size_t plan_bytes() const;
  private:
   void build_device();
  public:
+};
+
+// ---- level-scheduled solves over a forest of factors (one persistent cooperative kernel) -----------------------------
+struct ForestSub { const double* L; const FrontDev* fronts; const int* rowIdx; int64_t xoff; };
+struct ForestItem { int sub, f, rb, cb; };
+class SolveForest {
+ public:
+  // plans[s] solves rows [xoff[s], xoff[s]+n_s) of the concatenated (permuted) vectors
+  void build(const std::vector<const LdltPlan*>& plans, const std::vector<int64_t>& xoff);
+  void set_factors(const std::vector<const double*>& L, cudaStream_t st);
+  // X (forward sweep, overwritten) -> Y (result); row-major blocks with leading dimension ldx, columns j0..j0+nr-1
+  void solve(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const;
+  int nlev = 0;
+  int64_t ntot = 0;
+ private:
+  std::vector<const LdltPlan*> plans_;
+  std::vector<int64_t> xoff_;
+  std::vector<ForestSub> hSubs;
+  DevBuf<ForestSub> dSubs;
+  DevBuf<ForestItem> dItems;
+  DevBuf<int64_t> dRanges;
+  int gridBlocks[4] = {1, 1, 1, 1};
 };
 
 struct FactorStats { int neg = 0, perturbed = 0; double seconds = 0.; };
@@ -58,9 +78,11 @@ class LdltFactor {
   const LdltPlan& plan() const { return *plan_; }
   std::shared_ptr<LdltPlan> plan_ptr() const { return plan_; }
   DevBuf<double> L;
-  void release() { L.release(); }
+  void release() { L.release(); selfL_ = nullptr; }
  private:
   std::shared_ptr<LdltPlan> plan_;
+  mutable std::unique_ptr<SolveForest> self_;  // single-factor forest (eigen-solver, coarse operator)
+  mutable const double* selfL_ = nullptr;
 };
 
 // DGEMM self-test hooks (microbenchmarks / parity tests of the DMMA tile kernel).
