@@ -36,6 +36,13 @@ def device_count():
     return int(lib.geneo_device_count())
 
 
+def counters():
+    """{launches, h2d, d2h}: kernel launches and host<->device bytes issued by the library so far."""
+    c = np.zeros(3, dtype=np.int64)
+    _chk(lib.geneo_counters(_p(c, _i64p)))
+    return dict(launches=int(c[0]), h2d=int(c[1]), d2h=int(c[2]))
+
+
 def host_sym_eig(a):
     a = np.array(a, dtype=np.float64, order="C")
     n = a.shape[0]
@@ -140,7 +147,7 @@ class GeneoPC:
     TIMER_NAMES = ["lvl1SetupMinv", "lvl2SetupTauLoc", "lvl2SetupTauSyl", "lvl2SetupTauEig", "lvl2SetupGammaLoc",
                    "lvl2SetupGammaSyl", "lvl2SetupGammaEig", "lvl2SetupSyl", "lvl2SetupEig", "lvl2SetupZ", "lvl2SetupE",
                    "lvl1Apply", "lvl1ApplyScatter", "lvl1ApplyMinv", "lvl1ApplyGather", "lvl1ApplyPrjFS", "lvl2Apply",
-                   "lvl2ApplyZt", "lvl2ApplyEinv", "lvl2ApplyZ", "symbolic", "operator", "setup"]
+                   "lvl2ApplyZt", "lvl2ApplyEinv", "lvl2ApplyZ", "symbolic", "operator", "setup", "upload", "numeric"]
 
     def __init__(self, options=None):
         self.h = C.c_void_p()
@@ -165,6 +172,17 @@ class GeneoPC:
         self.problem = problem  # borrowed by the library: keep it alive
         _chk(lib.geneo_pc_setup(self.h, problem.h))
         return self
+
+    def refactor(self):
+        """Numeric setup again on the device-resident matrices (same pattern)."""
+        _chk(lib.geneo_pc_refactor(self.h))
+        return self
+
+    def kernel_time(self):
+        """(ms, launches) of the level-1 solve kernel since the last call (needs -geneo_kernel_timing)."""
+        ms, n = C.c_double(), C.c_int64()
+        _chk(lib.geneo_pc_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     @property
     def name(self):

@@ -183,6 +183,24 @@ int geneo_pc_setup(geneo_pc_t pc, geneo_problem_t p) {
   pc->ready = true;
   ABI_CATCH
 }
+int geneo_pc_refactor(geneo_pc_t pc) {
+  ABI_TRY
+  ABI_REQ(pc && pc->ready, "GenEO preconditioner without context");
+  pc->pc.numeric_setup();
+  ABI_CATCH
+}
+int geneo_pc_kernel_time(geneo_pc_t pc, double* ms, int64_t* launches) {
+  ABI_TRY
+  ABI_REQ(pc && pc->ready, "GenEO preconditioner without context");
+  pc->pc.kernel_time(ms, launches);
+  ABI_CATCH
+}
+int geneo_counters(int64_t c[3]) {
+  ABI_TRY
+  ABI_REQ(c, "null argument");
+  c[0] = (int64_t)g_kernel_launches; c[1] = (int64_t)g_h2d_bytes; c[2] = (int64_t)g_d2h_bytes;
+  ABI_CATCH
+}
 static int stage_apply(geneo_pc_t pc, const double* x, double* y, int what) {
   GeneoPC& g = pc->pc;
   DevBuf<double> dx(g.nLoc), dy(g.nLoc);
@@ -245,7 +263,7 @@ int geneo_pc_timers(geneo_pc_t pc, double* t, int cap) {
                       g.lvl2SetupSylTime, g.lvl2SetupEigTime, g.lvl2SetupZTime, g.lvl2SetupETime,   // 7-10
                       g.lvl1ApplyTime, g.lvl1ApplyScatterTime, g.lvl1ApplyMinvTime, g.lvl1ApplyGatherTime,  // 11-14
                       g.lvl1ApplyPrjFSTime, g.lvl2ApplyTime, g.lvl2ApplyZtTime, g.lvl2ApplyEinvTime, g.lvl2ApplyZTime,  // 15-19
-                      g.symbolicTime, g.operatorTime, g.setupTime};                                 // 20-22
+                      g.symbolicTime, g.operatorTime, g.setupTime, g.uploadTime, g.numericTime};   // 20-24
   const int n = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < std::min(n, cap); i++) t[i] = v[i];
   ABI_CATCH

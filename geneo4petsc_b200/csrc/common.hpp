@@ -33,6 +33,13 @@ inline double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Every kernel launch of the library goes through GENEO_TICK (wrapped around the grid argument of <<< >>>), so the
+// number of launches inside a timed region is a counted fact (bench.py "gpu_launches"), not an estimate.
+extern unsigned long long g_kernel_launches, g_h2d_bytes, g_d2h_bytes;
+template <class G>
+inline G launch_tick(G g) { ++g_kernel_launches; return g; }
+#define GENEO_TICK(g) ::geneo::launch_tick(g)
+
 // The product has NO CPU fallback: every numeric entry point calls this first.
 inline void require_device() {
   int n = 0;
@@ -69,6 +76,7 @@ struct DevBuf {
   void upload(const T* h, size_t cnt, cudaStream_t s = 0) {
     if (cnt > n) alloc(cnt);
     if (cnt) CUDA_CHECK(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+    g_h2d_bytes += cnt * sizeof(T);
   }
   void upload(const std::vector<T>& h, cudaStream_t s = 0) {
     if (h.size() != n) alloc(h.size());
@@ -76,6 +84,7 @@ struct DevBuf {
   }
   void download(T* h, size_t cnt, cudaStream_t s = 0) const {
     if (cnt) CUDA_CHECK(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
+    g_d2h_bytes += cnt * sizeof(T);
     CUDA_CHECK(cudaStreamSynchronize(s));
   }
   std::vector<T> to_host(cudaStream_t s = 0) const {

@@ -88,14 +88,14 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     return 0;
   };
 
-  k_fill_random<<<gridn((int64_t)n * bp), 256, 0, st>>>(n, bp, b, 0x1234567ull, w);
+  k_fill_random<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, bp, b, 0x1234567ull, w);
   std::vector<double> R0;
   for (int pass = 0; pass < 2; pass++) {  // CholQR2
     const int rc = orth_block();
     GENEO_CHECK(rc == 0, "block_lanczos: the B matrix of the pencil is not positive definite");
   }
-  k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, w, bp, Q.p, maxDim, b, b);
-  k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, bw, bp, BQ.p, maxDim, b, b);
+  k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, w, bp, Q.p, maxDim, b, b);
+  k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, bw, bp, BQ.p, maxDim, b, b);
 
   std::vector<double> Hm((size_t)maxDim * maxDim, 0.), T, theta, hC1, hC2, Rfirst;
   std::vector<double> ritzVal, ritzRes;
@@ -106,7 +106,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     const int j = steps;
     dim = (j + 1) * b;
     // W = F^-1 (B Q_j)
-    k_copy_block<<<gridn((int64_t)n * bp), 256, 0, st>>>(n, BQ.p + (size_t)j * b, maxDim, Xs.p, bp, b, bp);
+    k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)j * b, maxDim, Xs.p, bp, b, bp);
     for (int j0 = 0; j0 < bp; j0 += 8) F.solve_permuted(Xs.p, w, bp, j0, 8, st);
     // two passes of block classical Gram-Schmidt against Q[:, 0:dim] in the B inner product
     hC1.assign((size_t)dim * b, 0.);
@@ -153,7 +153,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       CUDA_CHECK(cudaMemcpyAsync(dC.p, M.data(), sizeof(double) * b * b, cudaMemcpyHostToDevice, st));
       CUDA_CHECK(cudaMemsetAsync(w2, 0, sizeof(double) * (size_t)n * bp, st));
       ts_update(n, w, bp, b, dC.p, b, b, w2, bp, 1., 0., st);  // w2 = W M (columns >= r are zero)
-      if (r < b) k_fill_random_cols<<<gridn((int64_t)n * (b - r)), 256, 0, st>>>(n, bp, r, b, 0xabcdef12ull + (uint64_t)steps * 7919ull, w2);
+      if (r < b) k_fill_random_cols<<<GENEO_TICK(gridn((int64_t)n * (b - r))), 256, 0, st>>>(n, bp, r, b, 0xabcdef12ull + (uint64_t)steps * 7919ull, w2);
       // re-orthogonalise against the basis (the 1/sqrt(s) scaling amplifies the loss of orthogonality)
       for (int pass = 0; pass < (r < b ? 2 : 1); pass++) {
         CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * (size_t)dim * b, st));
@@ -222,8 +222,8 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     res.nconv = nconv;
     if ((nconv == want && want == nev) || breakdown || !room || dim + b > n) done = true;
     if (!done) {
-      k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, w, bp, Q.p + (size_t)(j + 1) * b, maxDim, b, b);
-      k_copy_block<<<gridn((int64_t)n * b), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)(j + 1) * b, maxDim, b, b);
+      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, w, bp, Q.p + (size_t)(j + 1) * b, maxDim, b, b);
+      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)(j + 1) * b, maxDim, b, b);
     } else {
       // Ritz vectors X = Q[:, 0:dim] Y
       const int got = want;

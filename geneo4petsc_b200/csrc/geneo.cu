@@ -12,6 +12,8 @@
 
 namespace geneo {
 
+unsigned long long g_kernel_launches = 0, g_h2d_bytes = 0, g_d2h_bytes = 0;
+
 // =====================================================================================================================
 // Options
 // =====================================================================================================================
@@ -76,6 +78,7 @@ int GeneoOptions::parse(int argc, const char* const* argv, std::string& err) {
     else if (o == "-geneo_nb") { double c; const char* v = need(a, "-geneo_nb"); if (!v || !num(v, c, "-geneo_nb")) return 1; nb = (int)c; a++; }
     else if (o == "-geneo_ordering") { double c; const char* v = need(a, "-geneo_ordering"); if (!v || !num(v, c, "-geneo_ordering")) return 1; ordering = (int)c; a++; }
     else if (o == "-geneo_timing") timing = true;
+    else if (o == "-geneo_kernel_timing") kernelTiming = true;
   }
   // consistency (src/geneo.cpp:2486-2488)
   if (lvl2 >= 1 && tau <= 0.) { err = "GenEO preconditioner: tau must be > 0."; return 1; }
@@ -195,6 +198,7 @@ GeneoPC::GeneoPC() {}
 GeneoPC::~GeneoPC() {
   for (auto s : streams) cudaStreamDestroy(s);
   for (auto e : events) cudaEventDestroy(e);
+  for (auto e : ktEvents) cudaEventDestroy(e);
   if (evFork) cudaEventDestroy(evFork);
 }
 
@@ -309,8 +313,11 @@ void GeneoPC::setup(const Decomposition& dec) {
   }
   CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
 
-  // ---- numeric setup, subdomain by subdomain (each one fills the GPU) -----------------------------------------------------
-  LdltWorkspace ws;
+  // ---- upload every subdomain's matrices (the numeric phase below only touches device-resident data) ----------------
+  t0 = now_s();
+  connectivity.assign((size_t)dec.nbPart * dec.nbPart, 0);
+  for (int r = 0; r < dec.nbPart; r++)
+    for (int q = 0; q < dec.nbPart; q++) connectivity[(size_t)r * dec.nbPart + q] = dec.subs[r].intersect[q].empty() ? 1 : 0;
   for (int p = 0; p < P; p++) {
     SubdomainState& s = subs[p];
     HostPrep& H = prep[p];
@@ -323,8 +330,63 @@ void GeneoPC::setup(const Decomposition& dec) {
     s.gidx.upload(H.gidx, st);
     s.d.upload(H.dP, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
-    const double anorm = H.anorm;
     H = HostPrep();  // free host memory early
+  }
+  uploadTime = now_s() - t0;
+  numeric_setup();
+  setupTime = now_s() - tSetup0;
+}
+
+void GeneoPC::numeric_setup() {
+  const double tNum0 = now_s();
+  lvl1SetupMinvTime = lvl2SetupSylTime = lvl2SetupEigTime = lvl2SetupZTime = lvl2SetupETime = 0.;
+  lvl2SetupTauLocTime = lvl2SetupTauSylTime = lvl2SetupTauEigTime = 0.;
+  lvl2SetupGammaLocTime = lvl2SetupGammaSylTime = lvl2SetupGammaEigTime = 0.;
+  estimDimE = realDimE = nicolaides = 0;
+  factorBytes = factorNnz = 0;
+  factorFlops = 0.;
+  LdltWorkspace ws;
+  for (auto& s : subs) {
+    s.estim = s.nicolaides = s.eigSteps = s.eigDim = s.negL1 = s.perturbed = 0;
+    s.nev = 0;
+    numeric_subdomain(s, ws);
+  }
+  ws = LdltWorkspace();
+  {  // the forest of all level-1 factors
+    std::vector<const LdltPlan*> plans;
+    std::vector<int64_t> xoff;
+    std::vector<const double*> Ls;
+    for (auto& s : subs) { plans.push_back(s.plan.get()); xoff.push_back(s.off); Ls.push_back(s.L1->L.p); }
+    if (forest.nlev == 0) forest.build(plans, xoff);
+    forest.set_factors(Ls, st);
+  }
+  if (opt.lvl2 >= 1) {
+    const double te = now_s();
+    build_coarse();
+    lvl2SetupETime = now_s() - te;
+    infoL2 = "blocklanczos ldlt";
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  numericTime = now_s() - tNum0;
+}
+
+void GeneoPC::kernel_time(double* ms, int64_t* launches) {
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  double tot = 0.;
+  for (size_t i = 0; i + 1 < ktUsed; i += 2) {
+    float t = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&t, ktEvents[i], ktEvents[i + 1]));
+    tot += t;
+  }
+  if (ms) *ms = tot;
+  if (launches) *launches = (int64_t)(ktUsed / 2);
+  ktUsed = 0;
+}
+
+// every factorization and eigen-solve of one subdomain (level 2 first: its factors are transient)
+void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
+  {
+    const double anorm = s.anorm;
     // pivot threshold
     const double pivTol = opt.pivRel * std::max(anorm, 1e-300);
     // level 2 first (its factorizations are transient), then the persistent level-1 factor
@@ -346,11 +408,11 @@ void GeneoPC::setup(const Decomposition& dec) {
         eigen_local_problem(s, s.vNeu.p, s.vRob.p, tl, true, ws, vals, vecs, counts);
         double gl = opt.gamma;  // getLocalGenEOGamma, src/geneo.cpp:1120-1232 (connectivity quirk reproduced)
         if (!opt.cst) {
-          const int NP = dec.nbPart;
+          const int NP = nbPart;
           std::vector<double> C((size_t)NP * NP, 0.), F(NP, 0.), wv(NP);
           for (int r = 0; r < NP; r++)
             for (int q = 0; q < NP; q++)
-              C[(size_t)r * NP + q] = (r == q) ? 1. : (dec.subs[r].intersect[q].empty() ? 1. : 0.);
+              C[(size_t)r * NP + q] = (r == q) ? 1. : (connectivity[(size_t)r * NP + q] ? 1. : 0.);
           for (int r = 0; r < NP; r++) { double sum = 0.; for (int q = 0; q < NP; q++) sum += C[(size_t)r * NP + q]; F[r] = 1. / sum; }
           for (int r = 0; r < NP; r++) for (int q = 0; q < NP; q++) C[(size_t)r * NP + q] *= F[r] * F[q];
           sym_eig(NP, C.data(), wv.data());
@@ -393,7 +455,7 @@ void GeneoPC::setup(const Decomposition& dec) {
     }
     // level 1: factor A_dir (or A_rob), src/geneo.cpp:126-148
     const double tl1 = now_s();
-    s.L1.reset(new LdltFactor(s.plan));
+    if (!s.L1) s.L1.reset(new LdltFactor(s.plan));  // a re-factorization overwrites the resident factor in place
     FactorStats fs = s.L1->factorize(opt.lvl1ORAS ? s.vRob.p : s.pat.val.p, pivTol, ws, st);
     s.negL1 = fs.neg;
     s.perturbed = fs.perturbed;
@@ -405,23 +467,6 @@ void GeneoPC::setup(const Decomposition& dec) {
     realDimE += s.nev;
     nicolaides += s.nicolaides;
   }
-  ws = LdltWorkspace();
-  {  // the forest of all level-1 factors
-    std::vector<const LdltPlan*> plans;
-    std::vector<int64_t> xoff;
-    std::vector<const double*> Ls;
-    for (auto& s : subs) { plans.push_back(s.plan.get()); xoff.push_back(s.off); Ls.push_back(s.L1->L.p); }
-    forest.build(plans, xoff);
-    forest.set_factors(Ls, st);
-  }
-  if (opt.lvl2 >= 1) {
-    const double te = now_s();
-    build_coarse();
-    lvl2SetupETime = now_s() - te;
-    infoL2 = "blocklanczos ldlt";
-  }
-  CUDA_CHECK(cudaStreamSynchronize(st));
-  setupTime = now_s() - tSetup0;
 }
 
 // eigenLocalProblem (src/geneo.cpp:842-963) + estimateNumberOfEigenValues (:502-533) + eigenLocalSolve (:626-722)
@@ -607,7 +652,12 @@ void GeneoPC::level1(const double* xin, double* yout, bool addQ) {
   }
   tic();
   if (opt.lvl1RAS) vec_pointwise(nAll, dAll.p, Xall.p, st);  // D before the solve, src/geneo.cpp:1991-1993
+  if (opt.kernelTiming) {
+    while (ktEvents.size() < ktUsed + 2) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); ktEvents.push_back(e); }
+    CUDA_CHECK(cudaEventRecord(ktEvents[ktUsed], st));
+  }
   forest.solve(Xall.p, Yall.p, 1, 0, 1, st);  // every local subdomain in ONE persistent cooperative kernel
+  if (opt.kernelTiming) { CUDA_CHECK(cudaEventRecord(ktEvents[ktUsed + 1], st)); ktUsed += 2; }
   toc(lvl1ApplyMinvTime);
   if (addQ || opt.lvl1SRAS) {
     tic();

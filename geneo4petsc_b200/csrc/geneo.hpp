@@ -32,6 +32,7 @@ struct GeneoOptions {
   int epsMaxDim = 0;     // -els2_eps_ncv like bound on the Krylov dimension (0 = automatic)
   double pivRel = 1e-14; // static pivot threshold relative to max |a_ij| (stands for MUMPS CNTL(1/3), ICNTL(24))
   bool timing = false;   // synchronise and time every apply phase (reference timers hdr/geneo.hpp:115-123)
+  bool kernelTiming = false;  // CUDA-event pairs around the level-1 solve kernel (bench.py roofline leg), no host sync
 
   // Parse "-geneo_lvl ASM,1 -geneo_tau 0.1 ..." (grammar of src/geneo.cpp:2338-2481).  Unknown tokens are ignored
   // (they belong to the caller: PETSc options DB in the reference).  Returns 0, or 1 + message on a bad value.
@@ -86,7 +87,7 @@ class GeneoPC {
   double lvl2SetupGammaLocTime = 0., lvl2SetupGammaSylTime = 0., lvl2SetupGammaEigTime = 0.;
   double lvl1ApplyTime = 0., lvl1ApplyScatterTime = 0., lvl1ApplyMinvTime = 0., lvl1ApplyGatherTime = 0.;
   double lvl1ApplyPrjFSTime = 0., lvl2ApplyTime = 0., lvl2ApplyZtTime = 0., lvl2ApplyEinvTime = 0., lvl2ApplyZTime = 0.;
-  double symbolicTime = 0., operatorTime = 0., setupTime = 0.;
+  double symbolicTime = 0., operatorTime = 0., setupTime = 0., uploadTime = 0., numericTime = 0.;
   int estimDimE = 0, realDimE = 0, nicolaides = 0;
   int64_t factorBytes = 0, factorNnz = 0, applyCount = 0;
   double factorFlops = 0.;
@@ -96,6 +97,11 @@ class GeneoPC {
   ~GeneoPC();
   // All subdomains of `dec` whose matrices are present are local to this process (single-GPU path).
   void setup(const Decomposition& dec);
+  // Numeric half of the setup again (every factorization, eigen-solve, Z, E) on the matrices already resident in HBM:
+  // PCSetUp with an unchanged non-zero pattern.  setup() = host analysis + uploads + numeric_setup().
+  void numeric_setup();
+  // accumulated CUDA-event time of the level-1 solve kernel since the last call (ms) and its number of launches
+  void kernel_time(double* ms, int64_t* launches);
   void apply(const double* x, double* y);                 // device pointers, length nLoc; x is not modified
   void applyQ(const double* x, double* y);                // y = Z E^-1 Z^T x
   void mult(const double* x, double* y) { sell_spmv(A, x, y, st); }
@@ -110,13 +116,16 @@ class GeneoPC {
   void copy_einv(double* out) const;  // nE x nE row-major E^-1 to the host
 
  private:
-  void setup_subdomain_numeric(const Subdomain& S, SubdomainState& s, LdltWorkspace& ws);
+  void numeric_subdomain(SubdomainState& s, LdltWorkspace& ws);
   int eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb,
                           LdltWorkspace& ws, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs,
                           std::vector<int>& counts);
   void build_coarse();
   void level1(const double* xin, double* yout, bool addQ);
   SolveForest forest;
+  std::vector<char> connectivity;  // nbPart x nbPart: 1 when the intersection of two subdomains is EMPTY (src/geneo.cpp:1143-1145)
+  std::vector<cudaEvent_t> ktEvents;  // kernelTiming: pairs
+  size_t ktUsed = 0;
   DevBuf<double> Xall, Yall, w, w2, Einv, t1, t2, t3, scal;
   DevBuf<int> gidxAll;
   DevBuf<double> dAll;

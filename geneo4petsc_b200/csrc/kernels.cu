@@ -386,25 +386,25 @@ void SellMatrix::build(const CsrHost& a, cudaStream_t st) {
 
 void sell_spmv(const SellMatrix& A, const double* x, double* y, cudaStream_t st) {
   const int grid = std::max(1, std::min((A.nslices + 7) / 8, NSM * 8));
-  k_sell_spmv<false><<<grid, 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, x, nullptr, y);
+  k_sell_spmv<false><<<GENEO_TICK(grid), 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, x, nullptr, y);
   CUDA_CHECK(cudaGetLastError());
 }
 void sell_spmv_sub(const SellMatrix& A, const double* x, const double* b, double* y, cudaStream_t st) {
   const int grid = std::max(1, std::min((A.nslices + 7) / 8, NSM * 8));
-  k_sell_spmv<true><<<grid, 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, x, b, y);
+  k_sell_spmv<true><<<GENEO_TICK(grid), 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, x, b, y);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void sell_spmm8(const SellMatrix& A, const double* X, double* Y, cudaStream_t st) {
   const int grid = std::max(1, std::min((A.nslices + 7) / 8, NSM * 8));
-  k_sell_spmm8<<<grid, 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, X, Y);
+  k_sell_spmm8<<<GENEO_TICK(grid), 256, 0, st>>>(A.n, A.nslices, A.sliceOff.p, A.col.p, A.val.p, X, Y);
   CUDA_CHECK(cudaGetLastError());
 }
 void scatter_rows8(int n, const int* idx, const double* Z, int ldz, int c0, int nc, double* G, cudaStream_t st) {
-  if (n) k_scatter_rows8<<<grid_for((int64_t)n * 8, 256), 256, 0, st>>>(n, idx, Z, ldz, c0, nc, G);
+  if (n) k_scatter_rows8<<<GENEO_TICK(grid_for((int64_t)n * 8, 256)), 256, 0, st>>>(n, idx, Z, ldz, c0, nc, G);
 }
 void gather_rows8(int n, const int* idx, const double* G, double* out, cudaStream_t st) {
-  if (n) k_gather_rows8<<<grid_for((int64_t)n * 8, 256), 256, 0, st>>>(n, idx, G, out);
+  if (n) k_gather_rows8<<<GENEO_TICK(grid_for((int64_t)n * 8, 256)), 256, 0, st>>>(n, idx, G, out);
 }
 
 void CsrDev::upload_pattern(const CsrHost& a, cudaStream_t st) {
@@ -421,12 +421,12 @@ void csr_spmm(int n, const int64_t* ptr, const int* idx, const double* val, cons
   const int64_t tot = (int64_t)n * nr;
   const int grid = (int)((tot + 255) / 256);
   switch (nr) {
-    case 1: k_csr_spmm<1><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
-    case 2: k_csr_spmm<2><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
-    case 4: k_csr_spmm<4><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
-    case 8: k_csr_spmm<8><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
-    case 16: k_csr_spmm<16><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
-    case 32: k_csr_spmm<32><<<grid, 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 1: k_csr_spmm<1><<<GENEO_TICK(grid), 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 2: k_csr_spmm<2><<<GENEO_TICK(grid), 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 4: k_csr_spmm<4><<<GENEO_TICK(grid), 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 8: k_csr_spmm<8><<<GENEO_TICK(grid), 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 16: k_csr_spmm<16><<<GENEO_TICK(grid), 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
+    case 32: k_csr_spmm<32><<<GENEO_TICK(grid), 256, 0, st>>>(n, ptr, idx, val, X, ldx, Y, ldy); break;
     default: GENEO_CHECK(false, "csr_spmm: nr must be a power of two <= 32");
   }
   CUDA_CHECK(cudaGetLastError());
@@ -434,33 +434,33 @@ void csr_spmm(int n, const int64_t* ptr, const int* idx, const double* val, cons
 
 void vec_dot(int n, const double* x, const double* y, double* out, cudaStream_t st) {
   CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double), st));
-  k_dot<<<grid_for(n, 256, 4), 256, 0, st>>>(n, x, y, out);
+  k_dot<<<GENEO_TICK(grid_for(n, 256, 4)), 256, 0, st>>>(n, x, y, out);
 }
 void vec_dot2(int n, const double* x, const double* y, const double* z, double* out, cudaStream_t st) {
   CUDA_CHECK(cudaMemsetAsync(out, 0, 2 * sizeof(double), st));
-  k_dot2<<<grid_for(n, 256, 4), 256, 0, st>>>(n, x, y, z, out);
+  k_dot2<<<GENEO_TICK(grid_for(n, 256, 4)), 256, 0, st>>>(n, x, y, z, out);
 }
-void vec_axpy(int n, double a, const double* x, double* y, cudaStream_t st) { k_axpy<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, y); }
-void vec_aypx(int n, double a, const double* x, double* y, cudaStream_t st) { k_axpby<<<grid_for(n, 256), 256, 0, st>>>(n, 1., x, a, y); }
-void vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st) { k_axpby<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, b, y); }
+void vec_axpy(int n, double a, const double* x, double* y, cudaStream_t st) { k_axpy<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, a, x, y); }
+void vec_aypx(int n, double a, const double* x, double* y, cudaStream_t st) { k_axpby<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, 1., x, a, y); }
+void vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st) { k_axpby<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, a, x, b, y); }
 void vec_cg_update(int n, double a, const double* p, const double* w, double* x, double* r, cudaStream_t st) {
-  k_cg_update<<<grid_for(n, 256), 256, 0, st>>>(n, a, p, w, x, r);
+  k_cg_update<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, a, p, w, x, r);
 }
-void vec_scale(int n, double a, double* x, cudaStream_t st) { k_scale<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); }
-void vec_set(int n, double a, double* x, cudaStream_t st) { k_set<<<grid_for(n, 256), 256, 0, st>>>(n, a, 0., x); }
-void vec_iota(int n, double first, double* x, cudaStream_t st) { k_set<<<grid_for(n, 256), 256, 0, st>>>(n, first, 1., x); }
+void vec_scale(int n, double a, double* x, cudaStream_t st) { k_scale<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, a, x); }
+void vec_set(int n, double a, double* x, cudaStream_t st) { k_set<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, a, 0., x); }
+void vec_iota(int n, double first, double* x, cudaStream_t st) { k_set<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, first, 1., x); }
 void vec_mdot(int n, int nv, const double* V, int64_t ldv, const double* w, double* out, cudaStream_t st) {
   CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)((nv + 3) / 4 * 4), st));
-  k_mdot<<<grid_for(n, 256, 4), 256, 0, st>>>(n, nv, V, ldv, w, out);
+  k_mdot<<<GENEO_TICK(grid_for(n, 256, 4)), 256, 0, st>>>(n, nv, V, ldv, w, out);
 }
 void vec_maxpy(int n, int nv, const double* V, int64_t ldv, const double* coef, double* w, cudaStream_t st) {
-  k_maxpy<<<grid_for(n, 256), 256, 0, st>>>(n, nv, V, ldv, coef, w);
+  k_maxpy<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, nv, V, ldv, coef, w);
 }
 void gather_rows(int64_t cnt, const int* idx, const double* scale, const double* x, double* out, cudaStream_t st) {
-  if (cnt) k_gather<<<grid_for(cnt, 256), 256, 0, st>>>(cnt, idx, scale, x, out);
+  if (cnt) k_gather<<<GENEO_TICK(grid_for(cnt, 256)), 256, 0, st>>>(cnt, idx, scale, x, out);
 }
 void pull_sum(int n, const int64_t* ptr, const int64_t* pos, const double* t, double* y, bool accumulate, cudaStream_t st) {
-  k_pull_sum<<<grid_for(n, 256), 256, 0, st>>>(n, ptr, pos, t, y, accumulate);
+  k_pull_sum<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, ptr, pos, t, y, accumulate);
 }
 void ts_gram(int n, const double* X, int ldx, int p, const double* Y, int ldy, int q, double* G, int ldg, cudaStream_t st) {
   const int tp = (p + 31) / 32, tq = (q + 31) / 32;
@@ -468,7 +468,7 @@ void ts_gram(int n, const double* X, int ldx, int p, const double* Y, int ldy, i
   int rowsPerCta = ((n + nz - 1) / nz + GR - 1) / GR * GR;
   nz = (n + rowsPerCta - 1) / rowsPerCta;
   dim3 grid(tp, tq, nz);
-  k_ts_gram<<<grid, 256, 0, st>>>(n, X, ldx, p, Y, ldy, q, G, ldg, rowsPerCta);
+  k_ts_gram<<<GENEO_TICK(grid), 256, 0, st>>>(n, X, ldx, p, Y, ldy, q, G, ldg, rowsPerCta);
   CUDA_CHECK(cudaGetLastError());
 }
 void ts_update(int n, const double* Q, int ldq, int p, const double* C, int ldc, int q, double* W, int ldw, double alpha,
@@ -479,7 +479,7 @@ void ts_update(int n, const double* Q, int ldq, int p, const double* C, int ldc,
     while (qpad < qc) qpad <<= 1;
     const int rowsPerCta = 256 / qpad;
     const int grid = (n + rowsPerCta - 1) / rowsPerCta;
-    k_ts_update<<<grid, 256, 64 * qpad * sizeof(double), st>>>(n, Q, ldq, p, C + j0, ldc, qc, W + j0, ldw, alpha, beta, qpad);
+    k_ts_update<<<GENEO_TICK(grid), 256, 64 * qpad * sizeof(double), st>>>(n, Q, ldq, p, C + j0, ldc, qc, W + j0, ldw, alpha, beta, qpad);
   }
   CUDA_CHECK(cudaGetLastError());
 }
@@ -490,33 +490,33 @@ void zt_x(int n, int nev, const double* Z, int ldz, const double* x, double* w, 
   nevPad = std::min(nevPad, 256);
   const int rstride = 256 / nevPad;
   const int grid = std::max(1, std::min((n + rstride * 8 - 1) / (rstride * 8), NSM * 4));
-  k_zt_x<<<grid, 256, 0, st>>>(n, nev, Z, ldz, x, w);
+  k_zt_x<<<GENEO_TICK(grid), 256, 0, st>>>(n, nev, Z, ldz, x, w);
   CUDA_CHECK(cudaGetLastError());
 }
 void z_w_add(int n, int nev, const double* Z, int ldz, const double* w, const double* d, double* t, cudaStream_t st) {
   const int grid = std::max(1, std::min((n + 7) / 8, NSM * 8));
-  k_z_w_add<<<grid, 256, 0, st>>>(n, nev, Z, ldz, w, d, t);
+  k_z_w_add<<<GENEO_TICK(grid), 256, 0, st>>>(n, nev, Z, ldz, w, d, t);
   CUDA_CHECK(cudaGetLastError());
 }
 void dense_gemv(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t st) {
   if (m == 0) return;
-  k_dense_gemv<<<(m + 7) / 8, 256, 0, st>>>(m, n, A, lda, x, y);
+  k_dense_gemv<<<GENEO_TICK((m + 7) / 8), 256, 0, st>>>(m, n, A, lda, x, y);
   CUDA_CHECK(cudaGetLastError());
 }
-void vec_pointwise(int64_t n, const double* d, double* x, cudaStream_t st) { k_pointwise<<<grid_for(n, 256), 256, 0, st>>>(n, d, x); }
+void vec_pointwise(int64_t n, const double* d, double* x, cudaStream_t st) { k_pointwise<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, d, x); }
 void rows_scale(int n, int ld, const double* d, double* Z, cudaStream_t st) {
   const int64_t tot = (int64_t)n * ld;
-  if (tot) k_rows_scale<<<grid_for(tot, 256), 256, 0, st>>>(tot, ld, d, Z);
+  if (tot) k_rows_scale<<<GENEO_TICK(grid_for(tot, 256)), 256, 0, st>>>(tot, ld, d, Z);
 }
 void csr_scale_sym(int n, const int64_t* ptr, const int* idx, const double* val, const double* d, double* out, cudaStream_t st) {
-  k_csr_scale_sym<<<grid_for(n, 256), 256, 0, st>>>(n, ptr, idx, val, d, out);
+  k_csr_scale_sym<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, ptr, idx, val, d, out);
 }
 void vals_axpby(int64_t nnz, const double* a, double tau, const double* b, double* out, cudaStream_t st) {
-  k_vals_axpby<<<grid_for(nnz, 256), 256, 0, st>>>(nnz, a, tau, b, out);
+  k_vals_axpby<<<GENEO_TICK(grid_for(nnz, 256)), 256, 0, st>>>(nnz, a, tau, b, out);
 }
 void csr_sum_all(int64_t nnz, const double* val, double* out, cudaStream_t st) {
   CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double), st));
-  k_sum_all<<<grid_for(nnz, 256, 4), 256, 0, st>>>(nnz, val, out);
+  k_sum_all<<<GENEO_TICK(grid_for(nnz, 256, 4)), 256, 0, st>>>(nnz, val, out);
 }
 
 }  // namespace geneo

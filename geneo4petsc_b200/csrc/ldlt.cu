@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(NR <= 2 ? 1024 : 512) k_solve_forest(const For
 void dgemm_nt_device(int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                      int mode, cudaStream_t st) {
   dim3 grid((M + TS - 1) / TS, (N + TS - 1) / TS);
-  k_dgemm_nt<<<grid, GEMM_THREADS, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, mode);
+  k_dgemm_nt<<<GENEO_TICK(grid), GEMM_THREADS, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, mode);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -540,7 +540,7 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   {
     const int64_t cnt = (int64_t)P.dAsmSrc.n;
     const int grid = (int)std::min<int64_t>((cnt + 255) / 256, 148 * 16);
-    if (cnt) k_assemble<<<grid, 256, 0, st>>>(cnt, P.dAsmSrc.p, P.dAsmDst.p, dVals, L.p);
+    if (cnt) k_assemble<<<GENEO_TICK(grid), 256, 0, st>>>(cnt, P.dAsmSrc.p, P.dAsmDst.p, dVals, L.p);
     CUDA_CHECK(cudaGetLastError());
   }
   const WorkItem* items = P.dItems.p;
@@ -549,15 +549,15 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
     double* Uprev = (l & 1) ? ws.u0.p : ws.u1.p;
     if (P.levelU[l] > 0) CUDA_CHECK(cudaMemsetAsync(Ucur, 0, (size_t)P.levelU[l] * sizeof(double), st));
     if (P.eaddItems[l].cnt)
-      k_extend_add<<<P.eaddItems[l].cnt, 256, 0, st>>>(items + P.eaddItems[l].off, P.dFronts.p, P.dRel.p, L.p, Uprev, Ucur);
+      k_extend_add<<<GENEO_TICK(P.eaddItems[l].cnt), 256, 0, st>>>(items + P.eaddItems[l].off, P.dFronts.p, P.dRel.p, L.p, Uprev, Ucur);
     if (P.diagItems[l].cnt)
-      k_diag_invert<<<P.diagItems[l].cnt, 256, 0, st>>>(items + P.diagItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
+      k_diag_invert<<<GENEO_TICK(P.diagItems[l].cnt), 256, 0, st>>>(items + P.diagItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
     if (P.copyItems[l].cnt)
-      k_copy_panel<<<P.copyItems[l].cnt, 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, L.p, ws.w.p);
+      k_copy_panel<<<GENEO_TICK(P.copyItems[l].cnt), 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, L.p, ws.w.p);
     if (P.panelItems[l].cnt)
-      k_panel<<<P.panelItems[l].cnt, GEMM_THREADS, 0, st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
+      k_panel<<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, 0, st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
     if (P.schurItems[l].cnt)
-      k_schur<<<P.schurItems[l].cnt, GEMM_THREADS, 0, st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, Ucur);
+      k_schur<<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, 0, st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, Ucur);
     CUDA_CHECK(cudaGetLastError());
   }
   int h[2] = {0, 0};
@@ -660,6 +660,7 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
     case 8: fn = (const void*)k_solve_forest<8>; q = 3; break;
     default: GENEO_CHECK(false, "nrhs chunk must be 1, 2, 4 or 8");
   }
+  ++g_kernel_launches;
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(q <= 1 ? 1024 : 512), args, 0, st));
 }
 

@@ -95,6 +95,8 @@ void colcounts(int n, const int64_t* ptr, const int* idx, const std::vector<int>
 }  // namespace
 
 void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt, Symbolic& S) {
+  const double tStart = now_s();
+  (void)tStart;
   S = Symbolic();
   S.n = n;
   S.nb = opt.nb;
@@ -124,6 +126,10 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
   }
   if (!useMetis) { std::iota(perm.begin(), perm.end(), 0); std::iota(iperm.begin(), iperm.end(), 0); }
 
+  const bool tm = getenv("GENEO_SYM_TIMING") != nullptr;
+  double tq = now_s();
+  auto lap = [&](const char* what) { if (tm) { const double t = now_s(); fprintf(stderr, "symbolic n=%d %s %.3fs\n", n, what, t - tq); tq = t; } };
+  lap("ordering");
   // ---- 2. etree, postorder, column counts; relabel so that the ordering IS a postorder -----------------------------
   std::vector<int> parent, post, cc;
   etree(n, ptr, idx, perm, iperm, parent);
@@ -142,6 +148,7 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
     for (int k = 0; k < n; k++) iperm[perm[k]] = k;
   }
 
+  lap("etree+colcounts");
   // ---- 3. supernodes (maximal: same structure as the next column) + relaxed amalgamation ----------------------------
   std::vector<int> snFirst, snK, snH;
   for (int j = 0; j < n; j++) {
@@ -226,6 +233,7 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
   }
   S.nnzRowIdx = (int64_t)rowIdx.size();
 
+  lap("supernodes+rowidx");
   // ---- 5. cut supernodes into panels (fronts) ------------------------------------------------------------------------
   const int NB = opt.nb;
   std::vector<int> firstFrontOfSn(ns), lastFrontOfSn(ns);
@@ -311,6 +319,7 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
     S.wArena = std::max(S.wArena, w);
   }
 
+  lap("fronts+levels");
   // ---- 7. scatter map of the input values (lower triangle of P A P^T) into the panels --------------------------------
   S.perm = perm;
   S.iperm = iperm;
@@ -335,6 +344,7 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
       S.asmDst.push_back(F.lOff + pos + (int64_t)(j - F.col0) * F.h);
     }
   }
+  lap("asm map");
 }
 
 }  // namespace geneo

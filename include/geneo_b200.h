@@ -67,6 +67,14 @@ int geneo_pc_setup(geneo_pc_t pc, geneo_problem_t p);
 int geneo_pc_apply(geneo_pc_t pc, const double* x, double* y);
 int geneo_pc_apply_device(geneo_pc_t pc, const double* dx, double* dy);     /* same with device pointers            */
 int geneo_pc_apply_q_device(geneo_pc_t pc, const double* dx, double* dy);   /* applyQ, :1435-1542                   */
+/* PCSetUp again with an unchanged non-zero pattern: every factorization, eigen-solve, Z and E recomputed from the
+ * matrices already resident in HBM (no host analysis, no upload).  setUpGenEOPC is re-entered the same way when PETSc
+ * flags the operator as changed (src/geneo.cpp:1672-1843). */
+int geneo_pc_refactor(geneo_pc_t pc);
+/* With -geneo_kernel_timing: CUDA-event time (ms) and launch count of the level-1 solve kernel since the last call. */
+int geneo_pc_kernel_time(geneo_pc_t pc, double* ms, int64_t* launches);
+/* process-wide counters: {kernel launches, host->device bytes, device->host bytes} issued by this library so far */
+int geneo_counters(int64_t c[3]);
 int geneo_pc_destroy(geneo_pc_t pc);                                         /* destroyGenEOPC, :2217-2243           */
 /* geneoContext fields the driver reads (src/geneo4PETSc.cpp:928-986, 1123-1225) */
 int geneo_pc_name(geneo_pc_t pc, char* buf, int cap);                        /* gCtx->name                           */

@@ -458,13 +458,24 @@ class GenEOOracle:
         self.z_off = None
         self.e = None
         self.e_lu = None
+        # One worker thread per subdomain stands for the reference's one MPI rank per subdomain (src/geneo4PETSc.cpp:604);
+        # SuperLU / ARPACK / LAPACK release the GIL inside scipy.  1 = serial (tests).
+        self.workers = 1
+
+    def _map(self, fn, items):
+        if self.workers <= 1 or len(items) <= 1:
+            return [fn(i) for i in items]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=self.workers) as ex:
+            return list(ex.map(fn, items))
 
     # ---- setup: src/geneo.cpp:1672-1843 (setUpGenEOPC) ---------------------------------------------------------------
     def setup(self, b: Optional[np.ndarray] = None):
         opt = self.opt
         asm, ras, sras, oras, lvl2, hybrid, eff = opt.flags()
         t0 = time.perf_counter()
-        for p in range(self.dec.nb_part):
+
+        def one(p):
             nodes = self.dec.nodes[p]
             a_dir = self.a[nodes][:, nodes].tocsr()  # MatCreateSubMatrices, :1699
             a_dir.sort_indices()
@@ -481,7 +492,9 @@ class GenEOOracle:
                         a_rob = (a_rob + opt.optim * add).tocsr()
             m1 = a_rob if oras else a_dir  # setUpLevel1 :137-143
             lu = spla.splu(sp.csc_matrix(m1))
-            self.sub.append(SubdomainSetup(len(nodes), self.a_neu[p], a_dir, a_rob, d, lu.solve))
+            return SubdomainSetup(len(nodes), self.a_neu[p], a_dir, a_rob, d, lu.solve)
+
+        self.sub.extend(self._map(one, list(range(self.dec.nb_part))))
         self.timers["l1_setup"] = time.perf_counter() - t0
         self.x0 = np.zeros(self.n)
         if lvl2:
@@ -553,7 +566,9 @@ class GenEOOracle:
         if lvl2 == 2 and cut >= 2:
             cut = cut // 2  # :1275
         t0 = time.perf_counter()
-        for p, s in enumerate(self.sub):
+
+        def one(p):
+            s = self.sub[p]
             dd = sp.diags(s.d)
             dadird = (dd @ s.a_dir @ dd).tocsr()  # :1243-1246
             vals, vecs = [], []
@@ -572,6 +587,8 @@ class GenEOOracle:
                 s.nicolaides += 1
             s.eigvals = vals
             s.z = np.stack(vecs, axis=1) * s.d[:, None]  # fillZE2L :261
+
+        self._map(one, list(range(len(self.sub))))
         self.timers["l2_eig"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         nev = [s.z.shape[1] for s in self.sub]
@@ -599,15 +616,19 @@ class GenEOOracle:
         """restrict, [D], M^-1, [D], prolong-add.  src/geneo.cpp:1980-2025, 1845-1900."""
         _, ras, sras, _, _, _, _ = self.opt.flags()
         out = np.zeros(self.n)
-        for p, s in enumerate(self.sub):
-            nodes = self.dec.nodes[p]
-            xl = x[nodes]
+
+        def one(p):
+            s = self.sub[p]
+            xl = x[self.dec.nodes[p]]
             if ras:
                 xl = xl * s.d
             xl = s.solve_l1(xl)
             if sras:
                 xl = xl * s.d
-            np.add.at(out, nodes, xl)
+            return xl
+
+        for p, xl in enumerate(self._map(one, list(range(len(self.sub))))):  # summed in subdomain order
+            np.add.at(out, self.dec.nodes[p], xl)
         return out
 
     def apply(self, x: np.ndarray) -> np.ndarray:
@@ -805,7 +826,8 @@ class SolveReport:
 
 def run_case(mesh: Mesh, nb_part: int, opt: GenEOOptions, dual: bool = True, overlap: int = 0, ksp: str = "gmres",
              rtol: float = 1e-5, atol: float = 1e-50, max_it: int = 10000, restart: int = 30,
-             b: Optional[np.ndarray] = None, part: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> SolveReport:
+             b: Optional[np.ndarray] = None, part: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+             workers: int = 1) -> SolveReport:
     if part is None:
         part = metis_partition(mesh, nb_part, dual)
     dec = decompose(mesh, nb_part, part[0], part[1], dual, overlap)
@@ -814,7 +836,9 @@ def run_case(mesh: Mesh, nb_part: int, opt: GenEOOptions, dual: bool = True, ove
     if b is None:  # createB :820-831
         b = a @ np.arange(1, mesh.nb_node + 1, dtype=float)
     t0 = time.perf_counter()
-    pc = GenEOOracle(mesh.nb_node, dec, a_neu, opt, a).setup(b)
+    pc = GenEOOracle(mesh.nb_node, dec, a_neu, opt, a)
+    pc.workers = workers
+    pc.setup(b)
     t1 = time.perf_counter()
     fn = ksp_cg if ksp == "cg" else ksp_gmres
     kw = dict(rtol=rtol, atol=atol, max_it=max_it)
