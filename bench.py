@@ -285,6 +285,7 @@ def run_b200(a):
         "detail": {"n_dof": n, "iterations": r["its"], "reason": r["reason_name"], "rnorm": r["rnorm"], "max_rel_err_vs_1..N": err,
                    "setup_numeric_s": setup_s / a.steps, "iter_s": iter_s / a.steps, "dimE": pc.info()["nE"],
                    "cold_setup": {k: tm_cold[k] for k in ("symbolic", "upload", "numeric", "operator", "setup")},
+                   "numeric_phases_s": {k: pc.timers()[k] for k in ("lvl1SetupMinv", "lvl2SetupSyl", "lvl2SetupEig", "lvl2SetupZ", "lvl2SetupE")},
                    "gen_s": t1 - t0, "part_decomp_s": t2 - t1, "factor_bytes": st["factor_bytes"], "factor_flops": st["factor_flops"],
                    "factor_TFLOPs_l1": st["factor_flops"] / max(tm_cold["lvl1SetupMinv"], 1e-9) / 1e12,
                    "pc_apply": rates["pc_apply"], "spmv": rates["spmv"], "hbm_peak_GBps": peak},
@@ -295,6 +296,8 @@ def run_b200(a):
                                "sample": "%s %d^3 = %d DOFs, %d subdomains, same options (%d its, %.1f s): scipy SuperLU/ARPACK "
                                          "restatement of the reference (PETSc/MUMPS/SLEPc absent)" % (a.kind, a.cpu_size, nn, a.subs_per_gpu, its, secs)}
     print(json.dumps(out))
+    if os.environ.get("GENEO_PROFILE"):
+        g.profile_dump(os.environ.get("GENEO_PROFILE_OUT", "gpurun_out/profile_sites.csv"))
 
 
 if __name__ == "__main__":

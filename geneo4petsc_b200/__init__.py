@@ -4,5 +4,5 @@ The product is the C ABI shared library ``libgeneob200.so`` (C++ host + hand-wri
 This Python package is only the thin ctypes mirror used by tests/, bench.py and __graft_entry__.py.
 It never imports anything under oracle/ and has no CPU fallback: numeric calls raise when no CUDA device is present.
 """
-from .api import (GeneoError, Problem, GeneoPC, Symbolic, lib, device_count, host_sym_eig, microbench, counters,  # noqa: F401
+from .api import (GeneoError, Problem, GeneoPC, Symbolic, lib, device_count, host_sym_eig, microbench, counters, profile_dump,  # noqa: F401
                   KSP_REASONS)

@@ -43,6 +43,10 @@ def counters():
     return dict(launches=int(c[0]), h2d=int(c[1]), d2h=int(c[2]))
 
 
+def profile_dump(path):
+    _chk(lib.geneo_profile_dump(str(path).encode()))
+
+
 def host_sym_eig(a):
     a = np.array(a, dtype=np.float64, order="C")
     n = a.shape[0]
@@ -302,7 +306,7 @@ class Symbolic:
         self.info = {k: int(v) for k, v in zip(keys, i)}
         self.info["flops"] = float(r[0])
         self.perm = np.zeros(self.n, dtype=np.int32)
-        self.fronts = np.zeros((self.info["nfronts"], 12), dtype=np.int64)
+        self.fronts = np.zeros((self.info["nfronts"], 13), dtype=np.int64)
         self.row_idx = np.zeros(self.info["nRowIdx"], dtype=np.int32)
         self.rel = np.zeros(max(1, self.info["nRel"]), dtype=np.int32)
         self.asm_src = np.zeros(self.info["nAsm"], dtype=np.int64)

@@ -1,7 +1,9 @@
 // abi.cpp -- the C ABI of include/geneo_b200.h (thin: argument checking, host<->device staging, error capture).
 #include "geneo_b200.h"
 
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "dense_host.hpp"
@@ -22,6 +24,7 @@ struct geneo_pc_s {
   const geneo_problem_s* prob = nullptr;  // borrowed (like pcA / pcMap in the reference, src/geneo.cpp:2221-2230)
 };
 struct geneo_symbolic_s { Symbolic s; };
+struct geneo_layout_s { RankLayout L; };
 
 static thread_local std::string g_err;
 #define ABI_TRY try {
@@ -183,6 +186,97 @@ int geneo_pc_setup(geneo_pc_t pc, geneo_problem_t p) {
   pc->ready = true;
   ABI_CATCH
 }
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------------
+int geneo_problem_decompose_owned(geneo_problem_t p, int nbPart, int metisDual, int overlap, const int32_t* elemPart,
+                                  const int32_t* nodePart, const int32_t* subRank, int rank) {
+  ABI_TRY
+  ABI_REQ(p && p->mesh.nbNode > 0 && subRank, "null argument");
+  ABI_REQ(nbPart >= 1, "bad number of partitions");
+  ABI_REQ((metisDual && elemPart) || (!metisDual && nodePart), "decompose_owned needs an explicit partition (identical on every rank)");
+  p->dual = metisDual != 0;
+  p->overlap = overlap;
+  p->elemPart.clear(); p->nodePart.clear();
+  if (elemPart) p->elemPart.assign(elemPart, elemPart + p->mesh.nbElem());
+  if (nodePart) p->nodePart.assign(nodePart, nodePart + p->mesh.nbNode);
+  std::vector<char> owner(nbPart, 0);
+  for (int q = 0; q < nbPart; q++) owner[q] = subRank[q] == rank;
+  decompose(p->mesh, nbPart, p->elemPart, p->nodePart, p->dual, overlap, owner, p->dec);
+  p->decomposed = true;
+  ABI_CATCH
+}
+int geneo_layout_create(geneo_problem_t p, int rank, int world, const int32_t* subRank, geneo_layout_t* out) {
+  ABI_TRY
+  ABI_REQ(p && p->decomposed && subRank && out, "layout needs a decomposed problem");
+  std::unique_ptr<geneo_layout_s> l(new geneo_layout_s());
+  std::vector<int> sr(subRank, subRank + p->dec.nbPart);
+  build_rank_layout(p->mesh, p->dec, sr, rank, world, l->L);
+  *out = l.release();
+  ABI_CATCH
+}
+int geneo_layout_destroy(geneo_layout_t l) { ABI_TRY delete l; ABI_CATCH }
+int geneo_layout_sizes(geneo_layout_t l, int64_t out[4]) {
+  ABI_TRY
+  ABI_REQ(l && out, "null argument");
+  out[0] = l->L.nOwn(); out[1] = l->L.nGhost(); out[2] = l->L.A.nnz(); out[3] = l->L.world;
+  ABI_CATCH
+}
+int geneo_layout_get(geneo_layout_t l, int32_t* owned, int32_t* ghost, int64_t* ghostPtr) {
+  ABI_TRY
+  ABI_REQ(l, "null argument");
+  if (owned) std::copy(l->L.owned.begin(), l->L.owned.end(), owned);
+  if (ghost) std::copy(l->L.ghost.begin(), l->L.ghost.end(), ghost);
+  if (ghostPtr) std::copy(l->L.ghostPtr.begin(), l->L.ghostPtr.end(), ghostPtr);
+  ABI_CATCH
+}
+int geneo_layout_matrix(geneo_layout_t l, int64_t* ptr, int32_t* idx, double* val) {
+  ABI_TRY
+  ABI_REQ(l && ptr && idx && val, "null argument");
+  const CsrHost& a = l->L.A;
+  std::copy(a.ptr.begin(), a.ptr.end(), ptr);
+  std::copy(a.idx.begin(), a.idx.end(), idx);
+  std::copy(a.val.begin(), a.val.end(), val);
+  ABI_CATCH
+}
+int geneo_layout_set_send(geneo_layout_t l, int peer, const int32_t* globalIds, int64_t n) {
+  ABI_TRY
+  ABI_REQ(l && peer >= 0 && peer < l->L.world && (n == 0 || globalIds), "bad argument");
+  std::vector<int>& s = l->L.sendIdx[peer];
+  s.resize((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const int g = globalIds[i];
+    ABI_REQ(g >= 0 && g < l->L.nbNode, "halo request outside the mesh");
+    const int li = l->L.g2l[g];
+    ABI_REQ(li >= 0 && li < l->L.nOwn(), "halo request for a node this rank does not own");
+    s[i] = li;
+  }
+  ABI_CATCH
+}
+int geneo_nccl_unique_id(void* out128) { ABI_TRY ABI_REQ(out128, "null argument"); require_device(); Comm::unique_id(out128); ABI_CATCH }
+int geneo_pc_setup_dist(geneo_pc_t pc, geneo_problem_t p, geneo_layout_t l, const void* ncclUid128) {
+  ABI_TRY
+  ABI_REQ(pc && p && p->decomposed && l, "GenEO preconditioner without a decomposed problem / layout");
+  require_device();
+  pc->prob = p;
+  pc->pc.setup(p->dec, &l->L, ncclUid128);
+  pc->ready = true;
+  ABI_CATCH
+}
+int geneo_pc_local_sizes(geneo_pc_t pc, int64_t out[2]) {
+  ABI_TRY
+  ABI_REQ(pc && pc->ready && out, "GenEO preconditioner without context");
+  out[0] = pc->pc.nOwn; out[1] = pc->pc.nLoc;
+  ABI_CATCH
+}
+int geneo_allreduce_sum(geneo_pc_t pc, double* h, int n) {
+  ABI_TRY
+  ABI_REQ(pc && pc->ready && h, "GenEO preconditioner without context");
+  pc->pc.comm.allreduce_sum_host(h, n, pc->pc.st);
+  ABI_CATCH
+}
+
+namespace geneo { int profile_dump(const char* path); }
+int geneo_profile_dump(const char* path) { ABI_TRY ABI_REQ(path, "null argument"); ABI_REQ(profile_dump(path) == 0, "cannot write the profile"); ABI_CATCH }
+
 int geneo_pc_refactor(geneo_pc_t pc) {
   ABI_TRY
   ABI_REQ(pc && pc->ready, "GenEO preconditioner without context");
@@ -241,11 +335,9 @@ int geneo_pc_info(geneo_pc_t pc, int64_t ints[16], double reals[4]) {
   ABI_REQ(pc, "null argument");
   const GeneoPC& g = pc->pc;
   int emin = 0, emax = 0, rmin = 0, rmax = 0;
-  for (size_t i = 0; i < g.subs.size(); i++) {
-    const SubdomainState& s = g.subs[i];
-    if (i == 0) { emin = emax = s.estim; rmin = rmax = s.nev; }
-    emin = std::min(emin, s.estim); emax = std::max(emax, s.estim);
-    rmin = std::min(rmin, s.nev); rmax = std::max(rmax, s.nev);
+  if (g.opt.lvl2 >= 1 && !g.nevGlobal.empty()) {  // over ALL subdomains (known on every rank)
+    emin = *std::min_element(g.estimGlobal.begin(), g.estimGlobal.end()); emax = *std::max_element(g.estimGlobal.begin(), g.estimGlobal.end());
+    rmin = *std::min_element(g.nevGlobal.begin(), g.nevGlobal.end()); rmax = *std::max_element(g.nevGlobal.begin(), g.nevGlobal.end());
   }
   const int64_t v[16] = {g.nbDof, g.nbPart, g.opt.lvl2, g.opt.hybrid, g.opt.effHybrid, g.opt.lvl1ORAS, g.opt.offload,
                          g.opt.noSyl, g.estimDimE, emin, emax, g.realDimE, rmin, rmax, g.nicolaides, g.nE};
@@ -402,8 +494,8 @@ int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32
   if (fronts)
     for (size_t f = 0; f < S.fronts.size(); f++) {
       const Front& F = S.fronts[f];
-      const int64_t v[12] = {F.col0, F.k, F.h, F.parent, F.level, F.chain, F.nchild, F.rowOff, F.lOff, F.uOff, F.wOff, F.relOff};
-      std::copy(v, v + 12, fronts + 12 * f);
+      const int64_t v[13] = {F.col0, F.k, F.h, F.parent, F.level, F.chain, F.nchild, F.rowOff, F.lOff, F.uOff, F.wOff, F.relOff, F.ld};
+      std::copy(v, v + 13, fronts + 13 * f);
     }
   if (rowIdx) std::copy(S.rowIdx.begin(), S.rowIdx.end(), rowIdx);
   if (rel) std::copy(S.rel.begin(), S.rel.end(), rel);

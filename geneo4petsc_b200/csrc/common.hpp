@@ -38,7 +38,11 @@ inline double now_s() {
 extern unsigned long long g_kernel_launches, g_h2d_bytes, g_d2h_bytes;
 template <class G>
 inline G launch_tick(G g) { ++g_kernel_launches; return g; }
-#define GENEO_TICK(g) ::geneo::launch_tick(g)
+// GENEO_PROFILE=1: a CUDA event is recorded on the (single, in-order) stream right before every launch, so consecutive
+// events bracket each kernel (plus whatever memset / idle gap follows it); geneo_profile_dump() aggregates by launch site.
+extern bool g_profile;
+void profile_tick(const char* file, int line);
+#define GENEO_TICK(g) ((::geneo::g_profile ? ::geneo::profile_tick(__FILE__, __LINE__) : (void)0), ::geneo::launch_tick(g))
 
 // The product has NO CPU fallback: every numeric entry point calls this first.
 inline void require_device() {

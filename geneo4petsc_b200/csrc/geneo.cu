@@ -14,6 +14,51 @@ namespace geneo {
 
 unsigned long long g_kernel_launches = 0, g_h2d_bytes = 0, g_d2h_bytes = 0;
 
+// ---- in-library launch profiler (GENEO_PROFILE=1) -----------------------------------------------------------------------
+bool g_profile = getenv("GENEO_PROFILE") != nullptr;
+namespace {
+struct ProfRec { const char* file; int line; cudaEvent_t ev; double host; };
+std::vector<ProfRec> g_prof;
+}  // namespace
+void profile_tick(const char* file, int line) {
+  if (g_prof.size() >= 400000) return;
+  ProfRec r{file, line, nullptr, now_s()};
+  if (cudaEventCreate(&r.ev) != cudaSuccess) return;
+  cudaEventRecord(r.ev, 0);
+  g_prof.push_back(r);
+}
+int profile_dump(const char* path) {
+  FILE* f = fopen(path, "w");
+  if (!f) return 1;
+  cudaEvent_t last;
+  cudaEventCreate(&last);
+  cudaEventRecord(last, 0);
+  cudaDeviceSynchronize();
+  const double hostEnd = now_s();
+  struct Agg { long n = 0; double gpu = 0., host = 0.; };
+  std::vector<std::pair<std::string, Agg>> agg;
+  auto find = [&](const std::string& k) -> Agg& {
+    for (auto& a : agg) if (a.first == k) return a.second;
+    agg.emplace_back(k, Agg());
+    return agg.back().second;
+  };
+  for (size_t i = 0; i < g_prof.size(); i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof[i].ev, i + 1 < g_prof.size() ? g_prof[i + 1].ev : last);
+    const double h = (i + 1 < g_prof.size() ? g_prof[i + 1].host : hostEnd) - g_prof[i].host;
+    const char* b = strrchr(g_prof[i].file, '/');
+    Agg& a = find(std::string(b ? b + 1 : g_prof[i].file) + ":" + std::to_string(g_prof[i].line));
+    a.n++; a.gpu += ms; a.host += 1e3 * h;
+  }
+  fprintf(f, "site,launches,gpu_ms_until_next_launch,host_ms_until_next_launch\n");
+  for (auto& a : agg) fprintf(f, "%s,%ld,%.3f,%.3f\n", a.first.c_str(), a.second.n, a.second.gpu, a.second.host);
+  fclose(f);
+  for (auto& r : g_prof) cudaEventDestroy(r.ev);
+  cudaEventDestroy(last);
+  g_prof.clear();
+  return 0;
+}
+
 // =====================================================================================================================
 // Options
 // =====================================================================================================================
@@ -204,13 +249,23 @@ GeneoPC::~GeneoPC() {
 
 double GeneoPC::dot(const double* x, const double* y) {
   vec_dot(nOwn, x, y, scal.p, st);
+  comm.allreduce_sum(scal.p, 1, st);
   double h = 0.;
   CUDA_CHECK(cudaMemcpyAsync(&h, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   return h;
 }
 
-void GeneoPC::setup(const Decomposition& dec) {
+void GeneoPC::mult(const double* x, double* y) {
+  comm.halo_forward(const_cast<double*>(x), 1, st);  // only the ghost copies of x are written
+  sell_spmv(A, x, y, st);
+}
+void GeneoPC::mult_sub(const double* x, const double* b, double* y) {
+  comm.halo_forward(const_cast<double*>(x), 1, st);
+  sell_spmv_sub(A, x, b, y, st);
+}
+
+void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const void* ncclUid) {
   require_device();
   const double tSetup0 = now_s();
   nbDof = dec.nbNode;
@@ -218,15 +273,29 @@ void GeneoPC::setup(const Decomposition& dec) {
   nbPart = dec.nbPart;
   scal.alloc(1024);
   std::vector<const Subdomain*> mine;
-  for (auto& S : dec.subs)
-    if (S.aNeu.n > 0) mine.push_back(&S);
-  GENEO_CHECK((int)mine.size() == dec.nbPart, "single-process setup needs every subdomain's matrices");
+  if (layout) {
+    nOwn = layout->nOwn();
+    nLoc = nOwn + layout->nGhost();
+    for (auto& S : dec.subs)
+      if (layout->subRank[S.id] == layout->rank) {
+        GENEO_CHECK(S.aNeu.n > 0, "multi-GPU setup: a local subdomain has no matrices");
+        mine.push_back(&S);
+      }
+    comm.init(layout->rank, layout->world, ncclUid, *layout, st);
+  } else {
+    for (auto& S : dec.subs)
+      if (S.aNeu.n > 0) mine.push_back(&S);
+    GENEO_CHECK((int)mine.size() == dec.nbPart, "single-process setup needs every subdomain's matrices");
+  }
+  auto localIndex = [&](int g) -> int { return layout ? layout->g2l[g] : g; };
   if (opt.lvl2 == 2 && !opt.lvl1ORAS)
     throw Error("geneo_b200: GenEO-2 needs an optimised level 1 (ORAS/SORAS) -- untested/unsupported in the reference too");
 
   // ---- operator A = sum_i R_i^T A_neu,i R_i  (MatConvert MATIS->AIJ, src/geneo.cpp:1692), SELL-32 on the device ------
   double t0 = now_s();
-  {
+  if (layout) {
+    A.build(layout->A, st);  // owned rows, assembled from the elements (mesh.cpp build_rank_layout)
+  } else {
     CsrHost g;
     g.n = g.ncols = nLoc;
     std::vector<int64_t> cnt(nLoc + 1, 0);
@@ -290,7 +359,11 @@ void GeneoPC::setup(const Decomposition& dec) {
     std::vector<double> dA((size_t)nAll);
     std::vector<int64_t> pp(nLoc + 1, 0);
     for (int p = 0; p < P; p++)
-      for (int k = 0; k < subs[p].n; k++) { gAll[subs[p].off + k] = prep[p].gidx[k]; dA[subs[p].off + k] = prep[p].dP[k]; pp[prep[p].gidx[k] + 1]++; }
+      for (int k = 0; k < subs[p].n; k++) {
+        prep[p].gidx[k] = localIndex(prep[p].gidx[k]);
+        GENEO_CHECK(prep[p].gidx[k] >= 0, "multi-GPU layout: a subdomain node is neither owned nor ghost");
+        gAll[subs[p].off + k] = prep[p].gidx[k]; dA[subs[p].off + k] = prep[p].dP[k]; pp[prep[p].gidx[k] + 1]++;
+      }
     for (int i = 0; i < nLoc; i++) pp[i + 1] += pp[i];
     std::vector<int64_t> ps((size_t)nAll);
     std::vector<int64_t> cur(pp.begin(), pp.end() - 1);
@@ -352,6 +425,15 @@ void GeneoPC::numeric_setup() {
     numeric_subdomain(s, ws);
   }
   ws = LdltWorkspace();
+  if (comm.active()) {  // the driver prints GLOBAL dimensions (src/geneo4PETSc.cpp:971-986 reduces them over the ranks)
+    double g[3] = {(double)estimDimE, (double)realDimE, (double)nicolaides};
+    comm.allreduce_sum_host(g, 3, st);
+    estimDimE = (int)std::lround(g[0]); realDimE = (int)std::lround(g[1]); nicolaides = (int)std::lround(g[2]);
+  }
+  if (opt.lvl2 == 0) {
+    nevGlobal.assign(nbPart, 0);
+    estimGlobal.assign(nbPart, 0);
+  }
   {  // the forest of all level-1 factors
     std::vector<const LdltPlan*> plans;
     std::vector<int64_t> xoff;
@@ -562,30 +644,48 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
 // Z offsets (all_gather of nev_i, src/geneo.cpp:363-375), E = Z^T A Z (MatPtAP :1033), E^-1 (dcs2_, :1059-1065)
 void GeneoPC::build_coarse() {
   const int P = (int)subs.size();
-  nE = 0;
-  for (auto& s : subs) { s.zoff = nE; nE += s.nev; }
+  // all_gather of nev_i (src/geneo.cpp:363) -> global column offsets of Z
+  std::vector<double> tmp(2 * (size_t)nbPart, 0.);
+  for (auto& s : subs) { tmp[s.id] = s.nev; tmp[nbPart + s.id] = s.estim; }
+  comm.allreduce_sum_host(tmp.data(), 2 * nbPart, st);
+  nevGlobal.assign(nbPart, 0);
+  estimGlobal.assign(nbPart, 0);
+  std::vector<int> zoffGlobal(nbPart + 1, 0), localOf(nbPart, -1);
+  for (int q = 0; q < nbPart; q++) {
+    nevGlobal[q] = (int)std::lround(tmp[q]);
+    estimGlobal[q] = (int)std::lround(tmp[nbPart + q]);
+    zoffGlobal[q + 1] = zoffGlobal[q] + nevGlobal[q];
+  }
+  nE = zoffGlobal[nbPart];
+  for (int p = 0; p < P; p++) { subs[p].zoff = zoffGlobal[subs[p].id]; localOf[subs[p].id] = p; }
   const int nEp = (nE + 7) / 8 * 8;
   DevBuf<double> dE((size_t)nE * nE);
   dE.zero(st);
   DevBuf<double> G((size_t)nLoc * 8), Wg((size_t)nLoc * 8);
   int nmax = 0;
   for (auto& s : subs) nmax = std::max(nmax, s.n);
-  DevBuf<double> Gi((size_t)nmax * 8);
-  for (int j = 0; j < P; j++) {
-    SubdomainState& sj = subs[j];
-    for (int c0 = 0; c0 < sj.nev; c0 += 8) {
-      const int nc = std::min(8, sj.nev - c0);
+  DevBuf<double> Gi((size_t)std::max(1, nmax) * 8);
+  for (int j = 0; j < nbPart; j++) {  // every rank walks the GLOBAL list of subdomains in lockstep (halo exchanges are collective)
+    const int jl = localOf[j];
+    for (int c0 = 0; c0 < nevGlobal[j]; c0 += 8) {
+      const int nc = std::min(8, nevGlobal[j] - c0);
       G.zero(st);
-      scatter_rows8(sj.n, sj.gidx.p, sj.Z.p, sj.nev, c0, nc, G.p, st);
+      if (jl >= 0) scatter_rows8(subs[jl].n, subs[jl].gidx.p, subs[jl].Z.p, subs[jl].nev, c0, nc, G.p, st);
+      if (comm.active()) {  // R_j^T Z_j lives on the owner rows: ghost parts go to their owners, then to every copy
+        comm.halo_reverse_add(G.p, 8, st);
+        comm.halo_forward(G.p, 8, st);
+      }
       sell_spmm8(A, G.p, Wg.p, st);
+      comm.halo_forward(Wg.p, 8, st);
       for (int i = 0; i < P; i++) {
         SubdomainState& si = subs[i];
         gather_rows8(si.n, si.gidx.p, Wg.p, Gi.p, st);
         // E[zoff_i + a, zoff_j + c0 + c] += sum_k Z_i[k,a] * Gi[k,c]
-        ts_gram(si.n, si.Z.p, si.nev, si.nev, Gi.p, 8, nc, dE.p + (size_t)si.zoff * nE + sj.zoff + c0, nE, st);
+        ts_gram(si.n, si.Z.p, si.nev, si.nev, Gi.p, 8, nc, dE.p + (size_t)si.zoff * nE + zoffGlobal[j] + c0, nE, st);
       }
     }
   }
+  comm.allreduce_sum(dE.p, nE * nE, st);  // every block row was computed by exactly one rank
   std::vector<double> hE = dE.to_host(st);
   for (int i = 0; i < nE; i++)
     for (int j = i + 1; j < nE; j++) hE[(size_t)i * nE + j] = hE[(size_t)j * nE + i] = 0.5 * (hE[(size_t)i * nE + j] + hE[(size_t)j * nE + i]);
@@ -623,13 +723,16 @@ void GeneoPC::build_coarse() {
 // =====================================================================================================================
 void GeneoPC::applyQ(const double* x, double* y) {  // src/geneo.cpp:1435-1517
   const int P = (int)subs.size();
+  comm.halo_forward(const_cast<double*>(x), 1, st);
   gather_rows(nAll, gidxAll.p, nullptr, x, Xall.p, st);
   w.zero(st);
   for (int p = 0; p < P; p++) zt_x(subs[p].n, subs[p].nev, subs[p].Z.p, subs[p].nev, Xall.p + subs[p].off, w.p + subs[p].zoff, st);
+  comm.allreduce_sum(w.p, nE, st);  // coarse gather: every rank gets the whole Z^T x (E^-1 is replicated)
   dense_gemv(nE, nE, Einv.p, (nE + 7) / 8 * 8, w.p, w2.p, st);
   Yall.zero(st);
   for (int p = 0; p < P; p++) z_w_add(subs[p].n, subs[p].nev, subs[p].Z.p, subs[p].nev, w2.p + subs[p].zoff, nullptr, Yall.p + subs[p].off, st);
   pull_sum(nLoc, pullPtr.p, pullPos.p, Yall.p, y, false, st);
+  comm.halo_reverse_add(y, 1, st);
 }
 
 // restrict, [D], M^-1, [D], (+ Z E^-1 Z^T fused when addQ), prolong-add.  src/geneo.cpp:1980-2025, 1845-1900.
@@ -639,12 +742,14 @@ void GeneoPC::level1(const double* xin, double* yout, bool addQ) {
   auto tic = [&]() { if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); tt = now_s(); } };
   auto toc = [&](double& acc) { if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); acc += now_s() - tt; } };
   tic();
+  comm.halo_forward(const_cast<double*>(xin), 1, st);
   gather_rows(nAll, gidxAll.p, nullptr, xin, Xall.p, st);
   toc(lvl1ApplyScatterTime);
   if (addQ) {
     tic();
     w.zero(st);
     for (int p = 0; p < P; p++) zt_x(subs[p].n, subs[p].nev, subs[p].Z.p, subs[p].nev, Xall.p + subs[p].off, w.p + subs[p].zoff, st);
+    comm.allreduce_sum(w.p, nE, st);
     toc(lvl2ApplyZtTime);
     tic();
     dense_gemv(nE, nE, Einv.p, (nE + 7) / 8 * 8, w.p, w2.p, st);
@@ -668,6 +773,7 @@ void GeneoPC::level1(const double* xin, double* yout, bool addQ) {
   }
   tic();
   pull_sum(nLoc, pullPtr.p, pullPos.p, Yall.p, yout, false, st);
+  comm.halo_reverse_add(yout, 1, st);
   toc(lvl1ApplyGatherTime);
 }
 
@@ -679,15 +785,15 @@ void GeneoPC::apply(const double* x, double* y) {  // applyGenEOPC, src/geneo.cp
   else if (!opt.hybrid) level1(x, y, true);                         // y = Q x + sum R^T [D] M^-1 [D] R x
   else if (!opt.effHybrid) {
     applyQ(x, t1.p);                                                // t1 = Q x
-    sell_spmv_sub(A, t1.p, x, t2.p, st);                            // t2 = x - A Q x = (I - P^T) x
+    mult_sub(t1.p, x, t2.p);                                        // t2 = x - A Q x = (I - P^T) x
     level1(t2.p, t3.p, false);
-    sell_spmv(A, t3.p, t2.p, st);
+    mult(t3.p, t2.p);
     applyQ(t2.p, y);                                                // y = Q A t3
     vec_axpby(nLoc, 1., t3.p, -1., y, st);                          // y = (I - P) t3
     vec_axpy(nLoc, 1., t1.p, y, st);                                // y += Q x
   } else {
     level1(x, t3.p, false);
-    sell_spmv(A, t3.p, t2.p, st);
+    mult(t3.p, t2.p);
     applyQ(t2.p, y);
     vec_axpby(nLoc, 1., t3.p, -1., y, st);
   }
@@ -743,7 +849,7 @@ struct ConvTest {  // KSPConvergedDefault
 KspResult GeneoPC::solve_cg(const double* b, double* x, double rtol, double atol, double dtol, int maxIt) {
   KspResult R;
   DevBuf<double> r(nLoc), z(nLoc), p(nLoc), wv(nLoc);
-  sell_spmv_sub(A, x, b, r.p, st);  // non-zero initial guess is ALWAYS flagged (src/geneo4PETSc.cpp:1348)
+  mult_sub(x, b, r.p);  // non-zero initial guess is ALWAYS flagged (src/geneo4PETSc.cpp:1348)
   apply(r.p, z.p);
   double dp = norm(z.p);
   R.history.push_back(dp);
@@ -772,6 +878,7 @@ KspResult GeneoPC::solve_cg(const double* b, double* x, double rtol, double atol
     vec_cg_update(nLoc, a, p.p, wv.p, x, r.p, st);
     apply(r.p, z.p);
     vec_dot2(nOwn, z.p, r.p, z.p, scal.p, st);  // beta = z.r and ||z||^2 in one pass
+    comm.allreduce_sum(scal.p, 2, st);
     double h[2];
     CUDA_CHECK(cudaMemcpyAsync(h, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -807,7 +914,7 @@ KspResult GeneoPC::solve_gmres(const double* b, double* x, double rtol, double a
   double res = 0.;
   int reason = 0;
   while (true) {
-    sell_spmv_sub(A, x, b, t.p, st);
+    mult_sub(x, b, t.p);
     apply(t.p, V.p);  // r = M^-1 (b - A x)
     res = norm(V.p);
     if (!haveTol) {
@@ -831,6 +938,7 @@ KspResult GeneoPC::solve_gmres(const double* b, double* x, double rtol, double a
       mult(vk, t.p);
       apply(t.p, vn);  // w = M^-1 A v_k
       vec_mdot(nOwn, k + 1, V.p, nLoc, vn, coef.p, st);  // classical Gram-Schmidt, no refinement (PETSc default)
+      comm.allreduce_sum(coef.p, k + 1, st);
       vec_maxpy(nLoc, k + 1, V.p, nLoc, coef.p, vn, st);
       CUDA_CHECK(cudaMemcpyAsync(hk.data(), coef.p, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, st));
       const double tt = norm(vn);

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.hpp"
 #include "eigen.hpp"
 #include "kernels.hpp"
 #include "ldlt.hpp"
@@ -92,11 +93,14 @@ class GeneoPC {
   int64_t factorBytes = 0, factorNnz = 0, applyCount = 0;
   double factorFlops = 0.;
   std::string infoL2;
+  std::vector<int> nevGlobal, estimGlobal;  // per subdomain (global ids), known on every rank
 
   GeneoPC();
   ~GeneoPC();
-  // All subdomains of `dec` whose matrices are present are local to this process (single-GPU path).
-  void setup(const Decomposition& dec);
+  // Single GPU (layout == nullptr): every subdomain of `dec` is local.  Multi-GPU: the subdomains with
+  // layout->subRank[p] == rank are local, vectors are [owned | ghost] (RankLayout), comm holds the NCCL plumbing.
+  void setup(const Decomposition& dec, const RankLayout* layout = nullptr, const void* ncclUid = nullptr);
+  Comm comm;
   // Numeric half of the setup again (every factorization, eigen-solve, Z, E) on the matrices already resident in HBM:
   // PCSetUp with an unchanged non-zero pattern.  setup() = host analysis + uploads + numeric_setup().
   void numeric_setup();
@@ -104,7 +108,8 @@ class GeneoPC {
   void kernel_time(double* ms, int64_t* launches);
   void apply(const double* x, double* y);                 // device pointers, length nLoc; x is not modified
   void applyQ(const double* x, double* y);                // y = Z E^-1 Z^T x
-  void mult(const double* x, double* y) { sell_spmv(A, x, y, st); }
+  void mult(const double* x, double* y);                  // y = A x on the owned rows (ghosts of x refreshed first)
+  void mult_sub(const double* x, const double* b, double* y);  // y = b - A x
   void initial_guess(const double* b, double* x0);        // x0 = Q b (efficient hybrid) or 0 (src/geneo.cpp:1601-1607)
   KspResult solve_cg(const double* b, double* x, double rtol, double atol, double dtol, int maxIt);
   KspResult solve_gmres(const double* b, double* x, double rtol, double atol, double dtol, int maxIt, int restart);

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_extend_add(const WorkItem* __restrict__
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const FrontDev P = fr[F.parent];
-  const int m = F.h - F.k, pk = P.k, ph = P.h, pm = P.h - P.k;
+  const int m = F.h - F.k, pk = P.k, ph = P.ld, pm = P.h - P.k;
   const double* Uc = Uchild + F.uOff;
   double* Up = Upar + P.uOff;
   double* Lp = L + P.lOff;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256, 1) k_diag_invert(const WorkItem* __restri
   __shared__ double cbuf[2][128];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
-  const int k = F.k, h = F.h;
+  const int k = F.k, h = F.ld;
   double* P = L + F.lOff;
   const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
   double a[8][8];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) k_copy_panel(const WorkItem* __restrict__
                                                     const double* __restrict__ L, double* __restrict__ W) {
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
-  const int m = F.h - F.k, k = F.k, h = F.h;
+  const int m = F.h - F.k, k = F.k, h = F.ld;
   const double* src = L + F.lOff + k;
   double* dst = W + F.wOff;
   const int r1 = min(m, (it.a + 1) * COPY_ROWS);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_panel(const WorkItem* __restri
   __shared__ double sA[2 * KC * SLD], sB[2 * KC * SLD];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
-  const int m = F.h - F.k, k = F.k, h = F.h;
+  const int m = F.h - F.k, k = F.k, h = F.ld;
   double* P = L + F.lOff;
   // L21[ti rows, tj cols] = W[ti rows, :] * Dinv[tj rows, :]^T   (Dinv symmetric)
   gemm_tile_nt(W + F.wOff + it.a * TS, m, min(TS, m - it.a * TS), P + it.b * TS, h, min(TS, k - it.b * TS), k,
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_schur(const WorkItem* __restri
   __shared__ double sA[2 * KC * SLD], sB[2 * KC * SLD];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
-  const int m = F.h - F.k, k = F.k, h = F.h;
+  const int m = F.h - F.k, k = F.k, h = F.ld;
   // U[ti, tj] -= L21[ti rows, :] * W[tj rows, :]^T   (lower triangle of tiles only)
   gemm_tile_nt(L + F.lOff + k + it.a * TS, h, min(TS, m - it.a * TS), W + F.wOff + it.b * TS, m,
                min(TS, m - it.b * TS), k, U + F.uOff + it.a * TS + (size_t)it.b * TS * m, m, 1, sA, sB);
@@ -272,135 +272,157 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_schur(const WorkItem* __restri
 
 // =====================================================================================================================
 // Solve: ONE persistent cooperative kernel per solve over a FOREST of factors (all local subdomains at once).
-// Work items are (subdomain, front, 32-row block, 32-column chunk); a warp streams its 8 KB (fwd / diag) or 32 KB (bwd)
-// tile of the factor with coalesced 256-byte loads; levels are separated by grid-wide barriers instead of kernel
-// launches, so a whole preconditioner application costs one launch and 2*levels+2 barriers.
+//
+//   forward + diagonal (fused):  [ y1 ; x2 ] (+,-)= P[:, c0:c1] * x1[c0:c1]   over ALL h rows of the panel: the first k rows
+//                                are D^-1 (-> Y += ...), the rest are L21 (-> X[rows] -= ...): one uniform GEMV stream.
+//   backward:                    y1[c0:c1] -= L21[:, c0:c1]^T * y2
+//
+// A work item is (subdomain, front, row tile, 32-column chunk).  A warp streams its tile with 16-byte loads (2 rows per
+// lane; panels have an even leading dimension), 8..32 independent loads in flight per lane, so that a few warps per SM
+// already cover the HBM latency-bandwidth product.  The backward (transposed) product keeps one accumulator per column
+// and finishes with a 31-shuffle butterfly transpose-reduction instead of 32 separate warp reductions.
+// Levels are separated by grid-wide barriers instead of kernel launches: one launch and 2*levels barriers per solve.
 // =====================================================================================================================
 constexpr int SOLVE_COLS = 32;
+constexpr int FWD_ROWS = 64;
 constexpr int BWD_ROWS = 128;
+constexpr int SOLVE_THREADS = 512;
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 template <int NR>
-__device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it, double* __restrict__ X, int ldx, int lane) {
+__device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it, double* __restrict__ X,
+                                         double* __restrict__ Y, int ldx, int lane) {
   const FrontDev F = S.fronts[it.f];
-  const int k = F.k, h = F.h, m = h - k;
-  const int r = it.rb * 32 + lane;
-  const bool ok = r < m;
-  const int c0 = it.cb * SOLVE_COLS, c1 = min(k, c0 + SOLVE_COLS);
-  const double* Lp = S.L + F.lOff + k + (ok ? r : 0);
+  const int k = F.k, h = F.h, ld = F.ld;
+  const int c0 = it.cb * SOLVE_COLS, nc = min(SOLVE_COLS, k - c0);
+  const int r0 = it.rb * FWD_ROWS + 2 * lane;  // panel rows r0, r0+1 (even: 16-byte aligned)
   const int col0 = S.rowIdx[F.rowOff];
-  const double* x1 = X + (size_t)(S.xoff + col0) * ldx;
-  double acc[NR];
+  const double* x1 = X + (size_t)(S.xoff + col0 + c0) * ldx;
+  const double* Lp = S.L + F.lOff + (size_t)c0 * ld + (r0 < h ? r0 : 0);
+  double xv = 0.;
+  if (NR == 1) xv = lane < nc ? x1[lane] : 0.;
+  double a0[NR], a1[NR];
 #pragma unroll
-  for (int j = 0; j < NR; j++) acc[j] = 0.;
-  int c = c0;
-  for (; c + 4 <= c1; c += 4) {
-    const double l0 = Lp[(size_t)c * h], l1 = Lp[(size_t)(c + 1) * h], l2 = Lp[(size_t)(c + 2) * h], l3 = Lp[(size_t)(c + 3) * h];
+  for (int j = 0; j < NR; j++) a0[j] = a1[j] = 0.;
+  int c = 0;
+  for (; c + 8 <= nc; c += 8) {
+    double2 v[8];
 #pragma unroll
-    for (int j = 0; j < NR; j++) {
-      acc[j] += l0 * x1[(size_t)c * ldx + j];
-      acc[j] += l1 * x1[(size_t)(c + 1) * ldx + j];
-      acc[j] += l2 * x1[(size_t)(c + 2) * ldx + j];
-      acc[j] += l3 * x1[(size_t)(c + 3) * ldx + j];
+    for (int u = 0; u < 8; u++) v[u] = ldg2(Lp + (size_t)(c + u) * ld);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (NR == 1) {
+        const double xc = __shfl_sync(0xffffffffu, xv, c + u);
+        a0[0] += v[u].x * xc;
+        a1[0] += v[u].y * xc;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+          const double xc = x1[(size_t)(c + u) * ldx + j];
+          a0[j] += v[u].x * xc;
+          a1[j] += v[u].y * xc;
+        }
+      }
     }
   }
-  for (; c < c1; c++) {
-    const double l0 = Lp[(size_t)c * h];
+  for (; c < nc; c++) {
+    const double2 v = ldg2(Lp + (size_t)c * ld);
+    if (NR == 1) {
+      const double xc = __shfl_sync(0xffffffffu, xv, c);
+      a0[0] += v.x * xc;
+      a1[0] += v.y * xc;
+    } else {
 #pragma unroll
-    for (int j = 0; j < NR; j++) acc[j] += l0 * x1[(size_t)c * ldx + j];
+      for (int j = 0; j < NR; j++) {
+        const double xc = x1[(size_t)c * ldx + j];
+        a0[j] += v.x * xc;
+        a1[j] += v.y * xc;
+      }
+    }
   }
-  if (ok) {
-    const int row = S.rowIdx[F.rowOff + k + r];
 #pragma unroll
-    for (int j = 0; j < NR; j++) atomicAdd(&X[(size_t)(S.xoff + row) * ldx + j], -acc[j]);
+  for (int e = 0; e < 2; e++) {
+    const int r = r0 + e;
+    if (r >= h) continue;
+    if (r < k) {  // D^-1 rows
+      double* dst = Y + (size_t)(S.xoff + col0 + r) * ldx;
+#pragma unroll
+      for (int j = 0; j < NR; j++) atomicAdd(dst + j, e ? a1[j] : a0[j]);
+    } else {      // L21 rows
+      double* dst = X + (size_t)(S.xoff + S.rowIdx[F.rowOff + r]) * ldx;
+#pragma unroll
+      for (int j = 0; j < NR; j++) atomicAdd(dst + j, -(e ? a1[j] : a0[j]));
+    }
   }
 }
 
-template <int NR>
-__device__ __forceinline__ void dsolve_item(const ForestSub& S, const ForestItem it, const double* __restrict__ X,
-                                            double* __restrict__ Y, int ldx, int lane) {
-  const FrontDev F = S.fronts[it.f];
-  const int k = F.k, h = F.h;
-  const int r = it.rb * 32 + lane;
-  const bool ok = r < k;
-  const int c0 = it.cb * SOLVE_COLS, c1 = min(k, c0 + SOLVE_COLS);
-  const double* Dp = S.L + F.lOff + (ok ? r : 0);
-  const int col0 = S.rowIdx[F.rowOff];
-  const double* x1 = X + (size_t)(S.xoff + col0) * ldx;
-  double acc[NR];
-#pragma unroll
-  for (int j = 0; j < NR; j++) acc[j] = 0.;
-  int c = c0;
-  for (; c + 4 <= c1; c += 4) {
-    const double l0 = Dp[(size_t)c * h], l1 = Dp[(size_t)(c + 1) * h], l2 = Dp[(size_t)(c + 2) * h], l3 = Dp[(size_t)(c + 3) * h];
-#pragma unroll
-    for (int j = 0; j < NR; j++) {
-      acc[j] += l0 * x1[(size_t)c * ldx + j];
-      acc[j] += l1 * x1[(size_t)(c + 1) * ldx + j];
-      acc[j] += l2 * x1[(size_t)(c + 2) * ldx + j];
-      acc[j] += l3 * x1[(size_t)(c + 3) * ldx + j];
-    }
-  }
-  for (; c < c1; c++) {
-    const double l0 = Dp[(size_t)c * h];
-#pragma unroll
-    for (int j = 0; j < NR; j++) acc[j] += l0 * x1[(size_t)c * ldx + j];
-  }
-  if (ok) {
-#pragma unroll
-    for (int j = 0; j < NR; j++) atomicAdd(&Y[(size_t)(S.xoff + col0 + r) * ldx + j], acc[j]);
-  }
-}
-
+// transposed product: one accumulator per (column, rhs) pair, CP = 32 / NR columns per pass
 template <int NR>
 __device__ __forceinline__ void bwd_item(const ForestSub& S, const ForestItem it, double* __restrict__ Y, int ldx, int lane) {
+  constexpr int CP = 32 / NR;
   const FrontDev F = S.fronts[it.f];
-  const int k = F.k, h = F.h, m = h - k;
+  const int k = F.k, h = F.h, ld = F.ld;
   const int col0 = S.rowIdx[F.rowOff];
-  const int c0 = it.cb * SOLVE_COLS, c1 = min(k, c0 + SOLVE_COLS);
-  const double* Lp = S.L + F.lOff + k;
-  double xb[4][NR];
-  int rr[4];
+  const int c0 = it.cb * SOLVE_COLS, nc = min(SOLVE_COLS, k - c0);
+  const int rbase = (k & ~1) + it.rb * BWD_ROWS + 2 * lane;  // even panel row; rows < k are masked out through y = 0
+  double y0[2][NR], y1[2][NR];
+  const double* Lt[2];
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int r = it.rb * BWD_ROWS + q * 32 + lane;
-    rr[q] = r < m ? r : -1;
-    const int row = r < m ? S.rowIdx[F.rowOff + k + r] : 0;
-#pragma unroll
-    for (int j = 0; j < NR; j++) xb[q][j] = r < m ? Y[(size_t)(S.xoff + row) * ldx + j] : 0.;
-  }
-  for (int c = c0; c < c1; c++) {
-    double p[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++) p[j] = 0.;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const double l0 = rr[q] >= 0 ? Lp[rr[q] + (size_t)c * h] : 0.;
-#pragma unroll
-      for (int j = 0; j < NR; j++) p[j] += l0 * xb[q][j];
-    }
+  for (int t = 0; t < 2; t++) {
+    const int r = rbase + t * 64;
+    const bool ok0 = r >= k && r < h, ok1 = r + 1 >= k && r + 1 < h;
+    const int row0 = ok0 ? S.rowIdx[F.rowOff + r] : 0, row1 = ok1 ? S.rowIdx[F.rowOff + r + 1] : 0;
 #pragma unroll
     for (int j = 0; j < NR; j++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
+      y0[t][j] = ok0 ? Y[(size_t)(S.xoff + row0) * ldx + j] : 0.;
+      y1[t][j] = ok1 ? Y[(size_t)(S.xoff + row1) * ldx + j] : 0.;
     }
-    if (lane == 0) {
+    Lt[t] = S.L + F.lOff + (size_t)c0 * ld + (r < h ? r : 0);
+  }
+  for (int cp = 0; cp < nc; cp += CP) {
+    double acc[32];
 #pragma unroll
-      for (int j = 0; j < NR; j++) atomicAdd(&Y[(size_t)(S.xoff + col0 + c) * ldx + j], -p[j]);
+    for (int q = 0; q < 32; q++) acc[q] = 0.;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+#pragma unroll
+      for (int cc = 0; cc < CP; cc++) {
+        if (cp + cc < nc) {  // warp-uniform
+          const double2 v = ldg2(Lt[t] + (size_t)(cp + cc) * ld);
+#pragma unroll
+          for (int j = 0; j < NR; j++) acc[cc * NR + j] += v.x * y0[t][j] + v.y * y1[t][j];
+        }
+      }
     }
+    // butterfly transpose-reduction: lane q ends up with the warp-wide sum of acc[q]
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; i++) {
+        const double send = upper ? acc[i] : acc[i + off];
+        const double keep = upper ? acc[i + off] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const int cc = lane / NR, j = lane % NR;
+    if (cp + cc < nc) atomicAdd(&Y[(size_t)(S.xoff + col0 + c0 + cp + cc) * ldx + j], -acc[0]);
   }
 }
 
 template <int NR>
-__global__ void __launch_bounds__(NR <= 2 ? 1024 : 512) k_solve_forest(const ForestSub* __restrict__ subs, const ForestItem* __restrict__ items,
-                                                      const int64_t* __restrict__ ranges, int nlev, int64_t ntot,
-                                                      double* __restrict__ X, double* __restrict__ Y, int ldx) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+k_solve_forest(const ForestSub* __restrict__ subs, const ForestItem* __restrict__ items, const int64_t* __restrict__ ranges,
+               int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y, int ldx) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  // Y = 0 (the diagonal solve accumulates into it); visible to everyone after the first barrier
+  // Y = 0 (the forward sweep accumulates D^-1 x into it); visible to everyone after the first barrier
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntot * NR; t += (int64_t)gridDim.x * blockDim.x)
     Y[(t / NR) * ldx + (t % NR)] = 0.;
+  grid.sync();
   const int64_t* fwdOff = ranges;
   const int64_t* fwdCnt = ranges + nlev;
   const int64_t* bwdOff = ranges + 2 * nlev;
@@ -409,15 +431,7 @@ __global__ void __launch_bounds__(NR <= 2 ? 1024 : 512) k_solve_forest(const For
     const int64_t off = fwdOff[l], cnt = fwdCnt[l];
     for (int64_t i = gw; i < cnt; i += nw) {
       const ForestItem it = items[off + i];
-      fwd_item<NR>(subs[it.sub], it, X, ldx, lane);
-    }
-    grid.sync();
-  }
-  {
-    const int64_t off = ranges[4 * nlev], cnt = ranges[4 * nlev + 1];
-    for (int64_t i = gw; i < cnt; i += nw) {
-      const ForestItem it = items[off + i];
-      dsolve_item<NR>(subs[it.sub], it, X, Y, ldx, lane);
+      fwd_item<NR>(subs[it.sub], it, X, Y, ldx, lane);
     }
     grid.sync();
   }
@@ -454,7 +468,7 @@ void LdltPlan::build_device() {
   std::vector<FrontDev> fd(nf);
   for (int f = 0; f < nf; f++) {
     const Front& F = sym.fronts[f];
-    fd[f] = FrontDev{F.lOff, F.uOff, F.wOff, F.rowOff, F.relOff, F.k, F.h, F.parent, F.nchild};
+    fd[f] = FrontDev{F.lOff, F.uOff, F.wOff, F.rowOff, F.relOff, F.k, F.h, F.ld, F.parent, F.nchild};
   }
   std::vector<WorkItem> items;
   auto begin = [&](Range& r) { r.off = (int64_t)items.size(); };
@@ -580,8 +594,8 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   ntot = 0;
   for (int s = 0; s < ns; s++) { nlev = std::max(nlev, plans[s]->sym.nlevels); ntot = std::max<int64_t>(ntot, xoff[s] + plans[s]->sym.n); }
   std::vector<ForestItem> items;
-  std::vector<int64_t> ranges(4 * (size_t)nlev + 2, 0);
-  for (int l = 0; l < nlev; l++) {
+  std::vector<int64_t> ranges(4 * (size_t)nlev, 0);
+  for (int l = 0; l < nlev; l++) {  // forward + diagonal: every row of the panel
     ranges[l] = (int64_t)items.size();
     for (int s = 0; s < ns; s++) {
       const Symbolic& S = plans[s]->sym;
@@ -589,13 +603,13 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
       for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
         const int f = S.levelFronts[t];
         const Front& F = S.fronts[f];
-        for (int rb = 0; rb * 32 < F.m(); rb++)
+        for (int rb = 0; rb * FWD_ROWS < F.h; rb++)
           for (int cb = 0; cb * SOLVE_COLS < F.k; cb++) items.push_back(ForestItem{s, f, rb, cb});
       }
     }
     ranges[nlev + l] = (int64_t)items.size() - ranges[l];
   }
-  for (int l = 0; l < nlev; l++) {
+  for (int l = 0; l < nlev; l++) {  // backward: the L21 rows, tiles start at the even row k & ~1
     ranges[2 * nlev + l] = (int64_t)items.size();
     for (int s = 0; s < ns; s++) {
       const Symbolic& S = plans[s]->sym;
@@ -603,20 +617,14 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
       for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
         const int f = S.levelFronts[t];
         const Front& F = S.fronts[f];
-        for (int rb = 0; rb * BWD_ROWS < F.m(); rb++)
+        if (F.m() == 0) continue;
+        const int span = F.h - (F.k & ~1);
+        for (int rb = 0; rb * BWD_ROWS < span; rb++)
           for (int cb = 0; cb * SOLVE_COLS < F.k; cb++) items.push_back(ForestItem{s, f, rb, cb});
       }
     }
     ranges[3 * nlev + l] = (int64_t)items.size() - ranges[2 * nlev + l];
   }
-  ranges[4 * nlev] = (int64_t)items.size();
-  for (int s = 0; s < ns; s++) {
-    const Symbolic& S = plans[s]->sym;
-    for (int f = 0; f < (int)S.fronts.size(); f++)
-      for (int rb = 0; rb * 32 < S.fronts[f].k; rb++)
-        for (int cb = 0; cb * SOLVE_COLS < S.fronts[f].k; cb++) items.push_back(ForestItem{s, f, rb, cb});
-  }
-  ranges[4 * nlev + 1] = (int64_t)items.size() - ranges[4 * nlev];
   dItems.upload(items);
   dRanges.upload(ranges);
   hSubs.assign(ns, ForestSub{nullptr, nullptr, nullptr, 0});
@@ -629,8 +637,7 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   const void* fns[4] = {(const void*)k_solve_forest<1>, (const void*)k_solve_forest<2>, (const void*)k_solve_forest<4>, (const void*)k_solve_forest<8>};
   for (int q = 0; q < 4; q++) {
     int nb = 0;
-    const int threads = q <= 1 ? 1024 : 512;  // few, fat CTAs: the grid barrier cost grows with the number of CTAs
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fns[q], threads, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fns[q], SOLVE_THREADS, 0));
     gridBlocks[q] = std::max(1, nb) * nsm;
   }
 }
@@ -661,7 +668,7 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
     default: GENEO_CHECK(false, "nrhs chunk must be 1, 2, 4 or 8");
   }
   ++g_kernel_launches;
-  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(q <= 1 ? 1024 : 512), args, 0, st));
+  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(SOLVE_THREADS), args, 0, st));
 }
 
 void LdltFactor::solve_permuted(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const {

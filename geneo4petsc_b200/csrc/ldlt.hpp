@@ -9,7 +9,7 @@ namespace geneo {
 
 struct FrontDev {  // device copy of what the kernels need from symbolic.hpp:Front
   int64_t lOff, uOff, wOff, rowOff, relOff;
-  int k, h, parent, nchild;
+  int k, h, ld, parent, nchild;
 };
 
 struct WorkItem { int f, a, b; };

@@ -345,6 +345,8 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
     for (int p = 0; p < nbPart; p++)
       for (int g : d.subs[p].nodes) n2d[pos[g]++] = p;
   }
+  d.nodeSubPtr = n2dPtr;
+  d.nodeSub = n2d;
   for (int p = 0; p < nbPart; p++) {
     Subdomain& s = d.subs[p];
     const int nl = (int)s.nodes.size();
@@ -426,6 +428,82 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
   for (auto& e : errs) GENEO_CHECK(e.empty(), e);
   d.nnzNeuTotal = 0;
   for (int p : mine) d.nnzNeuTotal += d.subs[p].aNeu.nnz();
+}
+
+void build_rank_layout(const Mesh& m, const Decomposition& d, const std::vector<int>& subRank, int rank, int world,
+                       RankLayout& L) {
+  const int nn = m.nbNode, ne = m.nbElem();
+  GENEO_CHECK((int)subRank.size() == d.nbPart, "layout: one rank per subdomain expected");
+  GENEO_CHECK(rank >= 0 && rank < world, "layout: bad rank");
+  L = RankLayout();
+  L.rank = rank; L.world = world; L.nbNode = nn; L.subRank = subRank;
+  auto ownerRank = [&](int g) -> int {  // rank of the lowest-numbered subdomain containing g (-1: in no subdomain)
+    return d.nodeSubPtr[g] < d.nodeSubPtr[g + 1] ? subRank[d.nodeSub[d.nodeSubPtr[g]]] : -1;
+  };
+  // 1 = owned, 2 = ghost
+  std::vector<char> flag(nn, 0);
+  for (int p = 0; p < d.nbPart; p++) {
+    if (subRank[p] != rank) continue;
+    for (int g : d.subs[p].nodes) flag[g] = (ownerRank(g) == rank) ? 1 : 2;
+  }
+  // node -> elements, for the owned rows only
+  std::vector<int64_t> n2ePtr(nn + 1, 0);
+  for (int e = 0; e < ne; e++)
+    for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++)
+      if (flag[m.elemIdx[t]] == 1) n2ePtr[m.elemIdx[t] + 1]++;
+  for (int i = 0; i < nn; i++) n2ePtr[i + 1] += n2ePtr[i];
+  std::vector<int> n2e(n2ePtr[nn]);
+  {
+    std::vector<int64_t> pos(n2ePtr.begin(), n2ePtr.end() - 1);
+    for (int e = 0; e < ne; e++)
+      for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++)
+        if (flag[m.elemIdx[t]] == 1) n2e[pos[m.elemIdx[t]]++] = e;
+  }
+  // columns of owned rows that are in none of the rank's subdomains become ghosts too
+  for (int g = 0; g < nn; g++) {
+    if (flag[g] != 1) continue;
+    for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
+      const int e = n2e[u];
+      for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++)
+        if (flag[m.elemIdx[t]] == 0) flag[m.elemIdx[t]] = 2;
+    }
+  }
+  std::vector<std::vector<int>> byOwner(world);
+  for (int g = 0; g < nn; g++) {
+    if (flag[g] == 1) L.owned.push_back(g);
+    else if (flag[g] == 2) {
+      const int q = ownerRank(g);
+      GENEO_CHECK(q >= 0 && q < world && q != rank, "layout: ghost node without a remote owner");
+      byOwner[q].push_back(g);
+    }
+  }
+  L.ghostPtr.assign(world + 1, 0);
+  for (int q = 0; q < world; q++) {
+    L.ghost.insert(L.ghost.end(), byOwner[q].begin(), byOwner[q].end());
+    L.ghostPtr[q + 1] = (int64_t)L.ghost.size();
+  }
+  L.g2l.assign(nn, -1);
+  for (int i = 0; i < L.nOwn(); i++) L.g2l[L.owned[i]] = i;
+  for (int i = 0; i < L.nGhost(); i++) L.g2l[L.ghost[i]] = L.nOwn() + i;
+  L.sendIdx.assign(world, std::vector<int>());
+  // owned rows of A = sum over ALL elements touching the node, full weight (== sum_i R_i^T A_neu,i R_i, SURVEY.md 8a note 1)
+  std::vector<int> rows, cols;
+  std::vector<double> vals;
+  for (int i = 0; i < L.nOwn(); i++) {
+    const int g = L.owned[i];
+    for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
+      const int e = n2e[u];
+      const int64_t b = m.elemPtr[e];
+      const int k = (int)(m.elemPtr[e + 1] - b);
+      const double* K = &m.matVal[m.matPtr[e]];
+      for (int a = 0; a < k; a++) {
+        if (m.elemIdx[b + a] != g) continue;
+        for (int j = 0; j < k; j++) { rows.push_back(i); cols.push_back(L.g2l[m.elemIdx[b + j]]); vals.push_back(K[a * k + j]); }
+      }
+    }
+  }
+  coo_to_csr(L.nOwn(), rows, cols, vals, L.A);
+  L.A.ncols = L.nOwn() + L.nGhost();
 }
 
 }  // namespace geneo

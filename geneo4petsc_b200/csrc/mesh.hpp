@@ -55,7 +55,30 @@ struct Decomposition {
   std::vector<int> nodeMult, elemMult;
   std::vector<Subdomain> subs;  // ALL subdomains' index sets; matrices only for the ones in `mine`
   int64_t nnzNeuTotal = 0;      // "nnz coefs" of the INFO line (sum over all local matrices)
+  // node -> subdomains containing it (CSR, ascending subdomain id): ownership for the multi-GPU layout
+  std::vector<int64_t> nodeSubPtr;
+  std::vector<int> nodeSub;
 };
+
+// ---- multi-GPU layout (one process per GPU) --------------------------------------------------------------
+// Rank r holds the subdomains p with subRank[p] == r and OWNS the rows of the nodes whose lowest-numbered subdomain it
+// holds (replaces the reference's block-by-index MatCreateIS layout, src/geneo4PETSc.cpp:755).  Local vectors are
+// [owned (ascending global id) | ghosts (grouped by owner rank, ascending global id inside a group)]; ghosts are the
+// non-owned nodes of the rank's subdomains plus the non-owned columns of its owned operator rows.
+struct RankLayout {
+  int rank = 0, world = 1, nbNode = 0;
+  std::vector<int> subRank;
+  std::vector<int> owned, ghost;
+  std::vector<int64_t> ghostPtr;            // [world+1] into ghost, by owner rank
+  std::vector<std::vector<int>> sendIdx;    // per peer: local OWNED indices it needs (set after the request exchange)
+  CsrHost A;                                // owned rows of A = sum_e K_e, local column numbering
+  std::vector<int> g2l;                     // global -> local (-1 when absent); size nbNode
+  int nOwn() const { return (int)owned.size(); }
+  int nGhost() const { return (int)ghost.size(); }
+};
+// The mesh may be a SUB-mesh (global node ids) as long as it holds every element touching a node of the rank's subdomains.
+void build_rank_layout(const Mesh& m, const Decomposition& d, const std::vector<int>& subRank, int rank, int world,
+                       RankLayout& L);
 
 // Build node/element sets, multiplicities, intersections for every subdomain; assemble aNeu/aDir for
 // subdomains p with owner[p] == true (all when owner is empty).

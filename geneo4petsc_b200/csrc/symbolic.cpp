@@ -248,6 +248,7 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
       f.col0 = fFirst[s] + off;
       f.k = std::min(NB, fK[s] - off);
       f.h = hs - off;
+      f.ld = (f.h + 1) & ~1;
       f.rowOff = snRowOff[s] + off;
       f.chain = (p + 1 < np) ? 1 : 0;
       const int id = (int)S.fronts.size();
@@ -299,7 +300,7 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
   for (int f = 0; f < nf; f++) {
     Front& F = S.fronts[f];
     F.lOff = lOff;
-    lOff += (int64_t)F.h * F.k;
+    lOff += (int64_t)F.ld * F.k;
     const double k = F.k, m = F.m();
     S.flops += k * k * k / 3. + m * k * k + m * m * k;
     S.maxK = std::max(S.maxK, F.k);
@@ -341,7 +342,7 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
         pos = F.k + (int)(it - b);
       }
       S.asmSrc.push_back(t);
-      S.asmDst.push_back(F.lOff + pos + (int64_t)(j - F.col0) * F.h);
+      S.asmDst.push_back(F.lOff + pos + (int64_t)(j - F.col0) * F.ld);
     }
   }
   lap("asm map");

@@ -21,12 +21,13 @@ struct Front {
   int col0 = 0;        // first pivot column (permuted numbering)
   int k = 0;           // pivot columns (<= NB)
   int h = 0;           // rows of the panel = k + m
+  int ld = 0;          // leading dimension of the panel in the factor array: h rounded up to even (16-byte columns)
   int parent = -1;     // parent front, -1 for a root
   int level = 0;       // schedule level (children are at level-1)
   int chain = 0;       // 1 if the parent is the next panel of the same supernode (identity relative indices)
   int nchild = 0;
   int64_t rowOff = 0;  // into Symbolic::rowIdx (h entries, ascending, first k = own columns)
-  int64_t lOff = 0;    // into the factor value array (h*k doubles)
+  int64_t lOff = 0;    // into the factor value array (ld*k doubles)
   int64_t uOff = -1;   // into the ping-pong update arena of parity (level & 1); m*m doubles, ld = m
   int64_t wOff = -1;   // into the per-level scratch holding the unscaled panel F21 (m*k doubles, ld = m)
   int64_t relOff = -1; // into Symbolic::rel (m entries: position of update row i in the parent's row list); -1 if chain

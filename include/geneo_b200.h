@@ -75,6 +75,8 @@ int geneo_pc_refactor(geneo_pc_t pc);
 int geneo_pc_kernel_time(geneo_pc_t pc, double* ms, int64_t* launches);
 /* process-wide counters: {kernel launches, host->device bytes, device->host bytes} issued by this library so far */
 int geneo_counters(int64_t c[3]);
+/* GENEO_PROFILE=1 in the environment: per-launch-site CUDA-event times accumulated so far -> CSV, then reset */
+int geneo_profile_dump(const char* path);
 int geneo_pc_destroy(geneo_pc_t pc);                                         /* destroyGenEOPC, :2217-2243           */
 /* geneoContext fields the driver reads (src/geneo4PETSc.cpp:928-986, 1123-1225) */
 int geneo_pc_name(geneo_pc_t pc, char* buf, int cap);                        /* gCtx->name                           */
@@ -109,6 +111,30 @@ int geneo_ksp_solve_device(geneo_pc_t pc, const char* ksp, const double* db, dou
 const char* geneo_ksp_reason_name(int reason);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU (replaces the MPI layer under PETSc VecScatter / MatMult(MATIS) / VecDot:
+ * src/geneo.cpp:1850-1852, 1881-1883, 1931-1935; one MPI rank per subdomain at src/geneo4PETSc.cpp:604 becomes
+ * several subdomains per GPU).  Every rank decomposes the SAME partition and assembles only its subdomains; a rank
+ * owns the rows of the nodes whose lowest-numbered subdomain it holds; local vectors are [owned | ghost].
+ * The caller provides the rendezvous (torch.distributed in bench.py/tests): the halo requests (ghost ids grouped by
+ * owner, geneo_layout_get) are exchanged by the caller and fed back through geneo_layout_set_send; the NCCL unique id
+ * of rank 0 (geneo_nccl_unique_id) is broadcast by the caller.  All later calls are collective over the ranks.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct geneo_layout_s* geneo_layout_t;
+/* like geneo_problem_decompose with an explicit partition, assembling matrices only for subRank[p] == rank */
+int geneo_problem_decompose_owned(geneo_problem_t p, int nbPart, int metisDual, int overlap, const int32_t* elemPart,
+                                  const int32_t* nodePart, const int32_t* subRank, int rank);
+int geneo_layout_create(geneo_problem_t p, int rank, int world, const int32_t* subRank, geneo_layout_t* out); /* host only */
+int geneo_layout_destroy(geneo_layout_t l);
+int geneo_layout_sizes(geneo_layout_t l, int64_t out[4] /* nOwn, nGhost, nnz(owned rows of A), world */);
+int geneo_layout_get(geneo_layout_t l, int32_t* owned, int32_t* ghost, int64_t* ghostPtr /* [world+1] */);
+int geneo_layout_matrix(geneo_layout_t l, int64_t* ptr, int32_t* idx, double* val); /* owned rows of A, local columns */
+int geneo_layout_set_send(geneo_layout_t l, int peer, const int32_t* globalIds, int64_t n);
+int geneo_nccl_unique_id(void* out128);
+int geneo_pc_setup_dist(geneo_pc_t pc, geneo_problem_t p, geneo_layout_t l, const void* ncclUid128);
+int geneo_pc_local_sizes(geneo_pc_t pc, int64_t out[2] /* nOwn, nLoc: lengths of the vectors the device entry points take */);
+int geneo_allreduce_sum(geneo_pc_t pc, double* h, int n); /* host array, in place (statistics) */
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Host-only test hooks (no device needed): symbolic analysis of a CSR pattern, dense symmetric eigen-solver
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct geneo_symbolic_s* geneo_symbolic_t;
@@ -117,7 +143,7 @@ int geneo_symbolic_create(int n, const int64_t* ptr, const int32_t* idx, int nb,
 int geneo_symbolic_destroy(geneo_symbolic_t s);
 /* ints = {n, nfronts, nlevels, lSize, uArena, wArena, nRowIdx, nRel, nAsm, nsuper} ; reals = {flops} */
 int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[10], double reals[1]);
-/* fronts: 12 int64 per front = {col0,k,h,parent,level,chain,nchild,rowOff,lOff,uOff,wOff,relOff} */
+/* fronts: 13 int64 per front = {col0,k,h,parent,level,chain,nchild,rowOff,lOff,uOff,wOff,relOff,ld} */
 int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32_t* rowIdx, int32_t* rel, int64_t* asmSrc,
                        int64_t* asmDst);
 int geneo_host_sym_eig(int n, double* a /* row-major in, eigenvectors (columns) out */, double* w);

@@ -3,7 +3,13 @@ the CUDA kernels consume (geneo4petsc_b200/csrc/symbolic.cpp).  Test infrastruct
 relative indices, levels and arena offsets on a CPU-only box."""
 import numpy as np
 
-F_COL0, F_K, F_H, F_PARENT, F_LEVEL, F_CHAIN, F_NCHILD, F_ROWOFF, F_LOFF, F_UOFF, F_WOFF, F_RELOFF = range(12)
+F_COL0, F_K, F_H, F_PARENT, F_LEVEL, F_CHAIN, F_NCHILD, F_ROWOFF, F_LOFF, F_UOFF, F_WOFF, F_RELOFF, F_LD = range(13)
+
+
+def _panel(L, fr, f):
+    """View of panel f: h x k, column-major with leading dimension ld (h rounded up to even)."""
+    k, h, ld = fr[f, F_K], fr[f, F_H], fr[f, F_LD]
+    return L[fr[f, F_LOFF]: fr[f, F_LOFF] + ld * k].reshape(ld, k, order="F")[:h, :]
 
 
 def factorize(sym, vals):
@@ -30,7 +36,7 @@ def factorize(sym, vals):
                 pm = ph - pk
                 U = prev[fr[c, F_UOFF]: fr[c, F_UOFF] + m * m].reshape(m, m, order="F")
                 rel = np.arange(m) if fr[c, F_RELOFF] < 0 else sym.rel[fr[c, F_RELOFF]: fr[c, F_RELOFF] + m]
-                Pp = L[fr[par, F_LOFF]: fr[par, F_LOFF] + ph * pk].reshape(ph, pk, order="F")
+                Pp = _panel(L, fr, par)
                 Up = cur[fr[par, F_UOFF]: fr[par, F_UOFF] + pm * pm].reshape(pm, pm, order="F") if pm > 0 else None
                 for cc in range(m):
                     pc = rel[cc]
@@ -43,7 +49,7 @@ def factorize(sym, vals):
         for f in order[levels[order] == lvl]:
             k, h = fr[f, F_K], fr[f, F_H]
             m = h - k
-            P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+            P = _panel(L, fr, f)
             F11 = np.tril(P[:k, :k]) + np.tril(P[:k, :k], -1).T
             # symmetric sweep (pivot signs = inertia)
             a = F11.copy()
@@ -77,13 +83,13 @@ def solve(sym, L, b):
         k, h = fr[f, F_K], fr[f, F_H]
         if h == k:
             continue
-        P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+        P = _panel(L, fr, f)
         rows = sym.row_idx[fr[f, F_ROWOFF]: fr[f, F_ROWOFF] + h]
         np.subtract.at(x, rows[k:], P[k:, :] @ x[rows[:k]])
     y = np.zeros_like(x)
     for f in range(len(fr)):
         k, h = fr[f, F_K], fr[f, F_H]
-        P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+        P = _panel(L, fr, f)
         rows = sym.row_idx[fr[f, F_ROWOFF]: fr[f, F_ROWOFF] + k]
         assert np.array_equal(rows, np.arange(fr[f, F_COL0], fr[f, F_COL0] + k))
         y[rows] = P[:k, :] @ x[rows]
@@ -91,7 +97,7 @@ def solve(sym, L, b):
         k, h = fr[f, F_K], fr[f, F_H]
         if h == k:
             continue
-        P = L[fr[f, F_LOFF]: fr[f, F_LOFF] + h * k].reshape(h, k, order="F")
+        P = _panel(L, fr, f)
         rows = sym.row_idx[fr[f, F_ROWOFF]: fr[f, F_ROWOFF] + h]
         y[rows[:k]] -= P[k:, :].T @ y[rows[k:]]
     out = np.zeros_like(y)
