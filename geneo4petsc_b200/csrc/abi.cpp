@@ -9,6 +9,7 @@
 #include "dense_host.hpp"
 #include "geneo.hpp"
 
+namespace geneo { int profile_dump(const char* path); }
 using namespace geneo;
 
 struct geneo_problem_s {
@@ -274,7 +275,6 @@ int geneo_allreduce_sum(geneo_pc_t pc, double* h, int n) {
   ABI_CATCH
 }
 
-namespace geneo { int profile_dump(const char* path); }
 int geneo_profile_dump(const char* path) { ABI_TRY ABI_REQ(path, "null argument"); ABI_REQ(profile_dump(path) == 0, "cannot write the profile"); ABI_CATCH }
 
 int geneo_pc_refactor(geneo_pc_t pc) {
