@@ -77,6 +77,25 @@ int geneo_problem_generate(geneo_problem_t p, const char* kind, const char* args
   p->decomposed = false;
   ABI_CATCH
 }
+int geneo_problem_generate_boxed(geneo_problem_t p, const char* kind, const char* args, const int32_t boxK[3],
+                                 const int32_t keepLo[3], const int32_t keepHi[3], int32_t* edge) {
+  ABI_TRY
+  ABI_REQ(p && kind && args && boxK, "null argument");
+  GridGenOptions o;
+  const std::string k(kind);
+  ABI_REQ(k == "laplacian" || k == "heat", "unknown generator (laplacian | heat)");
+  o.heat = (k == "heat");
+  ABI_REQ(parse_gen_args(args, o) == 0, "invalid generator command line");
+  for (int a = 0; a < 3; a++) {
+    o.boxK[a] = boxK[a];
+    if (keepLo && keepHi) { o.keepLo[a] = keepLo[a]; o.keepHi[a] = keepHi[a]; }
+  }
+  generate_grid(o, p->mesh, &p->elemPart);  // the box partition of the generated (sub-)mesh is kept for decompose_owned
+  p->nodePart.clear();
+  p->decomposed = false;
+  if (edge) *edge = grid_edge(o);
+  ABI_CATCH
+}
 int geneo_problem_read_file(geneo_problem_t p, const char* path, double inpEps) {
   ABI_TRY
   ABI_REQ(p && path, "null argument");
@@ -193,12 +212,15 @@ int geneo_problem_decompose_owned(geneo_problem_t p, int nbPart, int metisDual, 
   ABI_TRY
   ABI_REQ(p && p->mesh.nbNode > 0 && subRank, "null argument");
   ABI_REQ(nbPart >= 1, "bad number of partitions");
-  ABI_REQ((metisDual && elemPart) || (!metisDual && nodePart), "decompose_owned needs an explicit partition (identical on every rank)");
+  const bool stored = metisDual && !elemPart && (int)p->elemPart.size() == p->mesh.nbElem();  // from generate_boxed
+  ABI_REQ(stored || (metisDual && elemPart) || (!metisDual && nodePart), "decompose_owned needs an explicit partition (identical on every rank)");
   p->dual = metisDual != 0;
   p->overlap = overlap;
-  p->elemPart.clear(); p->nodePart.clear();
-  if (elemPart) p->elemPart.assign(elemPart, elemPart + p->mesh.nbElem());
-  if (nodePart) p->nodePart.assign(nodePart, nodePart + p->mesh.nbNode);
+  if (!stored) {
+    p->elemPart.clear(); p->nodePart.clear();
+    if (elemPart) p->elemPart.assign(elemPart, elemPart + p->mesh.nbElem());
+    if (nodePart) p->nodePart.assign(nodePart, nodePart + p->mesh.nbNode);
+  }
   std::vector<char> owner(nbPart, 0);
   for (int q = 0; q < nbPart; q++) owner[q] = subRank[q] == rank;
   decompose(p->mesh, nbPart, p->elemPart, p->nodePart, p->dual, overlap, owner, p->dec);

@@ -562,6 +562,7 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
   int nev = 1;  // SLEPc default when nothing is requested
   int est = 0;
   LdltFactor tmp(s.plan);
+  tmp.L = std::move(ws.spareL);  // cudaMalloc/cudaFree of a multi-GB factor per factorization costs more than the kernels
   if (!opt.noSyl) {
     const double t0 = now_s();
     DevBuf<double> vS((size_t)nnz);
@@ -615,6 +616,7 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     lvl2SetupEigTime += dt;
     (tauPb ? lvl2SetupTauEigTime : lvl2SetupGammaEigTime) += dt;
   }
+  ws.spareL = std::move(tmp.L);
   tmp.release();
   // Nicolaides (src/geneo.cpp:897-944): add the constant vector when eigenvalues were kept, none is ~0 and 1 is in ker(A)
   bool addOne = false;

@@ -248,32 +248,49 @@ __global__ void __launch_bounds__(256) k_ts_gram(int n, const double* __restrict
       if (q0 + qg * 4 + e < q) atomicAdd(&G[(size_t)(p0 + pi) * ldg + q0 + qg * 4 + e], acc[e]);
 }
 
-// W[r, j] = beta W[r,j] + alpha sum_p Q[r,p] C[p,j] ; thread per (row, j), j fastest; C tiles of 64 rows in smem
-__global__ void __launch_bounds__(256) k_ts_update(int n, const double* __restrict__ Q, int ldq, int p,
-                                                   const double* __restrict__ C, int ldc, int q, double* __restrict__ W,
-                                                   int ldw, double alpha, double beta, int qpad) {
-  extern __shared__ double sc[];  // [64][qpad]
-  const int rowsPerCta = 256 / qpad;
-  const int j = threadIdx.x % qpad;
-  const int64_t r = (int64_t)blockIdx.x * rowsPerCta + threadIdx.x / qpad;
-  const bool ok = (threadIdx.x / qpad) < rowsPerCta && r < n && j < q;
-  double acc = 0.;
-  for (int pb = 0; pb < p; pb += 64) {
-    const int pc = min(64, p - pb);
-    for (int e = threadIdx.x; e < pc * qpad; e += 256) {
-      const int pp = e / qpad, jj = e % qpad;
-      sc[e] = jj < q ? C[(size_t)(pb + pp) * ldc + jj] : 0.;
-    }
-    __syncthreads();
-    if (ok) {
-      const double* qr = Q + (size_t)r * ldq + pb;
-      for (int pp = 0; pp < pc; pp++) acc += qr[pp] * sc[pp * qpad + j];
-    }
-    __syncthreads();
+// W[r, 0:q] = beta W[r, 0:q] + alpha sum_p Q[r,p] C[p, 0:q],  q <= 8.  One thread per row (128 rows per CTA); Q tiles of
+// 128 rows x 32 columns go through shared memory so that the global reads are coalesced 256-byte row segments and the
+// per-row reads are conflict-free (leading dimension 33); C (p x 8) sits in shared memory and is read as a broadcast.
+constexpr int TSU_ROWS = 128, TSU_COLS = 32;
+__global__ void __launch_bounds__(TSU_ROWS) k_ts_update(int n, const double* __restrict__ Q, int ldq, int p,
+                                                        const double* __restrict__ C, int ldc, int q, double* __restrict__ W,
+                                                        int ldw, double alpha, double beta) {
+  extern __shared__ double sm[];
+  double* sC = sm;                    // [p][8]
+  double* tile = sm + (size_t)p * 8;  // [TSU_ROWS][TSU_COLS + 1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < p * 8; e += TSU_ROWS) {
+    const int pp = e >> 3, jj = e & 7;
+    sC[e] = jj < q ? C[(size_t)pp * ldc + jj] : 0.;
   }
-  if (ok) {
-    double* w = W + (size_t)r * ldw + j;
-    *w = (beta == 0. ? 0. : beta * *w) + alpha * acc;
+  const int64_t r0 = (int64_t)blockIdx.x * TSU_ROWS;
+  double acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = 0.;
+  for (int pb = 0; pb < p; pb += TSU_COLS) {
+    __syncthreads();
+    // warp w loads rows w*32 .. w*32+31 of the tile, lane = column
+#pragma unroll 8
+    for (int rr = 0; rr < 32; rr++) {
+      const int64_t r = r0 + warp * 32 + rr;
+      tile[(warp * 32 + rr) * (TSU_COLS + 1) + lane] = (r < n && pb + lane < p) ? Q[(size_t)r * ldq + pb + lane] : 0.;
+    }
+    __syncthreads();
+    const int pc = min(TSU_COLS, p - pb);
+    const double* trow = tile + tid * (TSU_COLS + 1);
+    for (int pp = 0; pp < pc; pp++) {
+      const double a = trow[pp];
+      const double* c = sC + (size_t)(pb + pp) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] += a * c[j];
+    }
+  }
+  const int64_t r = r0 + tid;
+  if (r < n) {
+    double* w = W + (size_t)r * ldw;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (j < q) w[j] = (beta == 0. ? 0. : beta * w[j]) + alpha * acc[j];
   }
 }
 
@@ -473,13 +490,17 @@ void ts_gram(int n, const double* X, int ldx, int p, const double* Y, int ldy, i
 }
 void ts_update(int n, const double* Q, int ldq, int p, const double* C, int ldc, int q, double* W, int ldw, double alpha,
                double beta, cudaStream_t st) {
-  for (int j0 = 0; j0 < q; j0 += 32) {  // column chunks of <= 32 keep the C tile (64 x 32 doubles) in 16 KB of smem
-    const int qc = std::min(32, q - j0);
-    int qpad = 1;
-    while (qpad < qc) qpad <<= 1;
-    const int rowsPerCta = 256 / qpad;
-    const int grid = (n + rowsPerCta - 1) / rowsPerCta;
-    k_ts_update<<<GENEO_TICK(grid), 256, 64 * qpad * sizeof(double), st>>>(n, Q, ldq, p, C + j0, ldc, qc, W + j0, ldw, alpha, beta, qpad);
+  constexpr int PCHUNK = 192;  // C chunk (192 x 8 doubles) + the Q tile stay below 48 KB of shared memory
+  const int grid = (n + TSU_ROWS - 1) / TSU_ROWS;
+  if (n <= 0) return;
+  for (int j0 = 0; j0 < q; j0 += 8) {
+    const int qc = std::min(8, q - j0);
+    for (int p0 = 0; p0 < std::max(p, 1); p0 += PCHUNK) {
+      const int pc = std::max(0, std::min(PCHUNK, p - p0));
+      const size_t smem = ((size_t)pc * 8 + (size_t)TSU_ROWS * (TSU_COLS + 1)) * sizeof(double);
+      k_ts_update<<<GENEO_TICK(grid), TSU_ROWS, smem, st>>>(n, Q + p0, ldq, pc, C + (size_t)p0 * ldc + j0, ldc, qc, W + j0, ldw, alpha,
+                                                             p0 == 0 ? beta : 1.);
+    }
   }
   CUDA_CHECK(cudaGetLastError());
 }

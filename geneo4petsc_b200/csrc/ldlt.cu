@@ -152,32 +152,35 @@ __global__ void __launch_bounds__(256) k_extend_add(const WorkItem* __restrict__
   }
 }
 
-// One CTA (256 threads) per front.  Thread (ti,tj) owns the 8x8 strided sub-block i = ti+16*ii, j = tj+16*jj of the
-// (padded to 128x128) pivot block in registers.  Symmetric sweep operator: after sweeping every pivot the block holds
-// -F11^-1; the pivots met on the way are the D of the LDL^T factorization (their signs give the inertia).
-__global__ void __launch_bounds__(256, 1) k_diag_invert(const WorkItem* __restrict__ items,
-                                                        const FrontDev* __restrict__ fr, double* __restrict__ L,
-                                                        double pivTol, int* __restrict__ counters) {
-  __shared__ double cbuf[2][128];
+// One CTA (TD*TD threads) per front.  Thread (ti,tj) owns the strided E x E sub-block i = ti+TD*ii, j = tj+TD*jj of the
+// pivot block (padded to KB = TD*E with the identity) in REGISTERS.  Symmetric sweep operator: after sweeping every pivot
+// the block holds -F11^-1; the pivots met on the way are the D of the LDL^T factorization (their signs give the
+// inertia).  Per pivot every element gets ONE fused multiply-add (a -= c_i * (c_j / d)); the pivot row and column are
+// patched afterwards by the few threads that own them.  <128,16>: k <= 128, 256 threads; <32,8>: k <= 32, 64 threads
+// (small fronts are the vast majority: many of them are resident per SM).
+template <int KB, int TD>
+__global__ void __launch_bounds__(TD * TD) k_diag_invert(const WorkItem* __restrict__ items, const FrontDev* __restrict__ fr,
+                                                        double* __restrict__ L, double pivTol, int* __restrict__ counters) {
+  constexpr int E = KB / TD;
+  __shared__ double cbuf[2][KB];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const int k = F.k, h = F.ld;
   double* P = L + F.lOff;
-  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
-  double a[8][8];
+  const int ti = threadIdx.x % TD, tj = threadIdx.x / TD;
+  double a[E][E];
 #pragma unroll
-  for (int ii = 0; ii < 8; ii++)
+  for (int ii = 0; ii < E; ii++)
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int i = ti + 16 * ii, j = tj + 16 * jj;
+    for (int jj = 0; jj < E; jj++) {
+      const int i = ti + TD * ii, j = tj + TD * jj;
       double v = (i == j) ? 1. : 0.;
       if (i < k && j < k) v = (i >= j) ? P[i + (size_t)j * h] : P[j + (size_t)i * h];
       a[ii][jj] = v;
     }
-  // publish column 0
-  if (tj == 0) {
+  if (tj == 0) {  // publish column 0
 #pragma unroll
-    for (int ii = 0; ii < 8; ii++) cbuf[0][ti + 16 * ii] = a[ii][0];
+    for (int ii = 0; ii < E; ii++) cbuf[0][ti + TD * ii] = a[ii][0];
   }
   __syncthreads();
   int neg = 0, pert = 0;
@@ -187,43 +190,51 @@ __global__ void __launch_bounds__(256, 1) k_diag_invert(const WorkItem* __restri
     if (!(fabs(d) >= pivTol)) { d = (d < 0.) ? -pivTol : pivTol; pert++; }
     if (d < 0.) neg++;
     const double rinv = 1. / d;
-    double ci[8], cj[8];
+    double ci[E], cjr[E];
 #pragma unroll
-    for (int q = 0; q < 8; q++) { ci[q] = cb[ti + 16 * q]; cj[q] = cb[tj + 16 * q]; }
+    for (int q = 0; q < E; q++) { ci[q] = cb[ti + TD * q]; cjr[q] = cb[tj + TD * q] * rinv; }
 #pragma unroll
-    for (int ii = 0; ii < 8; ii++) {
-      const int i = ti + 16 * ii;
+    for (int ii = 0; ii < E; ii++)
 #pragma unroll
-      for (int jj = 0; jj < 8; jj++) {
-        const int j = tj + 16 * jj;
-        double v;
-        if (i == p) v = (j == p) ? -rinv : cj[jj] * rinv;
-        else if (j == p) v = ci[ii] * rinv;
-        else v = a[ii][jj] - ci[ii] * cj[jj] * rinv;
-        a[ii][jj] = v;
-      }
+      for (int jj = 0; jj < E; jj++) a[ii][jj] = fma(-ci[ii], cjr[jj], a[ii][jj]);
+    const int pt = p % TD, pq = p / TD;
+    if (ti == pt) {  // row p: a[p][j] = c_j / d  (and the pivot itself: -1/d)
+#pragma unroll
+      for (int ii = 0; ii < E; ii++)
+        if (ii == pq) {
+#pragma unroll
+          for (int jj = 0; jj < E; jj++) a[ii][jj] = (tj + TD * jj == p) ? -rinv : cjr[jj];
+        }
+    }
+    if (tj == pt) {  // column p: a[i][p] = c_i / d
+#pragma unroll
+      for (int jj = 0; jj < E; jj++)
+        if (jj == pq) {
+#pragma unroll
+          for (int ii = 0; ii < E; ii++) a[ii][jj] = (ti + TD * ii == p) ? -rinv : ci[ii] * rinv;
+        }
     }
     // publish column p+1 for the next sweep
     const int pn = p + 1;
-    if (pn < k && tj == (pn & 15)) {
+    if (pn < k && tj == pn % TD) {
       double* nb = cbuf[pn & 1];
-      const int jj = pn >> 4;
+      const int jn = pn / TD;
 #pragma unroll
-      for (int ii = 0; ii < 8; ii++) {
+      for (int ii = 0; ii < E; ii++) {
         double v = 0.;
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-          if (q == jj) v = a[ii][q];
-        nb[ti + 16 * ii] = v;
+        for (int q = 0; q < E; q++)
+          if (q == jn) v = a[ii][q];
+        nb[ti + TD * ii] = v;
       }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int ii = 0; ii < 8; ii++)
+  for (int ii = 0; ii < E; ii++)
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int i = ti + 16 * ii, j = tj + 16 * jj;
+    for (int jj = 0; jj < E; jj++) {
+      const int i = ti + TD * ii, j = tj + TD * jj;
       if (i < k && j < k) P[i + (size_t)j * h] = -a[ii][jj];
     }
   if (threadIdx.x == 0 && (neg | pert)) {
@@ -474,7 +485,7 @@ void LdltPlan::build_device() {
   auto begin = [&](Range& r) { r.off = (int64_t)items.size(); };
   auto end = [&](Range& r) { r.cnt = (int)((int64_t)items.size() - r.off); };
   const int nl = sym.nlevels;
-  eaddItems.resize(nl); diagItems.resize(nl); copyItems.resize(nl); panelItems.resize(nl); schurItems.resize(nl);
+  eaddItems.resize(nl); diagItems.resize(nl); diagSmallItems.resize(nl); copyItems.resize(nl); panelItems.resize(nl); schurItems.resize(nl);
   levelU.assign(nl, 0);
   for (int l = 0; l < nl; l++) {
     const int* lf = &sym.levelFronts[sym.levelPtr[l]];
@@ -495,9 +506,14 @@ void LdltPlan::build_device() {
       }
     }
     end(eaddItems[l]);
-    begin(diagItems[l]);
-    for (int t = 0; t < cnt; t++) items.push_back(WorkItem{lf[t], 0, 0});
+    begin(diagItems[l]);   // pivot blocks wider than 32 columns: 256-thread CTAs
+    for (int t = 0; t < cnt; t++)
+      if (sym.fronts[lf[t]].k > 32) items.push_back(WorkItem{lf[t], 0, 0});
     end(diagItems[l]);
+    begin(diagSmallItems[l]);  // k <= 32: 64-thread CTAs
+    for (int t = 0; t < cnt; t++)
+      if (sym.fronts[lf[t]].k <= 32) items.push_back(WorkItem{lf[t], 0, 0});
+    end(diagSmallItems[l]);
     begin(copyItems[l]);
     for (int t = 0; t < cnt; t++)
       for (int rb = 0; rb * COPY_ROWS < sym.fronts[lf[t]].m(); rb++) items.push_back(WorkItem{lf[t], rb, 0});
@@ -548,8 +564,8 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   FactorStats stats;
   const double t0 = now_s();
   ws.ensure(S);
-  if ((int64_t)L.n != S.lSize) L.alloc((size_t)S.lSize);
-  L.zero(st);
+  if ((int64_t)L.n < S.lSize) L.alloc((size_t)S.lSize);  // a recycled (larger) buffer is fine
+  CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)S.lSize * sizeof(double), st));
   ws.counters.zero(st);
   {
     const int64_t cnt = (int64_t)P.dAsmSrc.n;
@@ -565,7 +581,9 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
     if (P.eaddItems[l].cnt)
       k_extend_add<<<GENEO_TICK(P.eaddItems[l].cnt), 256, 0, st>>>(items + P.eaddItems[l].off, P.dFronts.p, P.dRel.p, L.p, Uprev, Ucur);
     if (P.diagItems[l].cnt)
-      k_diag_invert<<<GENEO_TICK(P.diagItems[l].cnt), 256, 0, st>>>(items + P.diagItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
+      k_diag_invert<128, 16><<<GENEO_TICK(P.diagItems[l].cnt), 256, 0, st>>>(items + P.diagItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
+    if (P.diagSmallItems[l].cnt)
+      k_diag_invert<32, 8><<<GENEO_TICK(P.diagSmallItems[l].cnt), 64, 0, st>>>(items + P.diagSmallItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
     if (P.copyItems[l].cnt)
       k_copy_panel<<<GENEO_TICK(P.copyItems[l].cnt), 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, L.p, ws.w.p);
     if (P.panelItems[l].cnt)
@@ -667,7 +685,7 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
     case 8: fn = (const void*)k_solve_forest<8>; q = 3; break;
     default: GENEO_CHECK(false, "nrhs chunk must be 1, 2, 4 or 8");
   }
-  ++g_kernel_launches;
+  (void)GENEO_TICK(0);
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(SOLVE_THREADS), args, 0, st));
 }
 

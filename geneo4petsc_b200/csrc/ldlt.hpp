@@ -27,7 +27,7 @@ class LdltPlan {
   DevBuf<int64_t> dAsmSrc, dAsmDst;
   DevBuf<WorkItem> dItems;  // all item lists, concatenated
   struct Range { int64_t off = 0; int cnt = 0; };
-  std::vector<Range> eaddItems, diagItems, copyItems, panelItems, schurItems;  // per level (factor)
+  std::vector<Range> eaddItems, diagItems, diagSmallItems, copyItems, panelItems, schurItems;  // per level (factor)
   std::vector<int64_t> levelU;                                                 // doubles of update arena used per level
   DevBuf<int> dPerm;                                                           // new -> old
   size_t plan_bytes() const;
@@ -63,6 +63,7 @@ struct FactorStats { int neg = 0, perturbed = 0; double seconds = 0.; };
 // Shared scratch for numeric factorizations (two ping-pong update arenas + the per-level panel scratch).
 struct LdltWorkspace {
   DevBuf<double> u0, u1, w;
+  DevBuf<double> spareL;  // storage of the transient factors (inertia / shift-invert), recycled between subdomains
   DevBuf<int> counters;  // [0] negative pivots, [1] perturbed pivots
   void ensure(const Symbolic& s);
 };

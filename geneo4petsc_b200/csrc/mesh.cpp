@@ -57,11 +57,16 @@ static inline double kappa1d(int mode, double alpha, double beta, double x) {
   }
 }
 
-void generate_grid(const GridGenOptions& o, Mesh& m) {
+int grid_edge(const GridGenOptions& o) {
   int n = 0;  // grid edge, with the reference's float truncation (laplacian.cpp:101-105)
   if (o.dim == 1) n = o.size * o.weakScaling;
   if (o.dim == 2) n = (int)std::sqrt((double)(o.size * o.size * o.weakScaling));
   if (o.dim == 3) n = (int)std::cbrt((double)(o.size * o.size * o.size * o.weakScaling));
+  return n;
+}
+
+void generate_grid(const GridGenOptions& o, Mesh& m, std::vector<int>* elemPartOut) {
+  const int n = grid_edge(o);
   const int n1 = n, n2 = (o.dim >= 2) ? n : 1, n3 = (o.dim >= 3) ? n : 1;
   int mode = 0;
   double alpha = 0., beta = 1.;
@@ -74,10 +79,23 @@ void generate_grid(const GridGenOptions& o, Mesh& m) {
   GENEO_CHECK(npts < (int64_t)2147483647, "grid too large for 32-bit node ids");
   m.nbNode = (int)npts;
   m.elemPtr.clear(); m.elemIdx.clear(); m.matVal.clear();
-  m.elemPtr.reserve(npts * (o.dim + 0) + n1 * n2 + 1);
-  m.elemIdx.reserve(npts * 2 * o.dim);
-  m.matVal.reserve(npts * 4 * o.dim);
+  const bool sub = o.keepHi[0] >= 0;
+  if (!sub) {
+    m.elemPtr.reserve(npts * (o.dim + 0) + n1 * n2 + 1);
+    m.elemIdx.reserve(npts * 2 * o.dim);
+    m.matVal.reserve(npts * 4 * o.dim);
+  }
   m.elemPtr.push_back(0);
+  if (elemPartOut) elemPartOut->clear();
+  const int nn[3] = {n1, n2, n3};
+  auto inside = [&](int a, int b, int c) {
+    return !sub || (a >= o.keepLo[0] && a < o.keepHi[0] && b >= o.keepLo[1] && b < o.keepHi[1] && c >= o.keepLo[2] && c < o.keepHi[2]);
+  };
+  auto boxOf = [&](int a, int b, int c) {
+    const int K1 = std::max(1, o.boxK[0]), K2 = std::max(1, o.boxK[1]), K3 = std::max(1, o.boxK[2]);
+    const int b1 = (int)(((int64_t)a * K1) / nn[0]), b2 = (int)(((int64_t)b * K2) / nn[1]), b3 = (int)(((int64_t)c * K3) / nn[2]);
+    return b1 + K1 * (b2 + K2 * b3);
+  };
   std::vector<double> k1(n1), k2(n2), k3(n3);
   for (int i = 0; i < n1; i++) k1[i] = kappa1d(mode, alpha, beta, (double)i);
   for (int i = 0; i < n2; i++) k2[i] = kappa1d(mode, alpha, beta, (double)i);
@@ -104,12 +122,19 @@ void generate_grid(const GridGenOptions& o, Mesh& m) {
       for (int d1 = 0; d1 < n1; d1++) {
         const int c = d1 + n1 * d2 + n1 * n2 * d3;
         const double kappa = k1[d1] * k2[d2] * k3[d3];
-        if (o.dim == 1 && d1 == 0) add(c, -1, kappa);
-        if (d1 + 1 < n1) add(c, c + 1, kappa);
-        if (o.dim == 2 && d2 == 0) add(c, -1, kappa);
-        if (d2 + 1 < n2) add(c, c + n1, kappa);
-        if (o.dim == 3 && d3 == 0) add(c, -1, kappa);
-        if (d3 + 1 < n3) add(c, c + n1 * n2, kappa);
+        const bool inC = inside(d1, d2, d3);
+        const int box = elemPartOut ? boxOf(d1, d2, d3) : 0;
+        auto emit = [&](int nb, bool keep) {
+          if (!keep) return;
+          add(c, nb, kappa);
+          if (elemPartOut) elemPartOut->push_back(box);
+        };
+        if (o.dim == 1 && d1 == 0) emit(-1, inC);
+        if (d1 + 1 < n1) emit(c + 1, inC || inside(d1 + 1, d2, d3));
+        if (o.dim == 2 && d2 == 0) emit(-1, inC);
+        if (d2 + 1 < n2) emit(c + n1, inC || inside(d1, d2 + 1, d3));
+        if (o.dim == 3 && d3 == 0) emit(-1, inC);
+        if (d3 + 1 < n3) emit(c + n1 * n2, inC || inside(d1, d2, d3 + 1));
       }
   m.finalize();
 }

@@ -31,9 +31,16 @@ struct GridGenOptions {
   std::string kappaInterp;  // "", "lin", "quad", "minmax"
   bool heat = false;
   double lbd = 1.0, dt = 0.1;
+  // Box partition (multi-GPU runs, where METIS on the global mesh does not fit a rank): boxK[a] boxes along axis a,
+  // element -> box of its first (lower) node.  0 = no box partition.
+  int boxK[3] = {0, 0, 0};
+  // Sub-mesh: keep only the elements with a node inside [keepLo, keepHi) (node coordinates); keepHi[0] < 0 = everything.
+  // Node ids stay GLOBAL, so that every rank numbers nodes and subdomains identically.
+  int keepLo[3] = {0, 0, 0}, keepHi[3] = {-1, -1, -1};
 };
 int parse_gen_args(const std::string& args, GridGenOptions& o);  // same "--size S --dim D ..." grammar
-void generate_grid(const GridGenOptions& o, Mesh& m);
+void generate_grid(const GridGenOptions& o, Mesh& m, std::vector<int>* elemPartOut = nullptr);
+int grid_edge(const GridGenOptions& o);  // edge length incl. the reference's weak-scaling float truncation
 int read_input_file(const std::string& path, double inpEps, Mesh& m);             // text format A
 int read_rhs_file(const std::string& path, int n, std::vector<double>& b);        // text format B
 

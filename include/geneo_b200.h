@@ -120,6 +120,11 @@ const char* geneo_ksp_reason_name(int reason);
  * of rank 0 (geneo_nccl_unique_id) is broadcast by the caller.  All later calls are collective over the ranks.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct geneo_layout_s* geneo_layout_t;
+/* Structured generator + BOX partition (boxK boxes per axis, element -> box of its lower node) for runs where METIS on
+ * the global mesh does not fit one rank; optionally only the SUB-mesh with a node inside [keepLo, keepHi) (node
+ * coordinates, global node ids kept).  The partition is stored in the problem (elemPart = NULL in decompose_owned). */
+int geneo_problem_generate_boxed(geneo_problem_t p, const char* kind, const char* args, const int32_t boxK[3],
+                                 const int32_t keepLo[3] /* may be NULL */, const int32_t keepHi[3], int32_t* edge);
 /* like geneo_problem_decompose with an explicit partition, assembling matrices only for subRank[p] == rank */
 int geneo_problem_decompose_owned(geneo_problem_t p, int nbPart, int metisDual, int overlap, const int32_t* elemPart,
                                   const int32_t* nodePart, const int32_t* subRank, int rank);
