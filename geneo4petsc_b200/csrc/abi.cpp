@@ -468,7 +468,7 @@ int geneo_ksp_solve_device(geneo_pc_t pc, const char* ksp, const double* db, dou
   ABI_TRY
   ABI_REQ(pc && pc->ready && db && dx, "GenEO preconditioner without context");
   ksp_run(pc, ksp, db, dx, rtol, atol, dtol, maxIt, restart, out, rnorm, history, histCap);
-  CUDA_CHECK(cudaStreamSynchronize(pc->pc.st));
+  CUDA_CHECK(::geneo::sync_stream(pc->pc.st));
   ABI_CATCH
 }
 int geneo_ksp_solve(geneo_pc_t pc, const char* ksp, const double* b, double* x, double rtol, double atol, double dtol,

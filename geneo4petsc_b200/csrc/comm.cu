@@ -106,7 +106,7 @@ void Comm::init(int rank_, int world_, const void* uid128, const RankLayout& L, 
   }
   if (idx.empty()) idx.push_back(0);
   dSendIdx_.upload(idx, st);
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
   ensure(1);
 }
 
@@ -128,7 +128,7 @@ void Comm::allreduce_sum_host(double* h, int n, cudaStream_t st) {
   CUDA_CHECK(cudaMemcpyAsync(tmp_.p, h, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   allreduce_sum(tmp_.p, n, st);
   CUDA_CHECK(cudaMemcpyAsync(h, tmp_.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
 }
 
 void Comm::halo_forward(double* x, int width, cudaStream_t st) {

@@ -42,6 +42,12 @@ inline G launch_tick(G g) { ++g_kernel_launches; return g; }
 // events bracket each kernel (plus whatever memset / idle gap follows it); geneo_profile_dump() aggregates by launch site.
 extern bool g_profile;
 void profile_tick(const char* file, int line);
+// every host wait of the library goes through here: in profile mode a marker event closes the interval of the last
+// kernel, so that the idle gap while the host works is accounted to "host" and not to that kernel
+inline cudaError_t sync_stream(cudaStream_t s) {
+  if (g_profile) profile_tick("<host wait / idle>", 0);
+  return cudaStreamSynchronize(s);
+}
 #define GENEO_TICK(g) ((::geneo::g_profile ? ::geneo::profile_tick(__FILE__, __LINE__) : (void)0), ::geneo::launch_tick(g))
 
 // The product has NO CPU fallback: every numeric entry point calls this first.
@@ -89,7 +95,7 @@ struct DevBuf {
   void download(T* h, size_t cnt, cudaStream_t s = 0) const {
     if (cnt) CUDA_CHECK(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
     g_d2h_bytes += cnt * sizeof(T);
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    CUDA_CHECK(::geneo::sync_stream(s));
   }
   std::vector<T> to_host(cudaStream_t s = 0) const {
     std::vector<T> h(n);

@@ -72,7 +72,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * b * b, st));
     ts_gram(n, w, bp, b, bw, bp, b, dC.p, b, st);
     CUDA_CHECK(cudaMemcpyAsync(hR.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(::geneo::sync_stream(st));
     for (int i = 0; i < b; i++)
       for (int j = i + 1; j < b; j++) hR[i * b + j] = hR[j * b + i] = 0.5 * (hR[i * b + j] + hR[j * b + i]);
     const int bad = chol_upper(b, hR.data(), 1e-13);
@@ -116,7 +116,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       ts_update(n, Q.p, maxDim, dim, dC.p, b, b, w, bp, -1., 1., st);
       hC2.resize((size_t)dim * b);
       CUDA_CHECK(cudaMemcpyAsync(hC2.data(), dC.p, sizeof(double) * (size_t)dim * b, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(::geneo::sync_stream(st));
       for (size_t t = 0; t < hC1.size(); t++) hC1[t] += hC2[t];
     }
     for (int i = 0; i < dim; i++)
@@ -133,7 +133,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       ts_gram(n, w, bp, b, bw, bp, b, dC.p, b, st);
       std::vector<double> G((size_t)b * b), Gs((size_t)b * b), sv(b), dsc(b), M((size_t)b * b, 0.);
       CUDA_CHECK(cudaMemcpyAsync(G.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(::geneo::sync_stream(st));
       // a column whose B-norm fell below 1e-12 of its norm before the Gram-Schmidt sweep carries no information
       for (int i = 0; i < b; i++) {
         double ref = G[(size_t)i * b + i];
@@ -169,7 +169,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
         CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * b * b, st));
         ts_gram(n, wn, bp, b, bw2, bp, b, dC.p, b, st);
         CUDA_CHECK(cudaMemcpyAsync(hR.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(::geneo::sync_stream(st));
         for (int i = 0; i < b; i++)
           for (int c = i + 1; c < b; c++) hR[i * b + c] = hR[c * b + i] = 0.5 * (hR[i * b + c] + hR[c * b + i]);
         if (chol_upper(b, hR.data(), 1e-13) >= 0) { rc = 1; break; }
@@ -186,7 +186,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
         CUDA_CHECK(cudaMemsetAsync(dC.p, 0, sizeof(double) * b * b, st));
         ts_gram(n, wn, bp, b, worig_bw, bp, b, dC.p, b, st);
         CUDA_CHECK(cudaMemcpyAsync(hR.data(), dC.p, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(::geneo::sync_stream(st));
         // final block and its B image
         if (wn != w) std::swap(w, w2);  // make w point at the new block
         spmmB(w, bw);
@@ -234,7 +234,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       res.vecs.alloc((size_t)n * got);
       res.vecs.zero(st);
       ts_update(n, Q.p, maxDim, dim, dC.p, got, got, res.vecs.p, got, 1., 0., st);
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(::geneo::sync_stream(st));
       res.lambda.resize(got);
       res.resid = ritzRes;
       for (int q = 0; q < got; q++) res.lambda[q] = opt.invert ? 1. / ritzVal[q] : ritzVal[q];

@@ -176,11 +176,12 @@ struct HostPrep {  // everything the host prepares for one subdomain (worker thr
   std::string err;
 };
 
-void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, HostPrep& H) {
+void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth, HostPrep& H) {
   const int n = (int)S.nodes.size();
   SymbolicOptions so;
   so.nb = opt.nb;
   so.ordering = opt.ordering;
+  so.ndDepth = ndDepth;
   symbolic_analyze(n, S.aDir.ptr.data(), S.aDir.idx.data(), so, H.sym);
   const std::vector<int>& perm = H.sym.perm;
   const std::vector<int>& iperm = H.sym.iperm;
@@ -252,7 +253,7 @@ double GeneoPC::dot(const double* x, const double* y) {
   comm.allreduce_sum(scal.p, 1, st);
   double h = 0.;
   CUDA_CHECK(cudaMemcpyAsync(&h, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
   return h;
 }
 
@@ -336,12 +337,15 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   const int P = (int)mine.size();
   std::vector<HostPrep> prep(P);
   {
-    unsigned nt = std::max(1u, std::min((unsigned)P, std::thread::hardware_concurrency()));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    unsigned nt = std::max(1u, std::min((unsigned)P, hw));
+    int ndDepth = 0;  // spare host cores order the two halves of the top separators concurrently
+    while (P > 0 && ((unsigned)P << (ndDepth + 1)) <= hw && ndDepth < 3) ndDepth++;
     std::vector<std::thread> pool;
     for (unsigned tid = 0; tid < nt; tid++)
       pool.emplace_back([&, tid]() {
         for (int p = tid; p < P; p += nt) {
-          try { prepare_subdomain(*mine[p], opt, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
+          try { prepare_subdomain(*mine[p], opt, ndDepth, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
         }
       });
     for (auto& t : pool) t.join();
@@ -373,7 +377,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     dAll.upload(dA, st);
     pullPtr.upload(pp, st);
     pullPos.upload(ps, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(::geneo::sync_stream(st));
   }
   Xall.alloc((size_t)nAll); Yall.alloc((size_t)nAll);
   t1.alloc(nLoc); t2.alloc(nLoc); t3.alloc(nLoc);
@@ -391,6 +395,14 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   connectivity.assign((size_t)dec.nbPart * dec.nbPart, 0);
   for (int r = 0; r < dec.nbPart; r++)
     for (int q = 0; q < dec.nbPart; q++) connectivity[(size_t)r * dec.nbPart + q] = dec.subs[r].intersect[q].empty() ? 1 : 0;
+  if (layout && comm.active()) {  // a rank only knows the intersections of ITS subdomains: rows are summed over the ranks
+    std::vector<double> c((size_t)dec.nbPart * dec.nbPart, 0.);
+    for (int r = 0; r < dec.nbPart; r++)
+      if (layout->subRank[r] == layout->rank)
+        for (int q = 0; q < dec.nbPart; q++) c[(size_t)r * dec.nbPart + q] = connectivity[(size_t)r * dec.nbPart + q];
+    comm.allreduce_sum_host(c.data(), (int)c.size(), st);
+    for (size_t t = 0; t < c.size(); t++) connectivity[t] = c[t] > 0.5 ? 1 : 0;
+  }
   for (int p = 0; p < P; p++) {
     SubdomainState& s = subs[p];
     HostPrep& H = prep[p];
@@ -402,7 +414,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     if (opt.lvl1ORAS) s.vRob.upload(H.vRobP, st);
     s.gidx.upload(H.gidx, st);
     s.d.upload(H.dP, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(::geneo::sync_stream(st));
     H = HostPrep();  // free host memory early
   }
   uploadTime = now_s() - t0;
@@ -448,12 +460,12 @@ void GeneoPC::numeric_setup() {
     lvl2SetupETime = now_s() - te;
     infoL2 = "blocklanczos ldlt";
   }
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
   numericTime = now_s() - tNum0;
 }
 
 void GeneoPC::kernel_time(double* ms, int64_t* launches) {
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
   double tot = 0.;
   for (size_t i = 0; i + 1 < ktUsed; i += 2) {
     float t = 0.f;
@@ -529,10 +541,10 @@ void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
           c0 += nc;
         }
         rows_scale(s.n, nev, s.d.p, s.Z.p, st);  // Z = D V
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(::geneo::sync_stream(st));
         s.eigvals = vals;
       }
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(::geneo::sync_stream(st));
       lvl2SetupZTime += now_s() - tz;
     }
     // level 1: factor A_dir (or A_rob), src/geneo.cpp:126-148
@@ -610,7 +622,7 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
       X.alloc((size_t)n * got);
       CUDA_CHECK(cudaMemcpy2DAsync(X.p, sizeof(double) * got, er.vecs.p, sizeof(double) * er.lambda.size(),
                                    sizeof(double) * got, n, cudaMemcpyDeviceToDevice, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(::geneo::sync_stream(st));
     }
     const double dt = now_s() - t0;
     lvl2SetupEigTime += dt;
@@ -624,17 +636,17 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     double num = 0., den = 0.;
     csr_sum_all(nnz, vA, scal.p, st);
     CUDA_CHECK(cudaMemcpyAsync(&num, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(::geneo::sync_stream(st));
     csr_sum_all(nnz, vB, scal.p, st);
     CUDA_CHECK(cudaMemcpyAsync(&den, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(::geneo::sync_stream(st));
     if (std::fabs(num / den) <= (double)FLT_EPSILON) addOne = true;
   }
   if (got > 0) { vals.insert(vals.end(), lam.begin(), lam.end()); vecs.push_back(std::move(X)); counts.push_back(got); }
   if (addOne) {
     DevBuf<double> one((size_t)n);
     vec_set(n, 1., one.p, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(::geneo::sync_stream(st));
     vals.push_back(0.);
     vecs.push_back(std::move(one));
     counts.push_back(1);
@@ -717,7 +729,7 @@ void GeneoPC::build_coarse() {
   Einv.zero(st);
   for (int j0 = 0; j0 < nEp; j0 += 8) LE.solve_permuted(dI.p, Einv.p, nEp, j0, 8, st);
   w.alloc(nEp); w2.alloc(nEp);
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
 }
 
 // =====================================================================================================================
@@ -741,8 +753,8 @@ void GeneoPC::applyQ(const double* x, double* y) {  // src/geneo.cpp:1435-1517
 void GeneoPC::level1(const double* xin, double* yout, bool addQ) {
   const int P = (int)subs.size();
   double tt = 0.;
-  auto tic = [&]() { if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); tt = now_s(); } };
-  auto toc = [&](double& acc) { if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); acc += now_s() - tt; } };
+  auto tic = [&]() { if (opt.timing) { CUDA_CHECK(::geneo::sync_stream(st)); tt = now_s(); } };
+  auto toc = [&](double& acc) { if (opt.timing) { CUDA_CHECK(::geneo::sync_stream(st)); acc += now_s() - tt; } };
   tic();
   comm.halo_forward(const_cast<double*>(xin), 1, st);
   gather_rows(nAll, gidxAll.p, nullptr, xin, Xall.p, st);
@@ -782,7 +794,7 @@ void GeneoPC::level1(const double* xin, double* yout, bool addQ) {
 void GeneoPC::apply(const double* x, double* y) {  // applyGenEOPC, src/geneo.cpp:2051-2098
   applyCount++;
   double t0 = 0.;
-  if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); t0 = now_s(); }
+  if (opt.timing) { CUDA_CHECK(::geneo::sync_stream(st)); t0 = now_s(); }
   if (opt.lvl2 == 0) level1(x, y, false);
   else if (!opt.hybrid) level1(x, y, true);                         // y = Q x + sum R^T [D] M^-1 [D] R x
   else if (!opt.effHybrid) {
@@ -799,7 +811,7 @@ void GeneoPC::apply(const double* x, double* y) {  // applyGenEOPC, src/geneo.cp
     applyQ(t2.p, y);
     vec_axpby(nLoc, 1., t3.p, -1., y, st);
   }
-  if (opt.timing) { CUDA_CHECK(cudaStreamSynchronize(st)); lvl1ApplyTime += now_s() - t0; }
+  if (opt.timing) { CUDA_CHECK(::geneo::sync_stream(st)); lvl1ApplyTime += now_s() - t0; }
 }
 
 void GeneoPC::initial_guess(const double* b, double* x0) {
@@ -883,7 +895,7 @@ KspResult GeneoPC::solve_cg(const double* b, double* x, double rtol, double atol
     comm.allreduce_sum(scal.p, 2, st);
     double h[2];
     CUDA_CHECK(cudaMemcpyAsync(h, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(::geneo::sync_stream(st));
     dp = std::sqrt(h[1]);
     R.history.push_back(dp);
     R.rnorm = dp;
@@ -980,7 +992,7 @@ KspResult GeneoPC::solve_gmres(const double* b, double* x, double rtol, double a
       for (int i = 0; i < k; i++) hk[i] = -y[i];
       CUDA_CHECK(cudaMemcpyAsync(coef.p, hk.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
       vec_maxpy(nLoc, k, V.p, nLoc, coef.p, x, st);
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(::geneo::sync_stream(st));
     }
     if (reason) break;
     if (its >= maxIt) { reason = KSP_DIVERGED_ITS; break; }

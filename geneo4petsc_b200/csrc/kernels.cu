@@ -398,7 +398,7 @@ void SellMatrix::build(const CsrHost& a, cudaStream_t st) {
   sliceOff.upload(off, st);
   col.upload(c, st);
   val.upload(v, st);
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
 }
 
 void sell_spmv(const SellMatrix& A, const double* x, double* y, cudaStream_t st) {
@@ -430,7 +430,7 @@ void CsrDev::upload_pattern(const CsrHost& a, cudaStream_t st) {
   ptr.upload(a.ptr, st);
   idx.upload(a.idx, st);
   val.upload(a.val, st);
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
 }
 
 void csr_spmm(int n, const int64_t* ptr, const int* idx, const double* val, const double* X, int ldx, double* Y, int ldy,

@@ -541,7 +541,7 @@ void LdltPlan::build_device() {
   dAsmDst.upload(sym.asmDst);
   dItems.upload(items);
   dPerm.upload(sym.perm);
-  CUDA_CHECK(cudaStreamSynchronize(0));
+  CUDA_CHECK(::geneo::sync_stream(0));
   // the host copies of the big symbolic arrays are no longer needed
   std::vector<int64_t>().swap(sym.asmSrc);
   std::vector<int64_t>().swap(sym.asmDst);
@@ -594,7 +594,7 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   }
   int h[2] = {0, 0};
   CUDA_CHECK(cudaMemcpyAsync(h, ws.counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
   stats.neg = h[0];
   stats.perturbed = h[1];
   stats.seconds = now_s() - t0;
@@ -648,7 +648,7 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   hSubs.assign(ns, ForestSub{nullptr, nullptr, nullptr, 0});
   for (int s = 0; s < ns; s++) { hSubs[s].fronts = plans[s]->dFronts.p; hSubs[s].rowIdx = plans[s]->dRowIdx.p; hSubs[s].xoff = xoff[s]; }
   dSubs.alloc(ns);
-  CUDA_CHECK(cudaStreamSynchronize(0));
+  CUDA_CHECK(::geneo::sync_stream(0));
   int dev = 0, nsm = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -664,7 +664,7 @@ void SolveForest::set_factors(const std::vector<const double*>& L, cudaStream_t 
   GENEO_CHECK(L.size() == hSubs.size(), "forest: wrong number of factors");
   for (size_t s = 0; s < L.size(); s++) hSubs[s].L = L[s];
   CUDA_CHECK(cudaMemcpyAsync(dSubs.p, hSubs.data(), sizeof(ForestSub) * hSubs.size(), cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(::geneo::sync_stream(st));
 }
 
 void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const {

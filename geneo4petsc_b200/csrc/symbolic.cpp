@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <string>
+#include <thread>
 
 #include "common.hpp"
 
@@ -14,7 +16,77 @@ extern "C" int METIS_SetDefaultOptions(midx_t* options);
 extern "C" int METIS_NodeND(midx_t* nvtxs, midx_t* xadj, midx_t* adjncy, midx_t* vwgt, midx_t* options, midx_t* perm,
                             midx_t* iperm);
 
+extern "C" int METIS_ComputeVertexSeparator(midx_t* nvtxs, midx_t* xadj, midx_t* adjncy, midx_t* vwgt, midx_t* options,
+                                           midx_t* sepsize, midx_t* part);
+
 namespace {
+
+struct NdGraph { std::vector<midx_t> xadj, adj; int n() const { return (int)xadj.size() - 1; } };
+
+void metis_opts(midx_t* options) {
+  METIS_SetDefaultOptions(options);
+  if (const char* e = getenv("GENEO_METIS_OPTS")) {  // "idx=val,idx=val" experiment hook
+    std::string str(e);
+    size_t pos = 0;
+    while (pos < str.size()) {
+      size_t c = str.find(',', pos);
+      if (c == std::string::npos) c = str.size();
+      const std::string kv = str.substr(pos, c - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos) options[atoi(kv.substr(0, eq).c_str())] = atoi(kv.substr(eq + 1).c_str());
+      pos = c + 1;
+    }
+  }
+}
+
+// Nested dissection with the top `depth` levels done here so that the two halves can be ordered concurrently
+// (METIS_NodeND is serial; its own recursion does exactly this: separator last, halves recursively).  order: new -> old.
+void nd_recursive(NdGraph& g, int depth, std::vector<int>& order) {
+  const int n = g.n();
+  midx_t options[40];
+  metis_opts(options);
+  midx_t nv = n;
+  if (depth <= 0 || n < 20000) {
+    std::vector<midx_t> p(n), ip(n);
+    order.resize(n);
+    if (g.adj.empty()) { std::iota(order.begin(), order.end(), 0); return; }
+    const int rc = METIS_NodeND(&nv, g.xadj.data(), g.adj.data(), NULL, options, p.data(), ip.data());
+    GENEO_CHECK(rc == 1, "METIS_NodeND failed");
+    for (int i = 0; i < n; i++) order[i] = (int)p[i];
+    return;
+  }
+  std::vector<midx_t> part(n);
+  midx_t sep = 0;
+  const int rc = METIS_ComputeVertexSeparator(&nv, g.xadj.data(), g.adj.data(), NULL, options, &sep, part.data());
+  GENEO_CHECK(rc == 1, "METIS_ComputeVertexSeparator failed");
+  std::vector<int> ids[3];
+  for (int i = 0; i < n; i++) ids[part[i] < 0 || part[i] > 2 ? 2 : part[i]].push_back(i);
+  if (ids[0].empty() || ids[1].empty()) { nd_recursive(g, 0, order); return; }
+  std::vector<int> loc(n, -1);
+  NdGraph sub[2];
+  for (int s = 0; s < 2; s++) {
+    for (size_t t = 0; t < ids[s].size(); t++) loc[ids[s][t]] = (int)t;
+    sub[s].xadj.assign(ids[s].size() + 1, 0);
+    for (size_t t = 0; t < ids[s].size(); t++) {
+      const int v = ids[s][t];
+      for (midx_t e = g.xadj[v]; e < g.xadj[v + 1]; e++)
+        if (part[g.adj[e]] == s) sub[s].adj.push_back(loc[g.adj[e]]);
+      sub[s].xadj[t + 1] = (midx_t)sub[s].adj.size();
+    }
+  }
+  { NdGraph().xadj.swap(g.xadj); std::vector<midx_t>().swap(g.adj); }  // the parent graph is no longer needed
+  std::vector<int> ord[2];
+  std::string err;
+  std::thread th([&]() { try { nd_recursive(sub[0], depth - 1, ord[0]); } catch (std::exception& e) { err = e.what(); } });
+  nd_recursive(sub[1], depth - 1, ord[1]);
+  th.join();
+  GENEO_CHECK(err.empty(), err);
+  order.clear();
+  order.reserve(n);
+  for (int s = 0; s < 2; s++)
+    for (int v : ord[s]) order.push_back(ids[s][v]);
+  for (int v : ids[2]) order.push_back(v);
+}
 
 // Elimination tree of P A P^T (Liu, path compression).  Row j of the permuted matrix = row perm[j] of the input.
 void etree(int n, const int64_t* ptr, const int* idx, const std::vector<int>& perm, const std::vector<int>& iperm,
@@ -116,12 +188,15 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
     }
     if (adj.empty()) useMetis = false;
     else {
-      midx_t nv = n, options[40];
-      METIS_SetDefaultOptions(options);
-      std::vector<midx_t> p(n), ip(n);
-      int rc = METIS_NodeND(&nv, xadj.data(), adj.data(), NULL, options, p.data(), ip.data());
-      GENEO_CHECK(rc == 1, "METIS_NodeND failed");
-      for (int i = 0; i < n; i++) { perm[i] = (int)p[i]; iperm[i] = (int)ip[i]; }
+      NdGraph g;
+      g.xadj.swap(xadj);
+      g.adj.swap(adj);
+      std::vector<int> order;
+      int depth = opt.ndDepth;
+      if (const char* e = getenv("GENEO_ND_DEPTH")) depth = atoi(e);
+      nd_recursive(g, depth, order);
+      GENEO_CHECK((int)order.size() == n, "nested dissection lost vertices");
+      for (int i = 0; i < n; i++) { perm[i] = order[i]; iperm[order[i]] = i; }
     }
   }
   if (!useMetis) { std::iota(perm.begin(), perm.end(), 0); std::iota(iperm.begin(), iperm.end(), 0); }

@@ -62,6 +62,8 @@ struct SymbolicOptions {
   int nb = 128;        // panel width
   int ordering = 1;    // 0 natural, 1 METIS NodeND
   bool amalgamate = true;
+  int ndDepth = 0;     // top levels of the nested dissection done here (METIS_ComputeVertexSeparator) with the two halves
+                       // ordered by concurrent threads: 2^ndDepth threads per matrix; 0 = plain METIS_NodeND
 };
 
 // ptr/idx: CSR pattern of a structurally symmetric n x n matrix (both triangles; column order irrelevant).
