@@ -94,6 +94,24 @@ class Problem:
         _chk(lib.geneo_problem_decompose(self.h, C.c_int(nb_part), C.c_int(1 if dual else 0), C.c_int(overlap), _p(ep, _i32p), _p(npart, _i32p)))
         return self
 
+    def set_subdomains(self, nb_dof, subs):
+        """Pre-decomposed input: subs = [(global_ids ascending, A_neu scipy CSR[, A_dir scipy CSR]), ...] (initGenEOPC's view)."""
+        _chk(lib.geneo_problem_begin_subdomains(self.h, C.c_int64(nb_dof), C.c_int(len(subs))))
+        for s, item in enumerate(subs):
+            ids = np.ascontiguousarray(item[0], dtype=np.int32)
+            mats = []
+            for m in item[1:3]:
+                m = m.tocsr()
+                mats += [np.ascontiguousarray(m.indptr, dtype=np.int64), np.ascontiguousarray(m.indices, dtype=np.int32),
+                         np.ascontiguousarray(m.data, dtype=np.float64)]
+            while len(mats) < 6:
+                mats.append(None)
+            _chk(lib.geneo_problem_set_subdomain(self.h, C.c_int(s), C.c_int64(len(ids)), _p(ids, _i32p), _p(mats[0], _i64p),
+                                                 _p(mats[1], _i32p), _p(mats[2], _f64p), _p(mats[3], _i64p), _p(mats[4], _i32p),
+                                                 _p(mats[5], _f64p)))
+        _chk(lib.geneo_problem_end_subdomains(self.h))
+        return self
+
     def sizes(self):
         v = [C.c_int64() for _ in range(4)]
         _chk(lib.geneo_problem_sizes(self.h, *[C.byref(x) for x in v]))

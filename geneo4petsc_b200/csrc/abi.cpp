@@ -122,6 +122,56 @@ int geneo_problem_decompose(geneo_problem_t p, int nbPart, int metisDual, int ov
   p->decomposed = true;
   ABI_CATCH
 }
+// ---- pre-decomposed input (the PETSc plug-in's view: initGenEOPC / PCGenEOSetup) -----------------------------------------
+static void csr_from_c(int n, const int64_t* ptr, const int32_t* idx, const double* val, CsrHost& a) {
+  a.n = a.ncols = n;
+  a.ptr.assign(ptr, ptr + n + 1);
+  a.idx.assign(idx, idx + ptr[n]);
+  a.val.assign(val, val + ptr[n]);
+  for (int r = 0; r < n; r++) {  // sorted columns are assumed downstream
+    bool sorted = true;
+    for (int64_t t = a.ptr[r] + 1; t < a.ptr[r + 1]; t++) sorted = sorted && a.idx[t - 1] < a.idx[t];
+    if (sorted) continue;
+    std::vector<std::pair<int, double>> row;
+    for (int64_t t = a.ptr[r]; t < a.ptr[r + 1]; t++) row.emplace_back(a.idx[t], a.val[t]);
+    std::sort(row.begin(), row.end());
+    for (size_t k = 1; k < row.size(); k++)
+      if (row[k].first == row[k - 1].first) throw Error("geneo_b200: duplicate column in a local matrix row");
+    for (size_t k = 0; k < row.size(); k++) { a.idx[a.ptr[r] + k] = row[k].first; a.val[a.ptr[r] + k] = row[k].second; }
+  }
+}
+int geneo_problem_begin_subdomains(geneo_problem_t p, int64_t nbDof, int nbPart) {
+  ABI_TRY
+  ABI_REQ(p && nbDof > 0 && nbDof < 2147483647 && nbPart >= 1, "bad sizes");
+  p->mesh = Mesh();
+  p->dec = Decomposition();
+  p->dec.nbNode = (int)nbDof; p->dec.nbPart = nbPart; p->dec.nbElem = 0;
+  p->dec.subs.assign(nbPart, Subdomain());
+  p->elemPart.clear(); p->nodePart.clear();
+  p->decomposed = false;
+  ABI_CATCH
+}
+int geneo_problem_set_subdomain(geneo_problem_t p, int s, int64_t n, const int32_t* globalIds, const int64_t* neuPtr,
+                                const int32_t* neuIdx, const double* neuVal, const int64_t* dirPtr, const int32_t* dirIdx,
+                                const double* dirVal) {
+  ABI_TRY
+  ABI_REQ(p && s >= 0 && s < (int)p->dec.subs.size() && n > 0 && globalIds && neuPtr && neuIdx && neuVal, "bad argument");
+  Subdomain& S = p->dec.subs[s];
+  S = Subdomain();
+  S.id = s;
+  S.nodes.assign(globalIds, globalIds + n);
+  csr_from_c((int)n, neuPtr, neuIdx, neuVal, S.aNeu);
+  if (dirPtr && dirIdx && dirVal) csr_from_c((int)n, dirPtr, dirIdx, dirVal, S.aDir);
+  ABI_CATCH
+}
+int geneo_problem_end_subdomains(geneo_problem_t p) {
+  ABI_TRY
+  ABI_REQ(p && !p->dec.subs.empty(), "no subdomains");
+  finish_predecomposed(p->dec);
+  p->decomposed = true;
+  ABI_CATCH
+}
+
 int geneo_problem_sizes(geneo_problem_t p, int64_t* nbNode, int64_t* nbElem, int64_t* nbPart, int64_t* nnz) {
   ABI_TRY
   ABI_REQ(p, "null argument");

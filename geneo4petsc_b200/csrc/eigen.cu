@@ -102,12 +102,16 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
   std::vector<double> Ysel;
   int dim = 0, steps = 0;
   bool done = false;
+  bool prefetched = false;  // the solve of this step was already queued behind the previous step's device work
+  auto launch_solve = [&](int jj) {  // W = F^-1 (B Q_jj)
+    k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)jj * b, maxDim, Xs.p, bp, b, bp);
+    for (int j0 = 0; j0 < bp; j0 += 8) F.solve_permuted(Xs.p, w, bp, j0, 8, st);
+  };
   while (!done) {
     const int j = steps;
     dim = (j + 1) * b;
-    // W = F^-1 (B Q_j)
-    k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)j * b, maxDim, Xs.p, bp, b, bp);
-    for (int j0 = 0; j0 < bp; j0 += 8) F.solve_permuted(Xs.p, w, bp, j0, 8, st);
+    if (!prefetched) launch_solve(j);
+    prefetched = false;
     // two passes of block classical Gram-Schmidt against Q[:, 0:dim] in the B inner product
     hC1.assign((size_t)dim * b, 0.);
     for (int pass = 0; pass < 2; pass++) {
@@ -196,6 +200,15 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     if (room)  // T Q_j = Q_{0..j} C_j + Q_{j+1} R : the sub-diagonal block of the projected matrix
       for (int r = 0; r < b; r++)
         for (int c = 0; c < b; c++) Hm[(size_t)(dim + r) * maxDim + j * b + c] = hR[(size_t)r * b + c];
+    // The next block is known: queue its copy into the basis and its solve NOW, so that the device streams the factor
+    // while the host does the Rayleigh-Ritz below (if that says "converged" the extra solve is simply dropped).
+    const bool canContinue = !breakdown && room && dim + b <= n;
+    if (canContinue) {
+      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, w, bp, Q.p + (size_t)(j + 1) * b, maxDim, b, b);
+      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)(j + 1) * b, maxDim, b, b);
+      launch_solve(j + 1);
+      prefetched = true;
+    }
     // Rayleigh-Ritz on the symmetrised leading dim x dim block
     T.assign((size_t)dim * dim, 0.);
     for (int i = 0; i < dim; i++)
@@ -221,10 +234,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     steps++;
     res.nconv = nconv;
     if ((nconv == want && want == nev) || breakdown || !room || dim + b > n) done = true;
-    if (!done) {
-      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, w, bp, Q.p + (size_t)(j + 1) * b, maxDim, b, b);
-      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)(j + 1) * b, maxDim, b, b);
-    } else {
+    if (done) {
       // Ritz vectors X = Q[:, 0:dim] Y
       const int got = want;
       Ysel.assign((size_t)dim * got, 0.);

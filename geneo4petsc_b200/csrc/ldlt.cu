@@ -302,11 +302,13 @@ constexpr int SOLVE_THREADS = 512;
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 template <int NR>
-__device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it, double* __restrict__ X,
+__device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it, int part, double* __restrict__ X,
                                          double* __restrict__ Y, int ldx, int lane) {
+  constexpr int FS = NR >= 4 ? 4 : 1;  // a block solve splits the 32 columns of an item into FS virtual items
   const FrontDev F = S.fronts[it.f];
   const int k = F.k, h = F.h, ld = F.ld;
-  const int c0 = it.cb * SOLVE_COLS, nc = min(SOLVE_COLS, k - c0);
+  const int c0 = it.cb * SOLVE_COLS + part * (SOLVE_COLS / FS), nc = min(SOLVE_COLS / FS, k - c0);
+  if (nc <= 0) return;
   const int r0 = it.rb * FWD_ROWS + 2 * lane;  // panel rows r0, r0+1 (even: 16-byte aligned)
   const int col0 = S.rowIdx[F.rowOff];
   const double* x1 = X + (size_t)(S.xoff + col0 + c0) * ldx;
@@ -370,7 +372,7 @@ __device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it
 
 // transposed product: one accumulator per (column, rhs) pair, CP = 32 / NR columns per pass
 template <int NR>
-__device__ __forceinline__ void bwd_item(const ForestSub& S, const ForestItem it, double* __restrict__ Y, int ldx, int lane) {
+__device__ __forceinline__ void bwd_item(const ForestSub& S, const ForestItem it, int pass, double* __restrict__ Y, int ldx, int lane) {
   constexpr int CP = 32 / NR;
   const FrontDev F = S.fronts[it.f];
   const int k = F.k, h = F.h, ld = F.ld;
@@ -391,7 +393,9 @@ __device__ __forceinline__ void bwd_item(const ForestSub& S, const ForestItem it
     }
     Lt[t] = S.L + F.lOff + (size_t)c0 * ld + (r < h ? r : 0);
   }
-  for (int cp = 0; cp < nc; cp += CP) {
+  {
+    const int cp = pass * CP;  // a block solve splits the 32 columns of an item into NR independent passes (virtual items)
+    if (cp >= nc) return;
     double acc[32];
 #pragma unroll
     for (int q = 0; q < 32; q++) acc[q] = 0.;
@@ -440,17 +444,18 @@ k_solve_forest(const ForestSub* __restrict__ subs, const ForestItem* __restrict_
   const int64_t* bwdCnt = ranges + 3 * nlev;
   for (int l = 0; l < nlev; l++) {
     const int64_t off = fwdOff[l], cnt = fwdCnt[l];
-    for (int64_t i = gw; i < cnt; i += nw) {
-      const ForestItem it = items[off + i];
-      fwd_item<NR>(subs[it.sub], it, X, Y, ldx, lane);
+    constexpr int FS = NR >= 4 ? 4 : 1;
+    for (int64_t i = gw; i < cnt * FS; i += nw) {
+      const ForestItem it = items[off + i / FS];
+      fwd_item<NR>(subs[it.sub], it, (int)(i % FS), X, Y, ldx, lane);
     }
     grid.sync();
   }
   for (int l = nlev - 1; l >= 0; l--) {
     const int64_t off = bwdOff[l], cnt = bwdCnt[l];
-    for (int64_t i = gw; i < cnt; i += nw) {
-      const ForestItem it = items[off + i];
-      bwd_item<NR>(subs[it.sub], it, Y, ldx, lane);
+    for (int64_t i = gw; i < cnt * NR; i += nw) {
+      const ForestItem it = items[off + i / NR];
+      bwd_item<NR>(subs[it.sub], it, (int)(i % NR), Y, ldx, lane);
     }
     if (l > 0) grid.sync();
   }

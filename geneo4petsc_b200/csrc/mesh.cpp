@@ -455,6 +455,80 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
   for (int p : mine) d.nnzNeuTotal += d.subs[p].aNeu.nnz();
 }
 
+void finish_predecomposed(Decomposition& d) {
+  const int nn = d.nbNode, P = d.nbPart;
+  GENEO_CHECK((int)d.subs.size() == P && P >= 1 && nn >= 1, "pre-decomposed problem: bad sizes");
+  d.nodeMult.assign(nn, 0);
+  for (int p = 0; p < P; p++) {
+    Subdomain& s = d.subs[p];
+    s.id = p;
+    GENEO_CHECK(!s.nodes.empty() && s.aNeu.n == (int)s.nodes.size(), "pre-decomposed problem: subdomain without nodes / matrix");
+    for (size_t l = 0; l < s.nodes.size(); l++) {
+      GENEO_CHECK(s.nodes[l] >= 0 && s.nodes[l] < nn, "pre-decomposed problem: global id out of range");
+      GENEO_CHECK(l == 0 || s.nodes[l - 1] < s.nodes[l], "pre-decomposed problem: global ids must be sorted ascending");
+      d.nodeMult[s.nodes[l]]++;
+    }
+  }
+  for (int g = 0; g < nn; g++) GENEO_CHECK(d.nodeMult[g] > 0, "pre-decomposed problem: a DOF belongs to no subdomain");
+  d.nodeSubPtr.assign(nn + 1, 0);
+  for (int g = 0; g < nn; g++) d.nodeSubPtr[g + 1] = d.nodeSubPtr[g] + d.nodeMult[g];
+  d.nodeSub.assign(d.nodeSubPtr[nn], 0);
+  {
+    std::vector<int64_t> pos(d.nodeSubPtr.begin(), d.nodeSubPtr.end() - 1);
+    for (int p = 0; p < P; p++)
+      for (int g : d.subs[p].nodes) d.nodeSub[pos[g]++] = p;
+  }
+  d.nnzNeuTotal = 0;
+  bool needDir = false;
+  for (int p = 0; p < P; p++) {
+    Subdomain& s = d.subs[p];
+    const int nl = (int)s.nodes.size();
+    s.mult.resize(nl);
+    s.intersect.assign(P, std::vector<int>());
+    for (int l = 0; l < nl; l++) {
+      const int g = s.nodes[l];
+      s.mult[l] = d.nodeMult[g];
+      if (d.nodeMult[g] > 1)
+        for (int64_t t = d.nodeSubPtr[g]; t < d.nodeSubPtr[g + 1]; t++)
+          if (d.nodeSub[t] != p) s.intersect[d.nodeSub[t]].push_back(l);
+    }
+    d.nnzNeuTotal += s.aNeu.nnz();
+    if (s.aDir.n != nl) needDir = true;
+  }
+  if (!needDir) return;
+  // global operator rows, then the sub-blocks
+  std::vector<int64_t> cnt(nn + 1, 0);
+  for (auto& s : d.subs)
+    for (int l = 0; l < s.aNeu.n; l++) cnt[s.nodes[l] + 1] += s.aNeu.ptr[l + 1] - s.aNeu.ptr[l];
+  for (int i = 0; i < nn; i++) cnt[i + 1] += cnt[i];
+  std::vector<int> ci((size_t)cnt[nn]);
+  std::vector<double> cv((size_t)cnt[nn]);
+  {
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (auto& s : d.subs)
+      for (int l = 0; l < s.aNeu.n; l++) {
+        int64_t& q = pos[s.nodes[l]];
+        for (int64_t t = s.aNeu.ptr[l]; t < s.aNeu.ptr[l + 1]; t++) { ci[q] = s.nodes[s.aNeu.idx[t]]; cv[q] = s.aNeu.val[t]; q++; }
+      }
+  }
+  std::vector<int> g2l(nn, -1);
+  for (int p = 0; p < P; p++) {
+    Subdomain& s = d.subs[p];
+    const int nl = (int)s.nodes.size();
+    if (s.aDir.n == nl) continue;
+    for (int l = 0; l < nl; l++) g2l[s.nodes[l]] = l;
+    std::vector<int> rows, cols;
+    std::vector<double> vals;
+    for (int l = 0; l < nl; l++) {
+      const int g = s.nodes[l];
+      for (int64_t t = cnt[g]; t < cnt[g + 1]; t++)
+        if (g2l[ci[t]] >= 0) { rows.push_back(l); cols.push_back(g2l[ci[t]]); vals.push_back(cv[t]); }
+    }
+    coo_to_csr(nl, rows, cols, vals, s.aDir);
+    for (int l = 0; l < nl; l++) g2l[s.nodes[l]] = -1;
+  }
+}
+
 void build_rank_layout(const Mesh& m, const Decomposition& d, const std::vector<int>& subRank, int rank, int world,
                        RankLayout& L) {
   const int nn = m.nbNode, ne = m.nbElem();

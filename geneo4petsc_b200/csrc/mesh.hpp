@@ -67,6 +67,13 @@ struct Decomposition {
   std::vector<int> nodeSub;
 };
 
+// Pre-decomposed input (what the PETSc plug-in receives: initGenEOPC, hdr/geneo.hpp:30-35 -- the local Neumann matrices
+// of a MATIS, the local-to-global maps, optionally the Dirichlet matrices).  Fills multiplicities (createPartitionOfUnity
+// input, src/geneo.cpp:977-980), intersections, the node -> subdomain map, and, where a subdomain has no Dirichlet matrix
+// yet, A_dir,i = R_i (sum_j R_j^T A_neu,j R_j) R_i^T  (MatConvert + MatCreateSubMatrices, src/geneo.cpp:1692-1699).
+// Every subs[p].nodes must be sorted ascending (the reference's local numbering, src/geneo4PETSc.cpp:485-489).
+void finish_predecomposed(Decomposition& d);
+
 // ---- multi-GPU layout (one process per GPU) --------------------------------------------------------------
 // Rank r holds the subdomains p with subRank[p] == r and OWNS the rows of the nodes whose lowest-numbered subdomain it
 // holds (replaces the reference's block-by-index MatCreateIS layout, src/geneo4PETSc.cpp:755).  Local vectors are

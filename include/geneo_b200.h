@@ -45,6 +45,16 @@ int geneo_problem_read_file(geneo_problem_t p, const char* path, double inpEps);
  * matrices R_i A R_i^T (src/geneo.cpp:1699).  nbPart replaces "mpirun -n" (src/geneo4PETSc.cpp:604). */
 int geneo_problem_decompose(geneo_problem_t p, int nbPart, int metisDual, int overlap, const int32_t* elemPart,
                             const int32_t* nodePart);
+/* Pre-decomposed input -- what the PETSc plug-in itself receives (initGenEOPC, hdr/geneo.hpp:30-35; PCGenEOSetup,
+ * hdr/geneo_c.h:10): per subdomain the local-to-global map (ISLocalToGlobalMapping; ascending, the reference's local
+ * numbering src/geneo4PETSc.cpp:485-489), the local Neumann matrix of the MATIS (MatISGetLocalMat, src/geneo.cpp:1714)
+ * and optionally the Dirichlet matrix (pcADirLoc).  end_subdomains derives the multiplicities (dofIdxMultLoc), the
+ * intersections (intersectLoc) and any missing A_dir,i = R_i A R_i^T (MatConvert + MatCreateSubMatrices, :1692-1699). */
+int geneo_problem_begin_subdomains(geneo_problem_t p, int64_t nbDof, int nbPart);
+int geneo_problem_set_subdomain(geneo_problem_t p, int s, int64_t n, const int32_t* globalIds, const int64_t* neuPtr,
+                                const int32_t* neuIdx, const double* neuVal, const int64_t* dirPtr /* may be NULL */,
+                                const int32_t* dirIdx, const double* dirVal);
+int geneo_problem_end_subdomains(geneo_problem_t p);
 int geneo_problem_sizes(geneo_problem_t p, int64_t* nbNode, int64_t* nbElem, int64_t* nbPart, int64_t* nnzNeuTotal);
 int geneo_problem_get_mesh(geneo_problem_t p, int64_t* elemPtr, int32_t* elemIdx, double* elemMat); /* sizes from _mesh_sizes */
 int geneo_problem_mesh_sizes(geneo_problem_t p, int64_t* nIdx, int64_t* nMat);

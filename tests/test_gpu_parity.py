@@ -153,3 +153,15 @@ def test_larger_case_roundtrip():
     rep = _oracle(mesh, p, 8, go.GenEOOptions(tau=0.2), ksp="cg", rtol=1e-10, atol=1e-50)
     assert [pc.sub_info(s)["nev"] for s in range(8)] == [s.z.shape[1] for s in rep.pc.sub]
     assert abs(r["its"] - rep.ksp.its) <= 1
+
+
+def test_predecomposed_input_gives_the_same_preconditioner(lap3d):
+    """The PETSc plug-in's view of the input (local Neumann matrices + local-to-global maps, geneo_problem_set_subdomain)
+    yields the same PC as the driver's mesh path."""
+    mesh = lap3d
+    p = _problem(mesh, 4, dual=False, overlap=1)
+    subs = [(p.sub_nodes(s)[0], p.sub_matrix(s, 0)) for s in range(4)]
+    q = g.Problem().set_subdomains(mesh.nb_node, subs)
+    x = np.random.default_rng(5).standard_normal(mesh.nb_node)
+    y = [g.GeneoPC(["-geneo_lvl", "ASM,1", "-geneo_tau", "0.3", "-els2_eps_tol", "1e-10"]).setup(pr).apply(x) for pr in (p, q)]
+    assert np.linalg.norm(y[0] - y[1]) <= 1e-8 * np.linalg.norm(y[0])

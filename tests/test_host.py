@@ -146,3 +146,20 @@ def test_host_sym_eig_matches_lapack():
         w, v = g.host_sym_eig(a)
         np.testing.assert_allclose(w, np.linalg.eigvalsh(a), atol=1e-11 * max(1, n))
         np.testing.assert_allclose(a @ v, v * w, atol=1e-10 * max(1, n))
+
+
+def test_predecomposed_input_matches_mesh_decomposition():
+    """initGenEOPC's view (local Neumann matrices + local-to-global maps) gives back the same multiplicities,
+    intersections and Dirichlet matrices as the driver's own decomposition."""
+    import geneo4petsc_b200 as g
+    for dual, overlap in ((True, 0), (False, 1)):
+        p = g.Problem().generate("laplacian", "--dim 3 --size 9 --inpEps 0.0001 --kappa 2. lin").decompose(4, dual, overlap)
+        subs = [(p.sub_nodes(s)[0], p.sub_matrix(s, 0)) for s in range(4)]
+        q = g.Problem().set_subdomains(p.sizes()["nb_node"], subs)
+        assert q.sizes()["nnz"] == p.sizes()["nnz"]
+        for s in range(4):
+            np.testing.assert_array_equal(q.sub_nodes(s)[1], p.sub_nodes(s)[1])
+            for t in range(4):
+                np.testing.assert_array_equal(q.sub_intersect(s, t), p.sub_intersect(s, t))
+            d = (q.sub_matrix(s, 1) - p.sub_matrix(s, 1)).tocoo()
+            assert d.nnz == 0 or np.abs(d.data).max() <= 1e-12 * np.abs(p.sub_matrix(s, 1).data).max()

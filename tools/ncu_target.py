@@ -1,4 +1,5 @@
-"""Small, fixed workload for ncu captures: 3-D Laplacian S^3, 8 subdomains, setup + a few PC applies."""
+"""Small, fixed workload for ncu captures: 3-D Laplacian S^3, 8 subdomains, setup, then (inside cudaProfilerStart/Stop)
+a few PC applies.  Run under `ncu --profile-from-start off` so that only the applies are seen."""
 import sys
 sys.path.insert(0, ".")
 import torch
@@ -9,7 +10,11 @@ pc = g.GeneoPC(["-geneo_lvl", "ASM,1"]).setup(p)
 n = p.sizes()["nb_node"]
 x = torch.randn(n, dtype=torch.float64, device="cuda")
 y = torch.zeros_like(x)
-for _ in range(4):
+pc.apply_device(x.data_ptr(), y.data_ptr())
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for _ in range(3):
     pc.apply_device(x.data_ptr(), y.data_ptr())
 torch.cuda.synchronize()
-print("ok", n, float(y.norm()))
+torch.cuda.cudart().cudaProfilerStop()
+print("ok", n, float(y.norm()), pc.stats()["trisolve_bytes"])
