@@ -12,6 +12,8 @@ pytestmark = pytest.mark.gpu
 
 def _worker(rank, world, port, lvl, ksp, q):
     try:
+        import faulthandler
+        faulthandler.dump_traceback_later(150, exit=True)  # a rank stuck in a collective shows where, then dies
         sys.path.insert(0, ROOT)
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
         import torch
@@ -20,10 +22,10 @@ def _worker(rank, world, port, lvl, ksp, q):
         from geneo4petsc_b200 import dist
         torch.cuda.set_device(rank)
         tdist.init_process_group("gloo", rank=rank, world_size=world)  # rendezvous only; the data path is the library's NCCL
-        kind, args = "laplacian", "--dim 3 --size 24 --inpEps 0.0001 --kappa 2. lin"
+        kind, args = "laplacian", "--dim 3 --size 32 --inpEps 0.0001 --kappa 2. lin"
         K, grid, sub_rank = dist.box_grid(world)
         nparts = len(sub_rank)
-        lo, hi = dist.keep_region(24, K, grid, rank)
+        lo, hi = dist.keep_region(32, K, grid, rank)
         prob = g.Problem()
         edge = dist.generate_boxed(prob, kind, args, K, lo, hi)
         dist.decompose_owned(prob, nparts, sub_rank, rank, True, 0)
@@ -100,8 +102,16 @@ def test_two_gpu_solve_matches_single_gpu(lvl, ksp):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, lvl, ksp, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-    for r in res:
-        assert r[1] == "ok", r
+    import queue
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=240))
+            assert res[-1][1] == "ok", res[-1]  # report the first failure at once: the other rank is then stuck in a collective
+    except queue.Empty:
+        pytest.fail("a rank did not answer; got %r" % (res,))
+    finally:
+        for p in procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.kill()
