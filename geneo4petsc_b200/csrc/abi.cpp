@@ -586,7 +586,13 @@ int geneo_microbench(int kind, int n, int reps, double result[2]) {
   CUDA_CHECK(cudaEventCreate(&e1));
   float ms = 0.f;
   result[0] = result[1] = 0.;
-  if (kind == 0) {
+  if (kind == 2) {  // solve-kernel streaming: n = panel height h; about 2 GB of 128-column panels at one level
+    const int k = 128, h = std::max(n, k);
+    const int nf = (int)std::max<int64_t>(8, (int64_t)(2.0e9 / ((double)h * k * 8.)));
+    double gb = 0.;
+    result[1] = solve_stream_bench(nf, h, k, reps, &gb);  // ms per solve (forward + backward)
+    result[0] = gb;                                       // algorithmic GB/s
+  } else if (kind == 0) {
     std::vector<double> hA((size_t)n * n), hB((size_t)n * n);
     for (size_t i = 0; i < hA.size(); i++) { hA[i] = (double)((i * 2654435761u) % 1000) / 1000. - 0.5; hB[i] = (double)((i * 40503u) % 1000) / 1000. - 0.5; }
     DevBuf<double> A, B, C((size_t)n * n);

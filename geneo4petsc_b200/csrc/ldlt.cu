@@ -300,31 +300,38 @@ constexpr int BWD_ROWS = 128;
 constexpr int SOLVE_THREADS = 512;
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ ForestItem load_item(const ForestItem* p) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+  union { int4 v[3]; ForestItem it; } u;
+  u.v[0] = __ldg(q); u.v[1] = __ldg(q + 1); u.v[2] = __ldg(q + 2);
+  return u.it;
+}
+constexpr int MAX_SMEM_SUBS = 64;
 
 template <int NR>
-__device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it, int part, double* __restrict__ X,
+__device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem& it, int part, double* __restrict__ X,
                                          double* __restrict__ Y, int ldx, int lane) {
   constexpr int FS = NR >= 4 ? 4 : 1;  // a block solve splits the 32 columns of an item into FS virtual items
-  const FrontDev F = S.fronts[it.f];
-  const int k = F.k, h = F.h, ld = F.ld;
-  const int c0 = it.cb * SOLVE_COLS + part * (SOLVE_COLS / FS), nc = min(SOLVE_COLS / FS, k - c0);
+  constexpr int UN = NR == 1 ? 16 : 8; // independent 16-byte loads in flight per lane
+  const int k = it.k, h = it.h, ld = it.ld;
+  const int cs = part * (SOLVE_COLS / FS);
+  const int nc = min(SOLVE_COLS / FS, it.nc - cs);
   if (nc <= 0) return;
-  const int r0 = it.rb * FWD_ROWS + 2 * lane;  // panel rows r0, r0+1 (even: 16-byte aligned)
-  const int col0 = S.rowIdx[F.rowOff];
-  const double* x1 = X + (size_t)(S.xoff + col0 + c0) * ldx;
-  const double* Lp = S.L + F.lOff + (size_t)c0 * ld + (r0 < h ? r0 : 0);
+  const int r0 = it.r0 + 2 * lane;  // panel rows r0, r0+1 (even: 16-byte aligned)
+  const double* x1 = X + (size_t)(S.xoff + it.col0 + it.c0 + cs) * ldx;
+  const double* Lp = S.L + it.lOff + (size_t)cs * ld + (r0 < h ? 2 * lane : 0);
   double xv = 0.;
   if (NR == 1) xv = lane < nc ? x1[lane] : 0.;
   double a0[NR], a1[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) a0[j] = a1[j] = 0.;
   int c = 0;
-  for (; c + 8 <= nc; c += 8) {
-    double2 v[8];
+  for (; c + UN <= nc; c += UN) {
+    double2 v[UN];
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = ldg2(Lp + (size_t)(c + u) * ld);
+    for (int u = 0; u < UN; u++) v[u] = ldg2(Lp + (size_t)(c + u) * ld);
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < UN; u++) {
       if (NR == 1) {
         const double xc = __shfl_sync(0xffffffffu, xv, c + u);
         a0[0] += v[u].x * xc;
@@ -359,78 +366,84 @@ __device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem it
     const int r = r0 + e;
     if (r >= h) continue;
     if (r < k) {  // D^-1 rows
-      double* dst = Y + (size_t)(S.xoff + col0 + r) * ldx;
+      double* dst = Y + (size_t)(S.xoff + it.col0 + r) * ldx;
 #pragma unroll
       for (int j = 0; j < NR; j++) atomicAdd(dst + j, e ? a1[j] : a0[j]);
     } else {      // L21 rows
-      double* dst = X + (size_t)(S.xoff + S.rowIdx[F.rowOff + r]) * ldx;
+      double* dst = X + (size_t)(S.xoff + S.rowIdx[it.rowOff + r]) * ldx;
 #pragma unroll
       for (int j = 0; j < NR; j++) atomicAdd(dst + j, -(e ? a1[j] : a0[j]));
     }
   }
 }
 
-// transposed product: one accumulator per (column, rhs) pair, CP = 32 / NR columns per pass
+// transposed product: one accumulator per (column, rhs) pair; PC = 16 / NR (NR <= 8) columns per pass keep the
+// accumulators + the loads in flight inside the register budget
 template <int NR>
-__device__ __forceinline__ void bwd_item(const ForestSub& S, const ForestItem it, int pass, double* __restrict__ Y, int ldx, int lane) {
-  constexpr int CP = 32 / NR;
-  const FrontDev F = S.fronts[it.f];
-  const int k = F.k, h = F.h, ld = F.ld;
-  const int col0 = S.rowIdx[F.rowOff];
-  const int c0 = it.cb * SOLVE_COLS, nc = min(SOLVE_COLS, k - c0);
-  const int rbase = (k & ~1) + it.rb * BWD_ROWS + 2 * lane;  // even panel row; rows < k are masked out through y = 0
+__device__ __forceinline__ void bwd_item(const ForestSub& S, const ForestItem& it, int pass, double* __restrict__ Y, int ldx, int lane) {
+  constexpr int NA = NR == 1 ? 16 : 32;  // accumulators per lane
+  constexpr int CP = NA / NR;            // columns per pass
+  const int k = it.k, h = it.h, ld = it.ld;
+  const int cp = pass * CP;  // the 32 columns of an item are split into 32/CP independent passes (virtual items)
+  if (cp >= it.nc) return;
+  const int rbase = it.r0 + 2 * lane;  // even panel row; rows < k are masked out through y = 0
   double y0[2][NR], y1[2][NR];
   const double* Lt[2];
 #pragma unroll
   for (int t = 0; t < 2; t++) {
     const int r = rbase + t * 64;
     const bool ok0 = r >= k && r < h, ok1 = r + 1 >= k && r + 1 < h;
-    const int row0 = ok0 ? S.rowIdx[F.rowOff + r] : 0, row1 = ok1 ? S.rowIdx[F.rowOff + r + 1] : 0;
+    const int row0 = ok0 ? S.rowIdx[it.rowOff + r] : 0, row1 = ok1 ? S.rowIdx[it.rowOff + r + 1] : 0;
 #pragma unroll
     for (int j = 0; j < NR; j++) {
       y0[t][j] = ok0 ? Y[(size_t)(S.xoff + row0) * ldx + j] : 0.;
       y1[t][j] = ok1 ? Y[(size_t)(S.xoff + row1) * ldx + j] : 0.;
     }
-    Lt[t] = S.L + F.lOff + (size_t)c0 * ld + (r < h ? r : 0);
+    Lt[t] = S.L + it.lOff + (size_t)cp * ld + (r < h ? 2 * lane + t * 64 : 0);
   }
-  {
-    const int cp = pass * CP;  // a block solve splits the 32 columns of an item into NR independent passes (virtual items)
-    if (cp >= nc) return;
-    double acc[32];
+  double acc[NA];
 #pragma unroll
-    for (int q = 0; q < 32; q++) acc[q] = 0.;
+  for (int q = 0; q < NA; q++) acc[q] = 0.;
 #pragma unroll
-    for (int t = 0; t < 2; t++) {
+  for (int t = 0; t < 2; t++) {
 #pragma unroll
-      for (int cc = 0; cc < CP; cc++) {
-        if (cp + cc < nc) {  // warp-uniform
-          const double2 v = ldg2(Lt[t] + (size_t)(cp + cc) * ld);
+    for (int cc = 0; cc < CP; cc++) {
+      if (cp + cc < it.nc) {  // warp-uniform
+        const double2 v = ldg2(Lt[t] + (size_t)cc * ld);
 #pragma unroll
-          for (int j = 0; j < NR; j++) acc[cc * NR + j] += v.x * y0[t][j] + v.y * y1[t][j];
-        }
+        for (int j = 0; j < NR; j++) acc[cc * NR + j] += v.x * y0[t][j] + v.y * y1[t][j];
       }
     }
-    // butterfly transpose-reduction: lane q ends up with the warp-wide sum of acc[q]
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const bool upper = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < off; i++) {
-        const double send = upper ? acc[i] : acc[i + off];
-        const double keep = upper ? acc[i + off] : acc[i];
-        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-      }
-    }
-    const int cc = lane / NR, j = lane % NR;
-    if (cp + cc < nc) atomicAdd(&Y[(size_t)(S.xoff + col0 + c0 + cp + cc) * ldx + j], -acc[0]);
   }
+  // butterfly transpose-reduction: NA values over 32 lanes; lane q (mod NA) ends up with the warp-wide sum of acc[q]
+  if (NA == 16) {  // first fold the two half-warps onto each other
+#pragma unroll
+    for (int q = 0; q < 16; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+  }
+#pragma unroll
+  for (int off = (NA == 16 ? 8 : 16); off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; i++) {
+      const double send = upper ? acc[i] : acc[i + off];
+      const double keep = upper ? acc[i + off] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  const int q = NA == 16 ? (lane & 15) : lane;
+  const int cc = q / NR, j = q % NR;
+  if ((NA == 32 || lane < 16) && cp + cc < it.nc)
+    atomicAdd(&Y[(size_t)(S.xoff + it.col0 + it.c0 + cp + cc) * ldx + j], -acc[0]);
 }
 
 template <int NR>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
-k_solve_forest(const ForestSub* __restrict__ subs, const ForestItem* __restrict__ items, const int64_t* __restrict__ ranges,
+k_solve_forest(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* __restrict__ items, const int64_t* __restrict__ ranges,
                int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y, int ldx) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ ForestSub sSubs[MAX_SMEM_SUBS];
+  for (int t = threadIdx.x; t < min(nsubs, MAX_SMEM_SUBS); t += blockDim.x) sSubs[t] = subs[t];
+  const bool inSmem = nsubs <= MAX_SMEM_SUBS;
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -442,20 +455,35 @@ k_solve_forest(const ForestSub* __restrict__ subs, const ForestItem* __restrict_
   const int64_t* fwdCnt = ranges + nlev;
   const int64_t* bwdOff = ranges + 2 * nlev;
   const int64_t* bwdCnt = ranges + 3 * nlev;
+  constexpr int FS = NR >= 4 ? 4 : 1;
+  constexpr int BP = 32 / ((NR == 1 ? 16 : 32) / NR);  // backward passes per item
   for (int l = 0; l < nlev; l++) {
-    const int64_t off = fwdOff[l], cnt = fwdCnt[l];
-    constexpr int FS = NR >= 4 ? 4 : 1;
-    for (int64_t i = gw; i < cnt * FS; i += nw) {
-      const ForestItem it = items[off + i / FS];
-      fwd_item<NR>(subs[it.sub], it, (int)(i % FS), X, Y, ldx, lane);
+    const int64_t off = fwdOff[l], cnt = fwdCnt[l] * FS;
+    int64_t i = gw;
+    ForestItem cur;
+    if (i < cnt) cur = load_item(items + off + i / FS);
+    while (i < cnt) {
+      const int64_t in = i + nw;
+      ForestItem nxt = cur;
+      if (in < cnt) nxt = load_item(items + off + in / FS);  // the next item's record travels while this one streams
+      fwd_item<NR>(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, (int)(i % FS), X, Y, ldx, lane);
+      cur = nxt;
+      i = in;
     }
     grid.sync();
   }
   for (int l = nlev - 1; l >= 0; l--) {
-    const int64_t off = bwdOff[l], cnt = bwdCnt[l];
-    for (int64_t i = gw; i < cnt * NR; i += nw) {
-      const ForestItem it = items[off + i / NR];
-      bwd_item<NR>(subs[it.sub], it, (int)(i % NR), Y, ldx, lane);
+    const int64_t off = bwdOff[l], cnt = bwdCnt[l] * BP;
+    int64_t i = gw;
+    ForestItem cur;
+    if (i < cnt) cur = load_item(items + off + i / BP);
+    while (i < cnt) {
+      const int64_t in = i + nw;
+      ForestItem nxt = cur;
+      if (in < cnt) nxt = load_item(items + off + in / BP);
+      bwd_item<NR>(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, (int)(i % BP), Y, ldx, lane);
+      cur = nxt;
+      i = in;
     }
     if (l > 0) grid.sync();
   }
@@ -618,19 +646,25 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   for (int s = 0; s < ns; s++) { nlev = std::max(nlev, plans[s]->sym.nlevels); ntot = std::max<int64_t>(ntot, xoff[s] + plans[s]->sym.n); }
   std::vector<ForestItem> items;
   std::vector<int64_t> ranges(4 * (size_t)nlev, 0);
+  auto by_size = [](const ForestItem& a, const ForestItem& b) {  // big tiles first: the tail of a level is made of small ones
+    const int64_t sa = (int64_t)std::min(a.h - a.r0, BWD_ROWS) * a.nc, sb = (int64_t)std::min(b.h - b.r0, BWD_ROWS) * b.nc;
+    return sa > sb;
+  };
   for (int l = 0; l < nlev; l++) {  // forward + diagonal: every row of the panel
     ranges[l] = (int64_t)items.size();
     for (int s = 0; s < ns; s++) {
       const Symbolic& S = plans[s]->sym;
       if (l >= S.nlevels) continue;
       for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
-        const int f = S.levelFronts[t];
-        const Front& F = S.fronts[f];
+        const Front& F = S.fronts[S.levelFronts[t]];
         for (int rb = 0; rb * FWD_ROWS < F.h; rb++)
-          for (int cb = 0; cb * SOLVE_COLS < F.k; cb++) items.push_back(ForestItem{s, f, rb, cb});
+          for (int c0 = 0; c0 < F.k; c0 += SOLVE_COLS)
+            items.push_back(ForestItem{F.lOff + (int64_t)c0 * F.ld + rb * FWD_ROWS, F.rowOff, s, F.ld, F.h, F.k, c0,
+                                       std::min(SOLVE_COLS, F.k - c0), rb * FWD_ROWS, F.col0});
       }
     }
     ranges[nlev + l] = (int64_t)items.size() - ranges[l];
+    std::stable_sort(items.begin() + ranges[l], items.end(), by_size);
   }
   for (int l = 0; l < nlev; l++) {  // backward: the L21 rows, tiles start at the even row k & ~1
     ranges[2 * nlev + l] = (int64_t)items.size();
@@ -638,15 +672,17 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
       const Symbolic& S = plans[s]->sym;
       if (l >= S.nlevels) continue;
       for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
-        const int f = S.levelFronts[t];
-        const Front& F = S.fronts[f];
+        const Front& F = S.fronts[S.levelFronts[t]];
         if (F.m() == 0) continue;
-        const int span = F.h - (F.k & ~1);
-        for (int rb = 0; rb * BWD_ROWS < span; rb++)
-          for (int cb = 0; cb * SOLVE_COLS < F.k; cb++) items.push_back(ForestItem{s, f, rb, cb});
+        const int rstart = F.k & ~1;
+        for (int r0 = rstart; r0 < F.h; r0 += BWD_ROWS)
+          for (int c0 = 0; c0 < F.k; c0 += SOLVE_COLS)
+            items.push_back(ForestItem{F.lOff + (int64_t)c0 * F.ld + r0, F.rowOff, s, F.ld, F.h, F.k, c0,
+                                       std::min(SOLVE_COLS, F.k - c0), r0, F.col0});
       }
     }
     ranges[3 * nlev + l] = (int64_t)items.size() - ranges[2 * nlev + l];
+    std::stable_sort(items.begin() + ranges[2 * nlev + l], items.end(), by_size);
   }
   dItems.upload(items);
   dRanges.upload(ranges);
@@ -676,11 +712,12 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   double* Xp = X + j0;
   double* Yp = Y + j0;
   const ForestSub* subs = dSubs.p;
+  int nsubs = (int)hSubs.size();
   const ForestItem* items = dItems.p;
   const int64_t* ranges = dRanges.p;
   int nl = nlev;
   int64_t nt = ntot;
-  void* args[] = {(void*)&subs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ldx};
+  void* args[] = {(void*)&subs, (void*)&nsubs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ldx};
   const void* fn = nullptr;
   int q = 0;
   switch (nr) {
@@ -692,6 +729,51 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   }
   (void)GENEO_TICK(0);
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(SOLVE_THREADS), args, 0, st));
+}
+
+// Synthetic streaming benchmark of the solve kernel: nf independent h x k panels at ONE level (no level effects, no
+// small fronts): what fraction of the HBM bandwidth do the forward / backward tiles reach on their own?
+double solve_stream_bench(int nf, int h, int k, int reps, double* gbps) {
+  Symbolic S;
+  S.n = nf * h;
+  S.nb = 128;
+  S.fronts.resize(nf);
+  S.rowIdx.resize((size_t)nf * h);
+  for (int64_t i = 0; i < (int64_t)nf * h; i++) S.rowIdx[i] = (int)i;
+  int64_t lOff = 0;
+  for (int f = 0; f < nf; f++) {
+    Front& F = S.fronts[f];
+    F.col0 = f * h; F.k = k; F.h = h; F.ld = (h + 1) & ~1; F.parent = -1; F.level = 0; F.rowOff = (int64_t)f * h; F.lOff = lOff;
+    lOff += (int64_t)F.ld * k;
+  }
+  S.lSize = lOff;
+  S.nlevels = 1;
+  S.levelPtr = {0, nf};
+  S.levelFronts.resize(nf);
+  for (int f = 0; f < nf; f++) S.levelFronts[f] = f;
+  S.perm.resize(S.n); S.iperm.resize(S.n);
+  for (int i = 0; i < S.n; i++) S.perm[i] = S.iperm[i] = i;
+  S.frontOfCol.assign(S.n, 0);
+  auto plan = std::make_shared<LdltPlan>(std::move(S));
+  DevBuf<double> L((size_t)lOff), X((size_t)nf * h), Y((size_t)nf * h);
+  CUDA_CHECK(cudaMemset(L.p, 0, L.bytes()));
+  CUDA_CHECK(cudaMemset(X.p, 0, X.bytes()));
+  SolveForest F;
+  F.build({plan.get()}, {0});
+  F.set_factors({L.p}, 0);
+  for (int i = 0; i < 2; i++) F.solve(X.p, Y.p, 1, 0, 1, 0);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, 0));
+  for (int i = 0; i < reps; i++) F.solve(X.p, Y.p, 1, 0, 1, 0);
+  CUDA_CHECK(cudaEventRecord(e1, 0));
+  CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const double bytes = (double)nf * 8. * (2. * (double)(h - k) * k + (double)k * k);
+  if (gbps) *gbps = bytes * reps / (ms * 1e-3) / 1e9;
+  return ms / reps;
 }
 
 void LdltFactor::solve_permuted(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const {

@@ -38,7 +38,9 @@ class LdltPlan {
 
 // ---- level-scheduled solves over a forest of factors (one persistent cooperative kernel) -----------------------------
 struct ForestSub { const double* L; const FrontDev* fronts; const int* rowIdx; int64_t xoff; };
-struct ForestItem { int sub, f, rb, cb; };
+// self-contained work item (48 bytes, three 16-byte loads): nothing but the subdomain's base pointers (kept in shared
+// memory) stands between reading the item and issuing the factor loads
+struct ForestItem { int64_t lOff, rowOff; int sub, ld, h, k; int c0, nc, r0, col0; };
 class SolveForest {
  public:
   // plans[s] solves rows [xoff[s], xoff[s]+n_s) of the concatenated (permuted) vectors
@@ -85,6 +87,8 @@ class LdltFactor {
   mutable std::unique_ptr<SolveForest> self_;  // single-factor forest (eigen-solver, coarse operator)
   mutable const double* selfL_ = nullptr;
 };
+
+double solve_stream_bench(int nf, int h, int k, int reps, double* gbps);  // ms per solve; synthetic one-level forest
 
 // DGEMM self-test hooks (microbenchmarks / parity tests of the DMMA tile kernel).
 void dgemm_nt_device(int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,

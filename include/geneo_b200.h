@@ -163,7 +163,9 @@ int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32
                        int64_t* asmDst);
 int geneo_host_sym_eig(int n, double* a /* row-major in, eigenvectors (columns) out */, double* w);
 /* microbenchmarks on the device (first-run calibration): kind 0 = DMMA 64x64-tile GEMM C=AB^T (M=N=K=n) TFLOP/s,
- * kind 1 = device copy GB/s over n doubles.  result[0] = rate, result[1] = max abs error vs a reference (kind 0). */
+ * kind 1 = device copy GB/s over n doubles, kind 2 = solve-kernel streaming over ~2 GB of synthetic n x 128 panels at a
+ * single level (result[0] = algorithmic GB/s, result[1] = ms per solve).  result[0] = rate, result[1] = max abs error vs a
+ * reference (kind 0). */
 int geneo_microbench(int kind, int n, int reps, double result[2]);
 
 #ifdef __cplusplus
