@@ -6,6 +6,9 @@
 #include <cmath>
 #include <cstring>
 #include <sstream>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "dense_host.hpp"
@@ -292,8 +295,51 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   if (opt.lvl2 == 2 && !opt.lvl1ORAS)
     throw Error("geneo_b200: GenEO-2 needs an optimised level 1 (ORAS/SORAS) -- untested/unsupported in the reference too");
 
-  // ---- operator A = sum_i R_i^T A_neu,i R_i  (MatConvert MATIS->AIJ, src/geneo.cpp:1692), SELL-32 on the device ------
   double t0 = now_s();
+  // ---- pipeline: worker threads do the host analysis of the subdomains IN ORDER (a few at a time, each one using the
+  //      other cores for the top levels of its nested dissection) while this thread uploads and runs the whole numeric
+  //      phase of every subdomain that is ready -> the device factorizes subdomain p while the host orders p+1, p+2.
+  t0 = now_s();
+  const int P = (int)mine.size();
+  std::vector<HostPrep> prep(P);
+  subs.resize(P);
+  nAll = 0;
+  for (int p = 0; p < P; p++) { subs[p].id = mine[p]->id; subs[p].n = (int)mine[p]->nodes.size(); subs[p].off = nAll; nAll += subs[p].n; }
+  connectivity.assign((size_t)dec.nbPart * dec.nbPart, 0);
+  for (int r = 0; r < dec.nbPart; r++)
+    for (int q = 0; q < dec.nbPart; q++) connectivity[(size_t)r * dec.nbPart + q] = dec.subs[r].intersect[q].empty() ? 1 : 0;
+  if (layout && comm.active()) {  // a rank only knows the intersections of ITS subdomains: rows are summed over the ranks
+    std::vector<double> c((size_t)dec.nbPart * dec.nbPart, 0.);
+    for (int r = 0; r < dec.nbPart; r++)
+      if (layout->subRank[r] == layout->rank)
+        for (int q = 0; q < dec.nbPart; q++) c[(size_t)r * dec.nbPart + q] = connectivity[(size_t)r * dec.nbPart + q];
+    comm.allreduce_sum_host(c.data(), (int)c.size(), st);
+    for (size_t t = 0; t < c.size(); t++) connectivity[t] = c[t] > 0.5 ? 1 : 0;
+  }
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int inFlight = std::max(1, std::min(P, hw >= 8 ? 2 : 1));  // subdomains analysed concurrently
+  int ndDepth = 0;
+  while ((unsigned)(inFlight << (ndDepth + 1)) <= hw && ndDepth < 4) ndDepth++;
+  std::mutex mtx;
+  std::condition_variable cv;
+  std::vector<char> ready(P, 0);
+  std::atomic<int> ticket(0);
+  std::vector<std::thread> pool;
+  for (int w = 0; w < inFlight; w++)
+    pool.emplace_back([&]() {
+      for (;;) {
+        const int p = ticket.fetch_add(1);
+        if (p >= P) break;
+        try { prepare_subdomain(*mine[p], opt, ndDepth, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
+        { std::lock_guard<std::mutex> lk(mtx); ready[p] = 1; }
+        cv.notify_all();
+      }
+    });
+  struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); } } joiner{pool};
+
+  // (assembled by this thread while the workers are already busy with the first subdomains)
+  // ---- operator A = sum_i R_i^T A_neu,i R_i  (MatConvert MATIS->AIJ, src/geneo.cpp:1692), SELL-32 on the device ------
+  t0 = now_s();
   if (layout) {
     A.build(layout->A, st);  // owned rows, assembled from the elements (mesh.cpp build_rank_layout)
   } else {
@@ -332,80 +378,30 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   }
   operatorTime = now_s() - t0;
 
-  // ---- host symbolic analysis of every subdomain, in parallel worker threads ---------------------------------------------
-  t0 = now_s();
-  const int P = (int)mine.size();
-  std::vector<HostPrep> prep(P);
-  {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    unsigned nt = std::max(1u, std::min((unsigned)P, hw));
-    int ndDepth = 0;  // spare host cores order the two halves of the top separators concurrently
-    while (P > 0 && ((unsigned)P << (ndDepth + 1)) <= hw && ndDepth < 3) ndDepth++;
-    std::vector<std::thread> pool;
-    for (unsigned tid = 0; tid < nt; tid++)
-      pool.emplace_back([&, tid]() {
-        for (int p = tid; p < P; p += nt) {
-          try { prepare_subdomain(*mine[p], opt, ndDepth, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
-        }
-      });
-    for (auto& t : pool) t.join();
-    for (auto& h : prep)
-      if (!h.err.empty()) throw Error(h.err);
-  }
-  symbolicTime = now_s() - t0;
 
-  // ---- concatenated subdomain layout, pull-prolong structure ---------------------------------------------------------------
-  subs.resize(P);
-  nAll = 0;
-  for (int p = 0; p < P; p++) { subs[p].id = mine[p]->id; subs[p].n = (int)mine[p]->nodes.size(); subs[p].off = nAll; nAll += subs[p].n; }
-  {
-    std::vector<int> gAll((size_t)nAll);
-    std::vector<double> dA((size_t)nAll);
-    std::vector<int64_t> pp(nLoc + 1, 0);
-    for (int p = 0; p < P; p++)
-      for (int k = 0; k < subs[p].n; k++) {
-        prep[p].gidx[k] = localIndex(prep[p].gidx[k]);
-        GENEO_CHECK(prep[p].gidx[k] >= 0, "multi-GPU layout: a subdomain node is neither owned nor ghost");
-        gAll[subs[p].off + k] = prep[p].gidx[k]; dA[subs[p].off + k] = prep[p].dP[k]; pp[prep[p].gidx[k] + 1]++;
-      }
-    for (int i = 0; i < nLoc; i++) pp[i + 1] += pp[i];
-    std::vector<int64_t> ps((size_t)nAll);
-    std::vector<int64_t> cur(pp.begin(), pp.end() - 1);
-    for (int p = 0; p < P; p++)  // ascending subdomain id inside every row: deterministic summation order
-      for (int k = 0; k < subs[p].n; k++) ps[cur[prep[p].gidx[k]]++] = subs[p].off + k;
-    gidxAll.upload(gAll, st);
-    dAll.upload(dA, st);
-    pullPtr.upload(pp, st);
-    pullPos.upload(ps, st);
-    CUDA_CHECK(::geneo::sync_stream(st));
-  }
-  Xall.alloc((size_t)nAll); Yall.alloc((size_t)nAll);
-  t1.alloc(nLoc); t2.alloc(nLoc); t3.alloc(nLoc);
-  const int nstreams = std::min(P, 8);
-  streams.resize(nstreams);
-  events.resize(nstreams);
-  for (int i = 0; i < nstreams; i++) {
-    CUDA_CHECK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&events[i], cudaEventDisableTiming));
-  }
-  CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
-
-  // ---- upload every subdomain's matrices (the numeric phase below only touches device-resident data) ----------------
-  t0 = now_s();
-  connectivity.assign((size_t)dec.nbPart * dec.nbPart, 0);
-  for (int r = 0; r < dec.nbPart; r++)
-    for (int q = 0; q < dec.nbPart; q++) connectivity[(size_t)r * dec.nbPart + q] = dec.subs[r].intersect[q].empty() ? 1 : 0;
-  if (layout && comm.active()) {  // a rank only knows the intersections of ITS subdomains: rows are summed over the ranks
-    std::vector<double> c((size_t)dec.nbPart * dec.nbPart, 0.);
-    for (int r = 0; r < dec.nbPart; r++)
-      if (layout->subRank[r] == layout->rank)
-        for (int q = 0; q < dec.nbPart; q++) c[(size_t)r * dec.nbPart + q] = connectivity[(size_t)r * dec.nbPart + q];
-    comm.allreduce_sum_host(c.data(), (int)c.size(), st);
-    for (size_t t = 0; t < c.size(); t++) connectivity[t] = c[t] > 0.5 ? 1 : 0;
-  }
+  numeric_begin();
+  LdltWorkspace ws;
+  std::vector<int> gAll((size_t)nAll);
+  std::vector<double> dA((size_t)nAll);
+  double waitHost = 0., tUp = 0., tNum = 0.;
   for (int p = 0; p < P; p++) {
-    SubdomainState& s = subs[p];
+    {
+      const double tw = now_s();
+      std::unique_lock<std::mutex> lk(mtx);
+      cv.wait(lk, [&]() { return ready[p] != 0; });
+      waitHost += now_s() - tw;
+    }
     HostPrep& H = prep[p];
+    if (!H.err.empty()) throw Error(H.err);
+    const double tu = now_s();
+    SubdomainState& s = subs[p];
+    for (int k = 0; k < s.n; k++) {
+      const int li = localIndex(H.gidx[k]);
+      GENEO_CHECK(li >= 0, "multi-GPU layout: a subdomain node is neither owned nor ghost");
+      H.gidx[k] = li;
+      gAll[s.off + k] = li;
+      dA[s.off + k] = H.dP[k];
+    }
     s.maxMult = H.maxMult;
     s.anorm = H.anorm;
     s.plan = std::make_shared<LdltPlan>(std::move(H.sym));
@@ -416,27 +412,53 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     s.d.upload(H.dP, st);
     CUDA_CHECK(::geneo::sync_stream(st));
     H = HostPrep();  // free host memory early
+    tUp += now_s() - tu;
+    const double tn = now_s();
+    numeric_subdomain(s, ws);
+    tNum += now_s() - tn;
   }
-  uploadTime = now_s() - t0;
-  numeric_setup();
+  ws = LdltWorkspace();
+  symbolicTime = waitHost;  // time this thread spent WAITING for the host analysis (the rest of it was hidden behind the device)
+  uploadTime = tUp;
+
+  // ---- concatenated subdomain layout, pull-prolong structure ---------------------------------------------------------------
+  t0 = now_s();
+  {
+    std::vector<int64_t> pp(nLoc + 1, 0);
+    for (int64_t t = 0; t < nAll; t++) pp[gAll[t] + 1]++;
+    for (int i = 0; i < nLoc; i++) pp[i + 1] += pp[i];
+    std::vector<int64_t> ps((size_t)nAll);
+    std::vector<int64_t> cur(pp.begin(), pp.end() - 1);
+    for (int64_t t = 0; t < nAll; t++) ps[cur[gAll[t]]++] = t;  // ascending subdomain id inside every row: deterministic sums
+    gidxAll.upload(gAll, st);
+    dAll.upload(dA, st);
+    pullPtr.upload(pp, st);
+    pullPos.upload(ps, st);
+    CUDA_CHECK(::geneo::sync_stream(st));
+  }
+  Xall.alloc((size_t)nAll); Yall.alloc((size_t)nAll);
+  t1.alloc(nLoc); t2.alloc(nLoc); t3.alloc(nLoc);
+  uploadTime += now_s() - t0;
+  const double te = now_s();
+  numeric_end();
+  numericTime = tNum + (now_s() - te);
   setupTime = now_s() - tSetup0;
 }
 
-void GeneoPC::numeric_setup() {
-  const double tNum0 = now_s();
+void GeneoPC::numeric_begin() {
   lvl1SetupMinvTime = lvl2SetupSylTime = lvl2SetupEigTime = lvl2SetupZTime = lvl2SetupETime = 0.;
   lvl2SetupTauLocTime = lvl2SetupTauSylTime = lvl2SetupTauEigTime = 0.;
   lvl2SetupGammaLocTime = lvl2SetupGammaSylTime = lvl2SetupGammaEigTime = 0.;
   estimDimE = realDimE = nicolaides = 0;
   factorBytes = factorNnz = 0;
   factorFlops = 0.;
-  LdltWorkspace ws;
   for (auto& s : subs) {
     s.estim = s.nicolaides = s.eigSteps = s.eigDim = s.negL1 = s.perturbed = 0;
     s.nev = 0;
-    numeric_subdomain(s, ws);
   }
-  ws = LdltWorkspace();
+}
+
+void GeneoPC::numeric_end() {
   if (comm.active()) {  // the driver prints GLOBAL dimensions (src/geneo4PETSc.cpp:971-986 reduces them over the ranks)
     double g[3] = {(double)estimDimE, (double)realDimE, (double)nicolaides};
     comm.allreduce_sum_host(g, 3, st);
@@ -461,6 +483,15 @@ void GeneoPC::numeric_setup() {
     infoL2 = "blocklanczos ldlt";
   }
   CUDA_CHECK(::geneo::sync_stream(st));
+}
+
+void GeneoPC::numeric_setup() {
+  const double tNum0 = now_s();
+  numeric_begin();
+  LdltWorkspace ws;
+  for (auto& s : subs) numeric_subdomain(s, ws);
+  ws = LdltWorkspace();
+  numeric_end();
   numericTime = now_s() - tNum0;
 }
 
@@ -596,15 +627,18 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
   int got = 0;
   if (opt.noSyl || est > 0) {
     const double t0 = now_s();
+    // Two guard pairs beyond the Sylvester estimate: the threshold filter below decides what is kept, so a pivot of
+    // A - theta B whose sign is lost to rounding (no pivoting across pivot blocks) cannot drop a genuine GenEO vector.
+    const int guard = (!opt.noSyl && (opt.cut <= 0 || nev < opt.cut)) ? 2 : 0;
     EigOptions eo;
     eo.block = opt.epsBlock; eo.tol = opt.epsTol; eo.maxDim = opt.epsMaxDim; eo.invert = tauPb;
     EigResult er;
     if (tauPb) {  // A x = lambda B x, smallest: T = A^-1 B
       tmp.factorize(vA, pivTol, ws, st);
-      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vB, std::min(nev, n), eo, er, st);
+      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vB, std::min(nev + guard, n), eo, er, st);
     } else {      // A x = lambda B x, largest: T = B^-1 A, self-adjoint in the A inner product
       tmp.factorize(vB, pivTol, ws, st);
-      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vA, std::min(nev, n), eo, er, st);
+      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vA, std::min(nev + guard, n), eo, er, st);
     }
     if (er.nconv < (int)er.lambda.size())
       fprintf(stderr, "WRNG: geneo_b200: eigen solve of subdomain %d converged %d/%d pairs (dim %d)\n", s.id, er.nconv,
@@ -615,6 +649,7 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     for (size_t i = 0; i < er.lambda.size(); i++) {
       const bool keep = tauPb ? (er.lambda[i] <= param) : (er.lambda[i] >= param);
       if (!keep) break;
+      if (opt.cut > 0 && (int)lam.size() >= opt.cut) break;  // -geneo_cut caps what is kept (src/geneo.cpp:532, 871-879)
       lam.push_back(er.lambda[i]);
     }
     got = (int)lam.size();

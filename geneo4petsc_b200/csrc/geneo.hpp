@@ -104,6 +104,8 @@ class GeneoPC {
   // Numeric half of the setup again (every factorization, eigen-solve, Z, E) on the matrices already resident in HBM:
   // PCSetUp with an unchanged non-zero pattern.  setup() = host analysis + uploads + numeric_setup().
   void numeric_setup();
+  void numeric_begin();
+  void numeric_end();
   // accumulated CUDA-event time of the level-1 solve kernel since the last call (ms) and its number of launches
   void kernel_time(double* ms, int64_t* launches);
   void apply(const double* x, double* y);                 // device pointers, length nLoc; x is not modified

@@ -322,6 +322,10 @@ __device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem& i
   const double* Lp = S.L + it.lOff + (size_t)cs * ld + (r0 < h ? 2 * lane : 0);
   double xv = 0.;
   if (NR == 1) xv = lane < nc ? x1[lane] : 0.;
+  // target rows of the two results: issued now so that they travel together with the factor loads
+  int row0 = -1, row1 = -1;
+  if (r0 >= k && r0 < h) row0 = S.rowIdx[it.rowOff + r0];
+  if (r0 + 1 >= k && r0 + 1 < h) row1 = S.rowIdx[it.rowOff + r0 + 1];
   double a0[NR], a1[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) a0[j] = a1[j] = 0.;
@@ -370,7 +374,7 @@ __device__ __forceinline__ void fwd_item(const ForestSub& S, const ForestItem& i
 #pragma unroll
       for (int j = 0; j < NR; j++) atomicAdd(dst + j, e ? a1[j] : a0[j]);
     } else {      // L21 rows
-      double* dst = X + (size_t)(S.xoff + S.rowIdx[it.rowOff + r]) * ldx;
+      double* dst = X + (size_t)(S.xoff + (e ? row1 : row0)) * ldx;
 #pragma unroll
       for (int j = 0; j < NR; j++) atomicAdd(dst + j, -(e ? a1[j] : a0[j]));
     }

@@ -62,6 +62,7 @@ struct SymbolicOptions {
   int nb = 128;        // panel width
   int ordering = 1;    // 0 natural, 1 METIS NodeND
   bool amalgamate = true;
+  int subtreeCols = 64; // subtrees of the assembly tree with at most this many columns are merged into one dense front
   int ndDepth = 0;     // top levels of the nested dissection done here (METIS_ComputeVertexSeparator) with the two halves
                        // ordered by concurrent threads: 2^ndDepth threads per matrix; 0 = plain METIS_NodeND
 };
