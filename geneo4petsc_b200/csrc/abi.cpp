@@ -592,6 +592,11 @@ int geneo_microbench(int kind, int n, int reps, double result[2]) {
     double gb = 0.;
     result[1] = solve_stream_bench(nf, h, k, reps, &gb);  // ms per solve (forward + backward)
     result[0] = gb;                                       // algorithmic GB/s
+  } else if (kind >= 100) {  // level-latency probe: kind = 100*nlev + nr; nlev levels of `reps` fronts of n x 128 each
+    const int nlev = kind / 100, nr = kind % 100;
+    double gb = 0.;
+    result[1] = solve_stream_bench(reps, std::max(n, 128), 128, 5, &gb, nlev, nr);
+    result[0] = gb;
   } else if (kind == 0) {
     std::vector<double> hA((size_t)n * n), hB((size_t)n * n);
     for (size_t i = 0; i < hA.size(); i++) { hA[i] = (double)((i * 2654435761u) % 1000) / 1000. - 0.5; hB[i] = (double)((i * 40503u) % 1000) / 1000. - 0.5; }

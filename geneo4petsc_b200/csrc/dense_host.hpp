@@ -102,7 +102,12 @@ inline void sym_eig(int n, double* a, double* w) {
   for (int j = 0; j < n; j++) { d[j] = V(n - 1, j); V(n - 1, j) = 0.; }
   V(n - 1, n - 1) = 1.;
   e[0] = 0.;
-  // implicit QL
+  // implicit QL.  The rotations combine two COLUMNS of V: they run on the transpose (two contiguous rows, vectorisable),
+  // which is what makes the O(n^3) accumulation of the eigenvectors cheap for the projected matrices of the block
+  // Lanczos solver (n up to a few hundred, once per step).
+  std::vector<double> vt((size_t)n * n);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) vt[(size_t)j * n + i] = V(i, j);
   for (int i = 1; i < n; i++) e[i - 1] = e[i];
   e[n - 1] = 0.;
   double f = 0., tst1 = 0.;
@@ -138,10 +143,14 @@ inline void sym_eig(int n, double* a, double* w) {
           c = p / r;
           p = c * d[i] - s * g;
           d[i + 1] = h + s * (c * g + s * d[i]);
-          for (int k = 0; k < n; k++) {
-            h = V(k, i + 1);
-            V(k, i + 1) = s * V(k, i) + c * h;
-            V(k, i) = c * V(k, i) - s * h;
+          {
+            double* __restrict__ vi = &vt[(size_t)i * n];
+            double* __restrict__ vi1 = &vt[(size_t)(i + 1) * n];
+            for (int k = 0; k < n; k++) {
+              const double hh = vi1[k];
+              vi1[k] = s * vi[k] + c * hh;
+              vi[k] = c * vi[k] - s * hh;
+            }
           }
         }
         p = -s * s2 * c3 * el1 * e[l] / dl1;
@@ -152,7 +161,7 @@ inline void sym_eig(int n, double* a, double* w) {
     d[l] = d[l] + f;
     e[l] = 0.;
   }
-  // sort ascending (selection sort on columns)
+  // sort ascending (selection sort on the rows of the transpose), then back to column layout
   for (int i = 0; i < n - 1; i++) {
     int k = i;
     double p = d[i];
@@ -161,9 +170,11 @@ inline void sym_eig(int n, double* a, double* w) {
     if (k != i) {
       d[k] = d[i];
       d[i] = p;
-      for (int j = 0; j < n; j++) std::swap(V(j, i), V(j, k));
+      std::swap_ranges(&vt[(size_t)i * n], &vt[(size_t)i * n] + n, &vt[(size_t)k * n]);
     }
   }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) V(i, j) = vt[(size_t)j * n + i];
 }
 
 }  // namespace geneo

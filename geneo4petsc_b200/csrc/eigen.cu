@@ -209,16 +209,19 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       launch_solve(j + 1);
       prefetched = true;
     }
-    // Rayleigh-Ritz on the symmetrised leading dim x dim block
+    // Rayleigh-Ritz on the symmetrised leading dim x dim block (skipped while the basis is too small for nev pairs to
+    // have converged: the O(dim^3) host eigen-solve is the one serial piece of a step)
+    const int want = std::min(nev, dim);
+    int nconv = 0;
+    const bool doRR = !(canContinue && dim < nev + b);
+    if (doRR) {
     T.assign((size_t)dim * dim, 0.);
     for (int i = 0; i < dim; i++)
       for (int c = 0; c < dim; c++) T[(size_t)i * dim + c] = 0.5 * (Hm[(size_t)i * maxDim + c] + Hm[(size_t)c * maxDim + i]);
     theta.assign(dim, 0.);
     sym_eig(dim, T.data(), theta.data());
-    const int want = std::min(nev, dim);
     ritzVal.assign(want, 0.);
     ritzRes.assign(want, 0.);
-    int nconv = 0;
     for (int q = 0; q < want; q++) {
       const int col = dim - 1 - q;  // largest theta first
       double s2 = 0.;
@@ -230,6 +233,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       ritzVal[q] = theta[col];
       ritzRes[q] = std::sqrt(s2) / std::max(std::fabs(theta[col]), 1e-300);
       if (ritzRes[q] <= opt.tol) nconv++;
+    }
     }
     steps++;
     res.nconv = nconv;

@@ -737,45 +737,48 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
 
 // Synthetic streaming benchmark of the solve kernel: nf independent h x k panels at ONE level (no level effects, no
 // small fronts): what fraction of the HBM bandwidth do the forward / backward tiles reach on their own?
-double solve_stream_bench(int nf, int h, int k, int reps, double* gbps) {
+double solve_stream_bench(int nf, int h, int k, int reps, double* gbps, int nlev, int nr) {
+  // nlev levels of nf independent h x k panels each (level l front f: rows/cols disjoint from everything else)
   Symbolic S;
-  S.n = nf * h;
+  const int nt = nf * nlev;
+  S.n = nt * h;
   S.nb = 128;
-  S.fronts.resize(nf);
-  S.rowIdx.resize((size_t)nf * h);
-  for (int64_t i = 0; i < (int64_t)nf * h; i++) S.rowIdx[i] = (int)i;
+  S.fronts.resize(nt);
+  S.rowIdx.resize((size_t)nt * h);
+  for (int64_t i = 0; i < (int64_t)nt * h; i++) S.rowIdx[i] = (int)i;
   int64_t lOff = 0;
-  for (int f = 0; f < nf; f++) {
+  for (int f = 0; f < nt; f++) {
     Front& F = S.fronts[f];
-    F.col0 = f * h; F.k = k; F.h = h; F.ld = (h + 1) & ~1; F.parent = -1; F.level = 0; F.rowOff = (int64_t)f * h; F.lOff = lOff;
+    F.col0 = f * h; F.k = k; F.h = h; F.ld = (h + 1) & ~1; F.parent = -1; F.level = f / nf; F.rowOff = (int64_t)f * h; F.lOff = lOff;
     lOff += (int64_t)F.ld * k;
   }
   S.lSize = lOff;
-  S.nlevels = 1;
-  S.levelPtr = {0, nf};
-  S.levelFronts.resize(nf);
-  for (int f = 0; f < nf; f++) S.levelFronts[f] = f;
+  S.nlevels = nlev;
+  S.levelPtr.resize(nlev + 1);
+  for (int l = 0; l <= nlev; l++) S.levelPtr[l] = l * nf;
+  S.levelFronts.resize(nt);
+  for (int f = 0; f < nt; f++) S.levelFronts[f] = f;
   S.perm.resize(S.n); S.iperm.resize(S.n);
   for (int i = 0; i < S.n; i++) S.perm[i] = S.iperm[i] = i;
   S.frontOfCol.assign(S.n, 0);
   auto plan = std::make_shared<LdltPlan>(std::move(S));
-  DevBuf<double> L((size_t)lOff), X((size_t)nf * h), Y((size_t)nf * h);
+  DevBuf<double> L((size_t)lOff), X((size_t)nt * h * nr), Y((size_t)nt * h * nr);
   CUDA_CHECK(cudaMemset(L.p, 0, L.bytes()));
   CUDA_CHECK(cudaMemset(X.p, 0, X.bytes()));
   SolveForest F;
   F.build({plan.get()}, {0});
   F.set_factors({L.p}, 0);
-  for (int i = 0; i < 2; i++) F.solve(X.p, Y.p, 1, 0, 1, 0);
+  for (int i = 0; i < 2; i++) F.solve(X.p, Y.p, nr, 0, nr, 0);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, 0));
-  for (int i = 0; i < reps; i++) F.solve(X.p, Y.p, 1, 0, 1, 0);
+  for (int i = 0; i < reps; i++) F.solve(X.p, Y.p, nr, 0, nr, 0);
   CUDA_CHECK(cudaEventRecord(e1, 0));
   CUDA_CHECK(cudaEventSynchronize(e1));
   float ms = 0.f;
   CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  const double bytes = (double)nf * 8. * (2. * (double)(h - k) * k + (double)k * k);
+  const double bytes = (double)nt * 8. * (2. * (double)(h - k) * k + (double)k * k);
   if (gbps) *gbps = bytes * reps / (ms * 1e-3) / 1e9;
   return ms / reps;
 }

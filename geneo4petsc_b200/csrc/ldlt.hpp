@@ -88,7 +88,7 @@ class LdltFactor {
   mutable const double* selfL_ = nullptr;
 };
 
-double solve_stream_bench(int nf, int h, int k, int reps, double* gbps);  // ms per solve; synthetic one-level forest
+double solve_stream_bench(int nf, int h, int k, int reps, double* gbps, int nlev = 1, int nr = 1);  // ms per solve; synthetic one-level forest
 
 // DGEMM self-test hooks (microbenchmarks / parity tests of the DMMA tile kernel).
 void dgemm_nt_device(int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
