@@ -493,6 +493,185 @@ k_solve_forest(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// NR = 1 (the preconditioner application): same tiles, but the first PF column loads of a warp's NEXT item are issued
+// BEFORE the grid barrier that ends the current level.  The factor does not depend on the barrier (only x / y do), so the
+// HBM latency of the first round of every level -- the dominant cost of a level that holds only one or two rounds of
+// tiles -- is hidden behind the barrier itself.  Level ranges and subdomain pointers sit in shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PF = 8;          // loads prefetched across the barrier = columns per backward pass
+constexpr int BPASS = 32 / PF;  // backward passes (virtual items) per 32-column item
+constexpr int MAX_SMEM_LEVELS = 512;
+
+__device__ __forceinline__ void issue1(const ForestSub& S, const ForestItem& it, bool bwd, int pass, int lane, double2 (&v)[PF]) {
+  const int cp = bwd ? pass * PF : 0;
+  const int r = it.r0 + 2 * lane;
+  const double* Lp = S.L + it.lOff + (size_t)cp * it.ld + (r < it.h ? 2 * lane : 0);
+  const int nc = it.nc - cp;
+#pragma unroll
+  for (int u = 0; u < PF; u++)
+    if (u < nc) v[u] = ldg2(Lp + (size_t)u * it.ld);  // warp-uniform predicate
+}
+
+__device__ __forceinline__ void consume_fwd1(const ForestSub& S, const ForestItem& it, double* __restrict__ X,
+                                             double* __restrict__ Y, int lane, const double2 (&v)[PF]) {
+  const int k = it.k, h = it.h, ld = it.ld, nc = it.nc;
+  const int r0 = it.r0 + 2 * lane;
+  const double* x1 = X + (S.xoff + it.col0 + it.c0);
+  const double xv = lane < nc ? x1[lane] : 0.;
+  int row0 = -1, row1 = -1;
+  if (r0 >= k && r0 < h) row0 = S.rowIdx[it.rowOff + r0];
+  if (r0 + 1 >= k && r0 + 1 < h) row1 = S.rowIdx[it.rowOff + r0 + 1];
+  const double* Lp = S.L + it.lOff + (r0 < h ? 2 * lane : 0);
+  double a0 = 0., a1 = 0.;
+#pragma unroll
+  for (int half = 0; half < (SOLVE_COLS - PF) / 8; half++) {  // the rest of the 32 columns, 8 loads at a time, issued before the first FMAs
+    double2 w[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (PF + half * 8 + u < nc) w[u] = ldg2(Lp + (size_t)(PF + half * 8 + u) * ld);
+    if (half == 0) {
+#pragma unroll
+      for (int u = 0; u < PF; u++)
+        if (u < nc) {
+          const double xc = __shfl_sync(0xffffffffu, xv, u);
+          a0 += v[u].x * xc;
+          a1 += v[u].y * xc;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (PF + half * 8 + u < nc) {
+        const double xc = __shfl_sync(0xffffffffu, xv, PF + half * 8 + u);
+        a0 += w[u].x * xc;
+        a1 += w[u].y * xc;
+      }
+  }
+  if (r0 < h) {
+    if (r0 < k) atomicAdd(Y + (S.xoff + it.col0 + r0), a0);
+    else atomicAdd(X + (S.xoff + row0), -a0);
+  }
+  if (r0 + 1 < h) {
+    if (r0 + 1 < k) atomicAdd(Y + (S.xoff + it.col0 + r0 + 1), a1);
+    else atomicAdd(X + (S.xoff + row1), -a1);
+  }
+}
+
+__device__ __forceinline__ void consume_bwd1(const ForestSub& S, const ForestItem& it, int pass, double* __restrict__ Y,
+                                             int lane, const double2 (&v)[PF]) {
+  const int k = it.k, h = it.h, ld = it.ld;
+  const int cp = pass * PF;
+  const int nc = it.nc - cp;
+  if (nc <= 0) return;
+  const int rbase = it.r0 + 2 * lane;
+  double y0[2], y1[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const int r = rbase + t * 64;
+    const bool ok0 = r >= k && r < h, ok1 = r + 1 >= k && r + 1 < h;
+    const int rw0 = ok0 ? S.rowIdx[it.rowOff + r] : 0, rw1 = ok1 ? S.rowIdx[it.rowOff + r + 1] : 0;
+    y0[t] = ok0 ? Y[S.xoff + rw0] : 0.;
+    y1[t] = ok1 ? Y[S.xoff + rw1] : 0.;
+  }
+  const double* L1 = S.L + it.lOff + (size_t)cp * ld + (rbase + 64 < h ? 2 * lane + 64 : 0);
+  double acc[PF];
+#pragma unroll
+  for (int half = 0; half < PF / 8; half++) {  // second row tile, 8 loads at a time
+    double2 w[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (half * 8 + u < nc) w[u] = ldg2(L1 + (size_t)(half * 8 + u) * ld);
+    if (half == 0) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) acc[u] = (u < nc) ? v[u].x * y0[0] + v[u].y * y1[0] : 0.;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (half * 8 + u < nc) acc[half * 8 + u] += w[u].x * y0[1] + w[u].y * y1[1];
+  }
+#pragma unroll
+  for (int q = 0; q < PF; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+  if (PF <= 8) {
+#pragma unroll
+    for (int q = 0; q < PF; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 8);
+  }
+#pragma unroll
+  for (int off = PF / 2; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; i++) {
+      const double send = upper ? acc[i] : acc[i + off];
+      const double keep = upper ? acc[i + off] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  if (lane < PF && lane < nc) atomicAdd(&Y[S.xoff + it.col0 + it.c0 + cp + lane], -acc[0]);
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+k_solve_forest1(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* __restrict__ items,
+                const int64_t* __restrict__ ranges, int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ ForestSub sSubs[MAX_SMEM_SUBS];
+  __shared__ int64_t sRanges[4 * MAX_SMEM_LEVELS];
+  for (int t = threadIdx.x; t < min(nsubs, MAX_SMEM_SUBS); t += blockDim.x) sSubs[t] = subs[t];
+  const bool lv = nlev <= MAX_SMEM_LEVELS;
+  if (lv)
+    for (int t = threadIdx.x; t < 4 * nlev; t += blockDim.x) sRanges[t] = ranges[t];
+  const int64_t* rg = lv ? sRanges : ranges;
+  const bool inSmem = nsubs <= MAX_SMEM_SUBS;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (int64_t)gridDim.x * blockDim.x) Y[t] = 0.;
+  __syncthreads();
+  const int nph = 2 * nlev;
+  auto phase = [&](int p, int64_t& off, int64_t& cnt, bool& bwd) {
+    bwd = p >= nlev;
+    const int l = bwd ? (2 * nlev - 1 - p) : p;
+    off = rg[(bwd ? 2 * nlev : 0) + l];
+    cnt = rg[(bwd ? 3 * nlev : nlev) + l] * (bwd ? BPASS : 1);  // backward items are BPASS passes of PF columns
+  };
+  ForestItem cur;
+  double2 v[PF];
+  bool pre = false;
+  {
+    int64_t off, cnt; bool bwd;
+    phase(0, off, cnt, bwd);
+    if (gw < cnt) {
+      cur = load_item(items + off + (bwd ? gw / BPASS : gw));
+      issue1(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, bwd, (int)(gw % BPASS), lane, v);
+      pre = true;
+    }
+  }
+  grid.sync();
+  for (int p = 0; p < nph; p++) {
+    int64_t off, cnt; bool bwd;
+    phase(p, off, cnt, bwd);
+    for (int64_t i = gw; i < cnt; i += nw) {
+      const int pass = bwd ? (int)(i % BPASS) : 0;
+      if (!pre) {
+        cur = load_item(items + off + (bwd ? i / BPASS : i));
+        issue1(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, bwd, pass, lane, v);
+      }
+      pre = false;
+      const ForestSub& S = inSmem ? sSubs[cur.sub] : subs[cur.sub];
+      if (bwd) consume_bwd1(S, cur, pass, Y, lane, v);
+      else consume_fwd1(S, cur, X, Y, lane, v);
+    }
+    if (p + 1 < nph) {
+      int64_t off2, cnt2; bool bwd2;
+      phase(p + 1, off2, cnt2, bwd2);
+      if (gw < cnt2) {  // the factor tiles of the next level do not depend on this level: their loads cross the barrier
+        cur = load_item(items + off2 + (bwd2 ? gw / BPASS : gw));
+        issue1(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, bwd2, (int)(gw % BPASS), lane, v);
+        pre = true;
+      }
+      grid.sync();
+    }
+  }
+}
+
 }  // namespace
 
 void dgemm_nt_device(int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
@@ -703,6 +882,11 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fns[q], SOLVE_THREADS, 0));
     gridBlocks[q] = std::max(1, nb) * nsm;
   }
+  {
+    int nb = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_forest1, SOLVE_THREADS, 0));
+    gridBlocks1 = std::max(1, nb) * nsm;
+  }
 }
 
 void SolveForest::set_factors(const std::vector<const double*>& L, cudaStream_t st) {
@@ -721,6 +905,12 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   const int64_t* ranges = dRanges.p;
   int nl = nlev;
   int64_t nt = ntot;
+  if (nr == 1 && ldx == 1 && !getenv("GENEO_SOLVE_GENERIC")) {
+    void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp};
+    (void)GENEO_TICK(0);
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_forest1, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, 0, st));
+    return;
+  }
   void* args[] = {(void*)&subs, (void*)&nsubs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ldx};
   const void* fn = nullptr;
   int q = 0;

@@ -58,6 +58,7 @@ class SolveForest {
   DevBuf<ForestItem> dItems;
   DevBuf<int64_t> dRanges;
   int gridBlocks[4] = {1, 1, 1, 1};
+  int gridBlocks1 = 1;
 };
 
 struct FactorStats { int neg = 0, perturbed = 0; double seconds = 0.; };
