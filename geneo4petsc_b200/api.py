@@ -200,6 +200,14 @@ class GeneoPC:
         _chk(lib.geneo_pc_refactor(self.h))
         return self
 
+    def level_profile(self):
+        """(us, bytes, items) per phase of one level-1 solve: forward levels leaves-first, then backward root-first."""
+        n = C.c_int()
+        _chk(lib.geneo_pc_level_profile(self.h, None, None, None, C.c_int(0), C.byref(n)))
+        us, by, it = np.zeros(n.value), np.zeros(n.value), np.zeros(n.value, dtype=np.int64)
+        _chk(lib.geneo_pc_level_profile(self.h, _p(us, _f64p), _p(by, _f64p), _p(it, _i64p), C.c_int(n.value), C.byref(n)))
+        return us, by, it
+
     def kernel_time(self):
         """(ms, launches) of the level-1 solve kernel since the last call (needs -geneo_kernel_timing)."""
         ms, n = C.c_double(), C.c_int64()

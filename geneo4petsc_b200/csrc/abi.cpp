@@ -361,6 +361,20 @@ int geneo_pc_kernel_time(geneo_pc_t pc, double* ms, int64_t* launches) {
   pc->pc.kernel_time(ms, launches);
   ABI_CATCH
 }
+int geneo_pc_level_profile(geneo_pc_t pc, double* us, double* bytes, int64_t* nitems, int cap, int* nphases) {
+  ABI_TRY
+  ABI_REQ(pc && pc->ready && nphases, "GenEO preconditioner without context");
+  std::vector<double> u, b;
+  std::vector<int64_t> c;
+  pc->pc.level_profile(u, b, c);
+  *nphases = (int)u.size();
+  for (int i = 0; i < (int)u.size() && i < cap; i++) {
+    if (us) us[i] = u[i];
+    if (bytes) bytes[i] = b[i];
+    if (nitems) nitems[i] = c[i];
+  }
+  ABI_CATCH
+}
 int geneo_counters(int64_t c[3]) {
   ABI_TRY
   ABI_REQ(c, "null argument");

@@ -495,6 +495,13 @@ void GeneoPC::numeric_setup() {
   numericTime = now_s() - tNum0;
 }
 
+void GeneoPC::level_profile(std::vector<double>& us, std::vector<double>& bytes, std::vector<int64_t>& nitems) {
+  CUDA_CHECK(::geneo::sync_stream(st));
+  Xall.zero(st);
+  CUDA_CHECK(::geneo::sync_stream(st));
+  forest.solve_profile(Xall.p, Yall.p, us, bytes, nitems);
+}
+
 void GeneoPC::kernel_time(double* ms, int64_t* launches) {
   CUDA_CHECK(::geneo::sync_stream(st));
   double tot = 0.;

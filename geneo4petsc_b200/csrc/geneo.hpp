@@ -108,6 +108,7 @@ class GeneoPC {
   void numeric_end();
   // accumulated CUDA-event time of the level-1 solve kernel since the last call (ms) and its number of launches
   void kernel_time(double* ms, int64_t* launches);
+  void level_profile(std::vector<double>& us, std::vector<double>& bytes, std::vector<int64_t>& nitems);
   void apply(const double* x, double* y);                 // device pointers, length nLoc; x is not modified
   void applyQ(const double* x, double* y);                // y = Z E^-1 Z^T x
   void mult(const double* x, double* y);                  // y = A x on the owned rows (ghosts of x refreshed first)

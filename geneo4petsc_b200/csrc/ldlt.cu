@@ -494,182 +494,257 @@ k_solve_forest(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// NR = 1 (the preconditioner application): same tiles, but the first PF column loads of a warp's NEXT item are issued
-// BEFORE the grid barrier that ends the current level.  The factor does not depend on the barrier (only x / y do), so the
-// HBM latency of the first round of every level -- the dominant cost of a level that holds only one or two rounds of
-// tiles -- is hidden behind the barrier itself.  Level ranges and subdomain pointers sit in shared memory.
+// NR = 1 (the preconditioner application): ring-buffered streaming solve.
+//
+// The factor does not depend on the sweep (only x / y do), so its tiles are moved by cp.async into a warp-private ring
+// of shared-memory stages that runs AHEAD of the arithmetic -- across item boundaries and across the grid barriers that
+// separate the levels.  HBM keeps streaming while a level drains, while the barrier is in flight and while the first x / y
+// values of the next level are fetched from L2; the barrier only gates the consumption of a stage, never its transfer.
+//
+//   item (RingItem)  forward : 64 rows x nc columns (nc <= 128: a span of 32-column groups chosen per level on the host)
+//                    backward: up to 512 rows x nc <= 16 columns (row span chosen per level on the host)
+//   chunk            64 rows x 8 columns = one ring stage: 8 x 16-byte cp.async per lane (4 KB per warp) plus the 64 row
+//                    indices of the tile (first column chunk of a row tile only)
+//   ring             RING_S stages per warp; RING_S-1 chunks (8 KB) in flight per warp, 128 KB per SM, 19 MB per chip
+//                    = the HBM latency-bandwidth product with margin for one barrier
+//   schedule         static: item j of phase p belongs to warp (j mod #warps); the producer side of a warp walks the same
+//                    sequence RING_S-1 chunks ahead of its consumer side and hands the item records over through a small
+//                    shared-memory record ring, so no thread ever waits on an item record.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int PF = 8;          // loads prefetched across the barrier = columns per backward pass
-constexpr int BPASS = 32 / PF;  // backward passes (virtual items) per 32-column item
-constexpr int MAX_SMEM_LEVELS = 512;
+constexpr int RING_S = 3;                      // stages per warp
+constexpr int RING_CH = 8;                     // columns per chunk
+constexpr int RING_TILE = RING_CH * 32 * 16;   // bytes of factor data per stage
+constexpr int RING_STAGE = RING_TILE + 256;    // + 64 row indices
+constexpr int RING_RS = 4;                     // item records in flight per warp (>= RING_S + 1 .. power of two)
+constexpr int RING_WARP_BYTES = RING_S * RING_STAGE + RING_RS * 48;
+constexpr int RING_SMEM = (SOLVE_THREADS / 32) * RING_WARP_BYTES;
+constexpr int RING_BWD_COLS = 16;
 
-__device__ __forceinline__ void issue1(const ForestSub& S, const ForestItem& it, bool bwd, int pass, int lane, double2 (&v)[PF]) {
-  const int cp = bwd ? pass * PF : 0;
-  const int r = it.r0 + 2 * lane;
-  const double* Lp = S.L + it.lOff + (size_t)cp * it.ld + (r < it.h ? 2 * lane : 0);
-  const int nc = it.nc - cp;
-#pragma unroll
-  for (int u = 0; u < PF; u++)
-    if (u < nc) v[u] = ldg2(Lp + (size_t)u * it.ld);  // warp-uniform predicate
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-__device__ __forceinline__ void consume_fwd1(const ForestSub& S, const ForestItem& it, double* __restrict__ X,
-                                             double* __restrict__ Y, int lane, const double2 (&v)[PF]) {
-  const int k = it.k, h = it.h, ld = it.ld, nc = it.nc;
-  const int r0 = it.r0 + 2 * lane;
-  const double* x1 = X + (S.xoff + it.col0 + it.c0);
-  const double xv = lane < nc ? x1[lane] : 0.;
-  int row0 = -1, row1 = -1;
-  if (r0 >= k && r0 < h) row0 = S.rowIdx[it.rowOff + r0];
-  if (r0 + 1 >= k && r0 + 1 < h) row1 = S.rowIdx[it.rowOff + r0 + 1];
-  const double* Lp = S.L + it.lOff + (r0 < h ? 2 * lane : 0);
-  double a0 = 0., a1 = 0.;
-#pragma unroll
-  for (int half = 0; half < (SOLVE_COLS - PF) / 8; half++) {  // the rest of the 32 columns, 8 loads at a time, issued before the first FMAs
-    double2 w[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (PF + half * 8 + u < nc) w[u] = ldg2(Lp + (size_t)(PF + half * 8 + u) * ld);
-    if (half == 0) {
-#pragma unroll
-      for (int u = 0; u < PF; u++)
-        if (u < nc) {
-          const double xc = __shfl_sync(0xffffffffu, xv, u);
-          a0 += v[u].x * xc;
-          a1 += v[u].y * xc;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (PF + half * 8 + u < nc) {
-        const double xc = __shfl_sync(0xffffffffu, xv, PF + half * 8 + u);
-        a0 += w[u].x * xc;
-        a1 += w[u].y * xc;
-      }
-  }
-  if (r0 < h) {
-    if (r0 < k) atomicAdd(Y + (S.xoff + it.col0 + r0), a0);
-    else atomicAdd(X + (S.xoff + row0), -a0);
-  }
-  if (r0 + 1 < h) {
-    if (r0 + 1 < k) atomicAdd(Y + (S.xoff + it.col0 + r0 + 1), a1);
-    else atomicAdd(X + (S.xoff + row1), -a1);
-  }
+// a RingItem travels as three int4: a = {lOff, rowOff}, b = {sub, ld, nrows, nc}, c = {kdiag, xcol, ydiag, pad}
+struct RingRec { int4 a, b, c; };
+__device__ __forceinline__ RingRec load_ring_item(const RingItem* p) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+  RingRec r;
+  r.a = __ldg(q); r.b = __ldg(q + 1); r.c = __ldg(q + 2);
+  return r;
 }
-
-__device__ __forceinline__ void consume_bwd1(const ForestSub& S, const ForestItem& it, int pass, double* __restrict__ Y,
-                                             int lane, const double2 (&v)[PF]) {
-  const int k = it.k, h = it.h, ld = it.ld;
-  const int cp = pass * PF;
-  const int nc = it.nc - cp;
-  if (nc <= 0) return;
-  const int rbase = it.r0 + 2 * lane;
-  double y0[2], y1[2];
-#pragma unroll
-  for (int t = 0; t < 2; t++) {
-    const int r = rbase + t * 64;
-    const bool ok0 = r >= k && r < h, ok1 = r + 1 >= k && r + 1 < h;
-    const int rw0 = ok0 ? S.rowIdx[it.rowOff + r] : 0, rw1 = ok1 ? S.rowIdx[it.rowOff + r + 1] : 0;
-    y0[t] = ok0 ? Y[S.xoff + rw0] : 0.;
-    y1[t] = ok1 ? Y[S.xoff + rw1] : 0.;
-  }
-  const double* L1 = S.L + it.lOff + (size_t)cp * ld + (rbase + 64 < h ? 2 * lane + 64 : 0);
-  double acc[PF];
-#pragma unroll
-  for (int half = 0; half < PF / 8; half++) {  // second row tile, 8 loads at a time
-    double2 w[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (half * 8 + u < nc) w[u] = ldg2(L1 + (size_t)(half * 8 + u) * ld);
-    if (half == 0) {
-#pragma unroll
-      for (int u = 0; u < PF; u++) acc[u] = (u < nc) ? v[u].x * y0[0] + v[u].y * y1[0] : 0.;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (half * 8 + u < nc) acc[half * 8 + u] += w[u].x * y0[1] + w[u].y * y1[1];
-  }
-#pragma unroll
-  for (int q = 0; q < PF; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
-  if (PF <= 8) {
-#pragma unroll
-    for (int q = 0; q < PF; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 8);
-  }
-#pragma unroll
-  for (int off = PF / 2; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; i++) {
-      const double send = upper ? acc[i] : acc[i + off];
-      const double keep = upper ? acc[i + off] : acc[i];
-      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  if (lane < PF && lane < nc) atomicAdd(&Y[S.xoff + it.col0 + it.c0 + cp + lane], -acc[0]);
-}
+__device__ __forceinline__ int64_t rec_i64(int lo, int hi) { return (int64_t)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
-k_solve_forest1(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* __restrict__ items,
-                const int64_t* __restrict__ ranges, int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y) {
+k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __restrict__ items,
+             const int64_t* __restrict__ ranges, int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y,
+             long long* __restrict__ tstamp) {
   cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char ringmem[];
   __shared__ ForestSub sSubs[MAX_SMEM_SUBS];
-  __shared__ int64_t sRanges[4 * MAX_SMEM_LEVELS];
   for (int t = threadIdx.x; t < min(nsubs, MAX_SMEM_SUBS); t += blockDim.x) sSubs[t] = subs[t];
-  const bool lv = nlev <= MAX_SMEM_LEVELS;
-  if (lv)
-    for (int t = threadIdx.x; t < 4 * nlev; t += blockDim.x) sRanges[t] = ranges[t];
-  const int64_t* rg = lv ? sRanges : ranges;
   const bool inSmem = nsubs <= MAX_SMEM_SUBS;
   const int lane = threadIdx.x & 31;
+  unsigned char* wmem = ringmem + (threadIdx.x >> 5) * RING_WARP_BYTES;
+  int4* recRing = reinterpret_cast<int4*>(wmem + RING_S * RING_STAGE);
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (int64_t)gridDim.x * blockDim.x) Y[t] = 0.;
   __syncthreads();
   const int nph = 2 * nlev;
-  auto phase = [&](int p, int64_t& off, int64_t& cnt, bool& bwd) {
-    bwd = p >= nlev;
+  auto phase_range = [&](int p, int64_t& off, int64_t& cnt) {  // phases 0..nlev-1 forward (level p), then backward from the root
+    const bool bwd = p >= nlev;
     const int l = bwd ? (2 * nlev - 1 - p) : p;
-    off = rg[(bwd ? 2 * nlev : 0) + l];
-    cnt = rg[(bwd ? 3 * nlev : nlev) + l] * (bwd ? BPASS : 1);  // backward items are BPASS passes of PF columns
+    off = __ldg(ranges + (bwd ? 2 * nlev : 0) + l);
+    cnt = __ldg(ranges + (bwd ? 3 * nlev : nlev) + l);
   };
-  ForestItem cur;
-  double2 v[PF];
-  bool pre = false;
-  {
-    int64_t off, cnt; bool bwd;
-    phase(0, off, cnt, bwd);
-    if (gw < cnt) {
-      cur = load_item(items + off + (bwd ? gw / BPASS : gw));
-      issue1(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, bwd, (int)(gw % BPASS), lane, v);
-      pre = true;
-    }
-  }
-  grid.sync();
-  for (int p = 0; p < nph; p++) {
-    int64_t off, cnt; bool bwd;
-    phase(p, off, cnt, bwd);
-    for (int64_t i = gw; i < cnt; i += nw) {
-      const int pass = bwd ? (int)(i % BPASS) : 0;
-      if (!pre) {
-        cur = load_item(items + off + (bwd ? i / BPASS : i));
-        issue1(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, bwd, pass, lane, v);
+
+  // ---------------- producer side (warp-uniform state) ----------------
+  int pp = 0;             // phase of the next record to fetch
+  int64_t pi = gw;        // index of that record inside its phase
+  RingRec nrec;           // fetched ahead
+  bool nvalid = false;
+  int nphase = 0;
+  auto fetch_next = [&]() {
+    nvalid = false;
+    while (pp < nph) {
+      int64_t off, cnt;
+      phase_range(pp, off, cnt);
+      if (pi < cnt) {
+        nrec = load_ring_item(items + off + pi);
+        nphase = pp;
+        nvalid = true;
+        pi += nw;
+        return;
       }
-      pre = false;
-      const ForestSub& S = inSmem ? sSubs[cur.sub] : subs[cur.sub];
-      if (bwd) consume_bwd1(S, cur, pass, Y, lane, v);
-      else consume_fwd1(S, cur, X, Y, lane, v);
+      pp++;
+      pi = gw;
+    }
+  };
+  const double* psrc = nullptr;  // per lane: first element of this lane's two rows in the item's first column
+  const int* pidx = nullptr;
+  int pld = 0, pnrows = 0, pnc = 0, pQ = 1, pnq = 0, pq = 0;
+  bool pactive = false;
+  unsigned pm = 0;         // records handed over so far
+  unsigned pcount = 0;     // chunks produced so far
+  auto begin_item = [&]() {
+    const ForestSub& S = inSmem ? sSubs[nrec.b.x] : subs[nrec.b.x];
+    psrc = S.L + rec_i64(nrec.a.x, nrec.a.y);
+    pidx = S.rowIdx + rec_i64(nrec.a.z, nrec.a.w);
+    pld = nrec.b.y; pnrows = nrec.b.z; pnc = nrec.b.w;
+    pQ = (pnc + RING_CH - 1) / RING_CH;
+    pnq = pQ * ((pnrows + 63) >> 6);
+    pq = 0;
+    pactive = true;
+    if (lane < 3) recRing[(pm & (RING_RS - 1)) * 3 + lane] = lane == 0 ? nrec.a : lane == 1 ? nrec.b : nrec.c;
+    pm++;
+    fetch_next();
+  };
+  auto produce_one = [&]() {
+    if (pactive) {
+      unsigned char* st = wmem + (pcount % RING_S) * RING_STAGE;
+      const int t = pq / pQ, cq = pq - t * pQ;
+      const int r = t * 64 + 2 * lane;
+      const bool rowok = r < pnrows;
+      const double* src = psrc + (size_t)(cq * RING_CH) * pld + (rowok ? r : 0);
+      double2* dst = reinterpret_cast<double2*>(st) + lane;
+      const int ncc = min(RING_CH, pnc - cq * RING_CH);
+#pragma unroll
+      for (int u = 0; u < RING_CH; u++)
+        if (u < ncc) cp_async16(dst + u * 32, src + (size_t)u * pld);  // warp-uniform predicate
+      if (cq == 0) {
+        int* di = reinterpret_cast<int*>(st + RING_TILE) + 2 * lane;
+        if (rowok) cp_async4(di, pidx + r);
+        if (r + 1 < pnrows) cp_async4(di + 1, pidx + r + 1);
+      }
+      pcount++;
+      if (++pq == pnq) {
+        if (nvalid) begin_item();
+        else pactive = false;
+      }
+    }
+    cp_async_commit();
+  };
+  fetch_next();
+  if (nvalid) begin_item();
+#pragma unroll
+  for (int s = 0; s < RING_S - 1; s++) produce_one();
+
+  // ---------------- consumer side ----------------
+  unsigned cm = 0, ccount = 0;
+  grid.sync();
+  if (tstamp && blockIdx.x == 0 && threadIdx.x == 0) tstamp[0] = gtimer();
+  for (int p = 0; p < nph; p++) {
+    const bool bwd = p >= nlev;
+    int64_t off, cnt;
+    phase_range(p, off, cnt);
+    for (int64_t i = gw; i < cnt; i += nw) {
+      __syncwarp();
+      const int4* rr = recRing + (cm & (RING_RS - 1)) * 3;
+      const int4 rb = rr[1], rc = rr[2];
+      cm++;
+      const ForestSub& S = inSmem ? sSubs[rb.x] : subs[rb.x];
+      const int nc = rb.w, nrows = rb.z, kd = rc.x;
+      struct { int xcol, ydiag; } it = {rc.y, rc.z};
+      const int Q = (nc + RING_CH - 1) / RING_CH;
+      if (!bwd) {
+        // [ y1 ; x2 ] (+,-)= P[r0:r0+64, c0:c0+nc] * x1
+        const double* x1 = X + (S.xoff + it.xcol);
+        double xv[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) xv[g] = (g * 32 + lane < nc) ? __ldcg(x1 + g * 32 + lane) : 0.;
+        double a0 = 0., a1 = 0.;
+        int row0 = 0, row1 = 0;
+        for (int q = 0; q < Q; q++) {
+          produce_one();
+          cp_async_wait<RING_S - 1>();
+          const unsigned char* st = wmem + (ccount % RING_S) * RING_STAGE;
+          ccount++;
+          if (q == 0) {
+            const int2 ri = *reinterpret_cast<const int2*>(st + RING_TILE + 8 * lane);
+            row0 = ri.x; row1 = ri.y;
+          }
+          const double2* tb = reinterpret_cast<const double2*>(st) + lane;
+          const int ncc = min(RING_CH, nc - q * RING_CH);
+          const double xg = (q >> 2) == 0 ? xv[0] : (q >> 2) == 1 ? xv[1] : (q >> 2) == 2 ? xv[2] : xv[3];
+#pragma unroll
+          for (int u = 0; u < RING_CH; u++)
+            if (u < ncc) {
+              const double2 v = tb[u * 32];
+              const double xc = __shfl_sync(0xffffffffu, xg, (q * RING_CH + u) & 31);
+              a0 += v.x * xc;
+              a1 += v.y * xc;
+            }
+        }
+        const int r = 2 * lane;
+        if (r < nrows) {
+          if (r < kd) atomicAdd(Y + (S.xoff + it.ydiag + r), a0);
+          else atomicAdd(X + (S.xoff + row0), -a0);
+        }
+        if (r + 1 < nrows) {
+          if (r + 1 < kd) atomicAdd(Y + (S.xoff + it.ydiag + r + 1), a1);
+          else atomicAdd(X + (S.xoff + row1), -a1);
+        }
+      } else {
+        // y1[c0:c0+nc] -= L21[rows, c0:c0+nc]^T * y2[rows]      (nc <= 16, rows in tiles of 64)
+        double acc[RING_BWD_COLS];
+#pragma unroll
+        for (int u = 0; u < RING_BWD_COLS; u++) acc[u] = 0.;
+        const int T = (nrows + 63) >> 6;
+        for (int t = 0; t < T; t++) {
+          double y0 = 0., y1 = 0.;
+#pragma unroll
+          for (int cq = 0; cq < RING_BWD_COLS / RING_CH; cq++) {
+            if (cq < Q) {  // warp-uniform
+              produce_one();
+              cp_async_wait<RING_S - 1>();
+              const unsigned char* st = wmem + (ccount % RING_S) * RING_STAGE;
+              ccount++;
+              if (cq == 0) {
+                const int r = t * 64 + 2 * lane;
+                const int2 ri = *reinterpret_cast<const int2*>(st + RING_TILE + 8 * lane);
+                if (r >= kd && r < nrows) y0 = __ldcg(Y + (S.xoff + ri.x));
+                if (r + 1 >= kd && r + 1 < nrows) y1 = __ldcg(Y + (S.xoff + ri.y));
+              }
+              const double2* tb = reinterpret_cast<const double2*>(st) + lane;
+              const int ncc = min(RING_CH, nc - cq * RING_CH);
+#pragma unroll
+              for (int u = 0; u < RING_CH; u++)
+                if (u < ncc) {
+                  const double2 v = tb[u * 32];
+                  acc[cq * RING_CH + u] += v.x * y0 + v.y * y1;
+                }
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < RING_BWD_COLS; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+#pragma unroll
+        for (int o = RING_BWD_COLS / 2; o >= 1; o >>= 1) {
+          const bool upper = (lane & o) != 0;
+#pragma unroll
+          for (int i2 = 0; i2 < o; i2++) {
+            const double send = upper ? acc[i2] : acc[i2 + o];
+            const double keep = upper ? acc[i2 + o] : acc[i2];
+            acc[i2] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        if (lane < RING_BWD_COLS && lane < nc) atomicAdd(&Y[S.xoff + it.xcol + lane], -acc[0]);
+      }
     }
     if (p + 1 < nph) {
-      int64_t off2, cnt2; bool bwd2;
-      phase(p + 1, off2, cnt2, bwd2);
-      if (gw < cnt2) {  // the factor tiles of the next level do not depend on this level: their loads cross the barrier
-        cur = load_item(items + off2 + (bwd2 ? gw / BPASS : gw));
-        issue1(inSmem ? sSubs[cur.sub] : subs[cur.sub], cur, bwd2, (int)(gw % BPASS), lane, v);
-        pre = true;
-      }
       grid.sync();
+      if (tstamp && blockIdx.x == 0 && threadIdx.x == 0) tstamp[p + 1] = gtimer();
     }
   }
+  cp_async_wait<0>();
+  if (tstamp && blockIdx.x == 0 && threadIdx.x == 0) tstamp[nph] = gtimer();
 }
 
 }  // namespace
@@ -884,9 +959,92 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   }
   {
     int nb = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_forest1, SOLVE_THREADS, 0));
+    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring, SOLVE_THREADS, RING_SMEM));
     gridBlocks1 = std::max(1, nb) * nsm;
   }
+  build_ring();
+}
+
+// Item lists of the ring kernel.  Per level the host picks the span of an item from the amount of work in the level: a
+// level with many tiles per warp gets wide (forward: up to all 128 columns of a panel) / tall (backward: up to 512 rows)
+// items -- fewer records, x / y fetches and atomics per byte --, a level near the root gets the finest tiles so that every
+// warp of the chip has something to stream.
+void SolveForest::build_ring() {
+  const int ns = (int)plans_.size();
+  const int64_t nw = (int64_t)gridBlocks1 * (SOLVE_THREADS / 32);
+  std::vector<RingItem> items;
+  std::vector<int64_t> ranges(4 * (size_t)nlev, 0);
+  ringBytes.assign(2 * (size_t)nlev, 0.);
+  ringCount.assign(2 * (size_t)nlev, 0);
+  auto by_size = [](const RingItem& a, const RingItem& b) { return (int64_t)a.nrows * a.nc > (int64_t)b.nrows * b.nc; };
+  auto pow2_floor = [](int64_t v, int lo, int hi) { int r = lo; while (2 * r <= hi && 2 * (int64_t)r <= v) r *= 2; return r; };
+  for (int l = 0; l < nlev; l++) {  // forward + diagonal: every row of the panel
+    int64_t tiles = 0;
+    double bytes = 0.;
+    for (int s = 0; s < ns; s++) {
+      const Symbolic& S = plans_[s]->sym;
+      if (l >= S.nlevels) continue;
+      for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
+        const Front& F = S.fronts[S.levelFronts[t]];
+        tiles += (int64_t)((F.h + 63) / 64) * ((F.k + 31) / 32);
+        bytes += 8. * F.h * F.k;
+      }
+    }
+    const int cspan = 32 * pow2_floor(tiles / (4 * nw), 1, 4);
+    ranges[l] = (int64_t)items.size();
+    for (int s = 0; s < ns; s++) {
+      const Symbolic& S = plans_[s]->sym;
+      if (l >= S.nlevels) continue;
+      for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
+        const Front& F = S.fronts[S.levelFronts[t]];
+        for (int r0 = 0; r0 < F.h; r0 += 64)
+          for (int c0 = 0; c0 < F.k; c0 += cspan)
+            items.push_back(RingItem{F.lOff + (int64_t)c0 * F.ld + r0, F.rowOff + r0, s, F.ld, std::min(64, F.h - r0),
+                                     std::min(cspan, F.k - c0), std::max(0, std::min(64, F.k - r0)), F.col0 + c0, F.col0 + r0, 0});
+      }
+    }
+    ranges[nlev + l] = (int64_t)items.size() - ranges[l];
+    std::stable_sort(items.begin() + ranges[l], items.end(), by_size);
+    ringBytes[l] = bytes;
+    ringCount[l] = ranges[nlev + l];
+  }
+  for (int l = 0; l < nlev; l++) {  // backward: the L21 rows, tiles start at the even row k & ~1 (row k-1 masked by kdiag)
+    int64_t tiles = 0;
+    double bytes = 0.;
+    for (int s = 0; s < ns; s++) {
+      const Symbolic& S = plans_[s]->sym;
+      if (l >= S.nlevels) continue;
+      for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
+        const Front& F = S.fronts[S.levelFronts[t]];
+        if (F.m() == 0) continue;
+        tiles += (int64_t)((F.h - (F.k & ~1) + 63) / 64) * ((F.k + RING_BWD_COLS - 1) / RING_BWD_COLS);
+        bytes += 8. * F.m() * F.k;
+      }
+    }
+    const int rspan = 64 * pow2_floor(tiles / (4 * nw), 1, 8);
+    ranges[2 * nlev + l] = (int64_t)items.size();
+    for (int s = 0; s < ns; s++) {
+      const Symbolic& S = plans_[s]->sym;
+      if (l >= S.nlevels) continue;
+      for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
+        const Front& F = S.fronts[S.levelFronts[t]];
+        if (F.m() == 0) continue;
+        const int rstart = F.k & ~1;
+        for (int r0 = rstart; r0 < F.h; r0 += rspan)
+          for (int c0 = 0; c0 < F.k; c0 += RING_BWD_COLS)
+            items.push_back(RingItem{F.lOff + (int64_t)c0 * F.ld + r0, F.rowOff + r0, s, F.ld, std::min(rspan, F.h - r0),
+                                     std::min(RING_BWD_COLS, F.k - c0), std::max(0, F.k - r0), F.col0 + c0, 0, 0});
+      }
+    }
+    ranges[3 * nlev + l] = (int64_t)items.size() - ranges[2 * nlev + l];
+    std::stable_sort(items.begin() + ranges[2 * nlev + l], items.end(), by_size);
+    ringBytes[2 * nlev - 1 - l] = bytes;  // phase order: backward runs from the root down
+    ringCount[2 * nlev - 1 - l] = ranges[3 * nlev + l];
+  }
+  dRing.upload(items);
+  dRingRanges.upload(ranges);
+  CUDA_CHECK(::geneo::sync_stream(0));
 }
 
 void SolveForest::set_factors(const std::vector<const double*>& L, cudaStream_t st) {
@@ -906,9 +1064,12 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   int nl = nlev;
   int64_t nt = ntot;
   if (nr == 1 && ldx == 1 && !getenv("GENEO_SOLVE_GENERIC")) {
-    void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp};
+    const RingItem* ritems = dRing.p;
+    const int64_t* rranges = dRingRanges.p;
+    long long* ts = nullptr;
+    void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ts};
     (void)GENEO_TICK(0);
-    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_forest1, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, 0, st));
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, RING_SMEM, st));
     return;
   }
   void* args[] = {(void*)&subs, (void*)&nsubs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ldx};
@@ -923,6 +1084,27 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   }
   (void)GENEO_TICK(0);
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(SOLVE_THREADS), args, 0, st));
+}
+
+void SolveForest::solve_profile(double* X, double* Y, std::vector<double>& us, std::vector<double>& bytes,
+                                std::vector<int64_t>& nitems) const {
+  const ForestSub* subs = dSubs.p;
+  int nsubs = (int)hSubs.size();
+  const RingItem* ritems = dRing.p;
+  const int64_t* rranges = dRingRanges.p;
+  int nl = nlev;
+  int64_t nt = ntot;
+  DevBuf<long long> dts((size_t)2 * nlev + 1);
+  long long* ts = dts.p;
+  void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&X, (void*)&Y, (void*)&ts};
+  (void)GENEO_TICK(0);
+  CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, RING_SMEM, 0));
+  CUDA_CHECK(::geneo::sync_stream(0));
+  std::vector<long long> h = dts.to_host();
+  us.resize(2 * (size_t)nlev);
+  for (int p = 0; p < 2 * nlev; p++) us[p] = 1e-3 * (double)(h[p + 1] - h[p]);
+  bytes = ringBytes;
+  nitems = ringCount;
 }
 
 // Synthetic streaming benchmark of the solve kernel: nf independent h x k panels at ONE level (no level effects, no

@@ -41,6 +41,10 @@ struct ForestSub { const double* L; const FrontDev* fronts; const int* rowIdx; i
 // self-contained work item (48 bytes, three 16-byte loads): nothing but the subdomain's base pointers (kept in shared
 // memory) stands between reading the item and issuing the factor loads
 struct ForestItem { int64_t lOff, rowOff; int sub, ld, h, k; int c0, nc, r0, col0; };
+// item of the ring-buffered NR = 1 kernel (48 bytes): lOff / rowOff point at the tile origin (row r0, column c0) of the
+// panel and at rowIdx[r0]; nrows x nc is the extent of the item; the first kdiag rows are pivot rows (forward: D^-1 rows
+// that go to Y[ydiag + i]; backward: masked); xcol = first pivot column of the item in the subdomain's permuted numbering
+struct RingItem { int64_t lOff, rowOff; int sub, ld, nrows, nc, kdiag, xcol, ydiag, pad; };
 class SolveForest {
  public:
   // plans[s] solves rows [xoff[s], xoff[s]+n_s) of the concatenated (permuted) vectors
@@ -48,15 +52,23 @@ class SolveForest {
   void set_factors(const std::vector<const double*>& L, cudaStream_t st);
   // X (forward sweep, overwritten) -> Y (result); row-major blocks with leading dimension ldx, columns j0..j0+nr-1
   void solve(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const;
+  // NR = 1 solve with a device timestamp after every level barrier: us[p] = duration of phase p (forward levels bottom-up,
+  // then backward levels top-down), bytes[p] = factor bytes streamed in it, nitems[p] = ring items
+  void solve_profile(double* X, double* Y, std::vector<double>& us, std::vector<double>& bytes, std::vector<int64_t>& nitems) const;
   int nlev = 0;
   int64_t ntot = 0;
  private:
+  void build_ring();
   std::vector<const LdltPlan*> plans_;
   std::vector<int64_t> xoff_;
   std::vector<ForestSub> hSubs;
   DevBuf<ForestSub> dSubs;
   DevBuf<ForestItem> dItems;
   DevBuf<int64_t> dRanges;
+  DevBuf<RingItem> dRing;       // NR = 1 ring kernel: its own item lists (spans chosen per level) and ranges
+  DevBuf<int64_t> dRingRanges;
+  std::vector<double> ringBytes;  // per phase (2 * nlev)
+  std::vector<int64_t> ringCount;
   int gridBlocks[4] = {1, 1, 1, 1};
   int gridBlocks1 = 1;
 };

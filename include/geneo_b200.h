@@ -83,6 +83,10 @@ int geneo_pc_apply_q_device(geneo_pc_t pc, const double* dx, double* dy);   /* a
 int geneo_pc_refactor(geneo_pc_t pc);
 /* With -geneo_kernel_timing: CUDA-event time (ms) and launch count of the level-1 solve kernel since the last call. */
 int geneo_pc_kernel_time(geneo_pc_t pc, double* ms, int64_t* launches);
+/* Diagnostic: one level-1 solve (the PC-apply kernel) with a device timestamp after every level barrier.  Phase p < nlev
+ * is the forward sweep of level p (leaves first), then the backward sweep from the root down.  us[p] = duration,
+ * bytes[p] = factor bytes streamed, nitems[p] = work items; *nphases = 2 * nlev (arrays may be NULL / shorter: cap). */
+int geneo_pc_level_profile(geneo_pc_t pc, double* us, double* bytes, int64_t* nitems, int cap, int* nphases);
 /* process-wide counters: {kernel launches, host->device bytes, device->host bytes} issued by this library so far */
 int geneo_counters(int64_t c[3]);
 /* GENEO_PROFILE=1 in the environment: per-launch-site CUDA-event times accumulated so far -> CSV, then reset */
