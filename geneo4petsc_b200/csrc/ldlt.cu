@@ -541,28 +541,42 @@ __device__ __forceinline__ RingRec load_ring_item(const RingItem* p) {
 }
 __device__ __forceinline__ int64_t rec_i64(int lo, int hi) { return (int64_t)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
 
+constexpr int RING_MAXPH = 1024;               // phases whose (offset, count) are kept in shared memory
+
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __restrict__ items,
              const int64_t* __restrict__ ranges, int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y,
-             long long* __restrict__ tstamp) {
+             long long* __restrict__ tstamp, int flags) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char ringmem[];
   __shared__ ForestSub sSubs[MAX_SMEM_SUBS];
+  __shared__ int64_t sOff[RING_MAXPH];
+  __shared__ int sCnt[RING_MAXPH];
+  const int nph = 2 * nlev;
+  const bool phSmem = nph <= RING_MAXPH;
   for (int t = threadIdx.x; t < min(nsubs, MAX_SMEM_SUBS); t += blockDim.x) sSubs[t] = subs[t];
+  if (phSmem)
+    for (int p = threadIdx.x; p < nph; p += blockDim.x) {  // phases 0..nlev-1 forward (level p), then backward from the root
+      const bool b = p >= nlev;
+      const int l = b ? (2 * nlev - 1 - p) : p;
+      sOff[p] = ranges[(b ? 2 * nlev : 0) + l];
+      sCnt[p] = (int)ranges[(b ? 3 * nlev : nlev) + l];
+    }
   const bool inSmem = nsubs <= MAX_SMEM_SUBS;
   const int lane = threadIdx.x & 31;
   unsigned char* wmem = ringmem + (threadIdx.x >> 5) * RING_WARP_BYTES;
   int4* recRing = reinterpret_cast<int4*>(wmem + RING_S * RING_STAGE);
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // consecutive items of a phase go to different SMs: a level with few items still uses every SM's LSU / L1 / RED path
+  const int64_t gw = (flags & 1) ? ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5 : (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (int64_t)gridDim.x * blockDim.x) Y[t] = 0.;
   __syncthreads();
-  const int nph = 2 * nlev;
-  auto phase_range = [&](int p, int64_t& off, int64_t& cnt) {  // phases 0..nlev-1 forward (level p), then backward from the root
-    const bool bwd = p >= nlev;
-    const int l = bwd ? (2 * nlev - 1 - p) : p;
-    off = __ldg(ranges + (bwd ? 2 * nlev : 0) + l);
-    cnt = __ldg(ranges + (bwd ? 3 * nlev : nlev) + l);
+  auto phase_range = [&](int p, int64_t& off, int64_t& cnt) {
+    if (phSmem) { off = sOff[p]; cnt = sCnt[p]; return; }
+    const bool b = p >= nlev;
+    const int l = b ? (2 * nlev - 1 - p) : p;
+    off = __ldg(ranges + (b ? 2 * nlev : 0) + l);
+    cnt = __ldg(ranges + (b ? 3 * nlev : nlev) + l);
   };
 
   // ---------------- producer side (warp-uniform state) ----------------
@@ -570,15 +584,12 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
   int64_t pi = gw;        // index of that record inside its phase
   RingRec nrec;           // fetched ahead
   bool nvalid = false;
-  int nphase = 0;
-  auto fetch_next = [&]() {
-    nvalid = false;
-    while (pp < nph) {
+  auto fetch_next = [&](int budget) {  // looks at no more than `budget` phases: never a long scan on somebody's critical path
+    while (pp < nph && budget-- > 0) {
       int64_t off, cnt;
       phase_range(pp, off, cnt);
       if (pi < cnt) {
         nrec = load_ring_item(items + off + pi);
-        nphase = pp;
         nvalid = true;
         pi += nw;
         return;
@@ -591,23 +602,26 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
   const int* pidx = nullptr;
   int pld = 0, pnrows = 0, pnc = 0, pQ = 1, pnq = 0, pq = 0;
   bool pactive = false;
-  unsigned pm = 0;         // records handed over so far
-  unsigned pcount = 0;     // chunks produced so far
-  auto begin_item = [&]() {
-    const ForestSub& S = inSmem ? sSubs[nrec.b.x] : subs[nrec.b.x];
-    psrc = S.L + rec_i64(nrec.a.x, nrec.a.y);
-    pidx = S.rowIdx + rec_i64(nrec.a.z, nrec.a.w);
-    pld = nrec.b.y; pnrows = nrec.b.z; pnc = nrec.b.w;
-    pQ = (pnc + RING_CH - 1) / RING_CH;
-    pnq = pQ * ((pnrows + 63) >> 6);
-    pq = 0;
-    pactive = true;
-    if (lane < 3) recRing[(pm & (RING_RS - 1)) * 3 + lane] = lane == 0 ? nrec.a : lane == 1 ? nrec.b : nrec.c;
-    pm++;
-    fetch_next();
-  };
-  auto produce_one = [&]() {
-    if (pactive) {
+  unsigned pm = 0;              // records handed over so far
+  unsigned pcount = 0;          // chunks produced so far
+  unsigned ccount = 0;          // chunks consumed so far
+  auto top_up = [&]() {         // keep the ring full: RING_S stages in use, the current one included
+    while (pcount - ccount < RING_S) {
+      if (!pactive) {
+        if (!nvalid) { fetch_next(8); if (!nvalid) break; }
+        const ForestSub& S = inSmem ? sSubs[nrec.b.x] : subs[nrec.b.x];
+        psrc = S.L + rec_i64(nrec.a.x, nrec.a.y);
+        pidx = S.rowIdx + rec_i64(nrec.a.z, nrec.a.w);
+        pld = nrec.b.y; pnrows = nrec.b.z; pnc = nrec.b.w;
+        pQ = (pnc + RING_CH - 1) / RING_CH;
+        pnq = pQ * ((pnrows + 63) >> 6);
+        pq = 0;
+        pactive = true;
+        if (lane < 3) recRing[(pm & (RING_RS - 1)) * 3 + lane] = lane == 0 ? nrec.a : lane == 1 ? nrec.b : nrec.c;
+        pm++;
+        nvalid = false;
+        fetch_next(2);  // the following record travels while this item streams
+      }
       unsigned char* st = wmem + (pcount % RING_S) * RING_STAGE;
       const int t = pq / pQ, cq = pq - t * pQ;
       const int r = t * 64 + 2 * lane;
@@ -623,52 +637,68 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
         if (rowok) cp_async4(di, pidx + r);
         if (r + 1 < pnrows) cp_async4(di + 1, pidx + r + 1);
       }
+      cp_async_commit();
       pcount++;
-      if (++pq == pnq) {
-        if (nvalid) begin_item();
-        else pactive = false;
-      }
+      if (++pq == pnq) pactive = false;
     }
-    cp_async_commit();
   };
-  fetch_next();
-  if (nvalid) begin_item();
-#pragma unroll
-  for (int s = 0; s < RING_S - 1; s++) produce_one();
+  auto acquire = [&]() -> const unsigned char* {  // next chunk of this warp's stream, landed
+    do top_up(); while (pcount == ccount);
+    const unsigned ahead = pcount - ccount - 1;   // groups committed after the one needed now
+    if (ahead >= 2) cp_async_wait<2>();
+    else if (ahead == 1) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    return wmem + (ccount % RING_S) * RING_STAGE;
+  };
+  top_up();
 
   // ---------------- consumer side ----------------
-  unsigned cm = 0, ccount = 0;
+  unsigned cm = 0;
   grid.sync();
   if (tstamp && blockIdx.x == 0 && threadIdx.x == 0) tstamp[0] = gtimer();
   for (int p = 0; p < nph; p++) {
     const bool bwd = p >= nlev;
     int64_t off, cnt;
     phase_range(p, off, cnt);
+    double xn[4];          // x1 of the NEXT forward item of this phase, fetched during the last chunk of the current one
+    bool havex = false;
     for (int64_t i = gw; i < cnt; i += nw) {
+      while (pm == cm) top_up();  // (only after a long idle stretch can a warp find its record not handed over yet)
       __syncwarp();
       const int4* rr = recRing + (cm & (RING_RS - 1)) * 3;
       const int4 rb = rr[1], rc = rr[2];
       cm++;
       const ForestSub& S = inSmem ? sSubs[rb.x] : subs[rb.x];
-      const int nc = rb.w, nrows = rb.z, kd = rc.x;
-      struct { int xcol, ydiag; } it = {rc.y, rc.z};
+      const int nc = rb.w, nrows = rb.z, kd = rc.x, xcol = rc.y, ydiag = rc.z;
       const int Q = (nc + RING_CH - 1) / RING_CH;
       if (!bwd) {
         // [ y1 ; x2 ] (+,-)= P[r0:r0+64, c0:c0+nc] * x1
-        const double* x1 = X + (S.xoff + it.xcol);
         double xv[4];
+        if (havex) {
 #pragma unroll
-        for (int g = 0; g < 4; g++) xv[g] = (g * 32 + lane < nc) ? __ldcg(x1 + g * 32 + lane) : 0.;
+          for (int g = 0; g < 4; g++) xv[g] = xn[g];
+        } else {
+          const double* x1 = X + (S.xoff + xcol);
+#pragma unroll
+          for (int g = 0; g < 4; g++) xv[g] = (g * 32 + lane < nc) ? __ldcg(x1 + g * 32 + lane) : 0.;
+        }
+        havex = false;
         double a0 = 0., a1 = 0.;
         int row0 = 0, row1 = 0;
         for (int q = 0; q < Q; q++) {
-          produce_one();
-          cp_async_wait<RING_S - 1>();
-          const unsigned char* st = wmem + (ccount % RING_S) * RING_STAGE;
-          ccount++;
+          const unsigned char* st = acquire();
           if (q == 0) {
             const int2 ri = *reinterpret_cast<const int2*>(st + RING_TILE + 8 * lane);
             row0 = ri.x; row1 = ri.y;
+          }
+          if (q == Q - 1 && i + nw < cnt && !(flags & 2)) {  // the next item's record has been handed over by now (RING_S >= 2)
+            __syncwarp();
+            const int4* r2 = recRing + (cm & (RING_RS - 1)) * 3;
+            const int4 b2 = r2[1], c2 = r2[2];
+            const double* x2 = X + ((inSmem ? sSubs[b2.x] : subs[b2.x]).xoff + c2.y);
+#pragma unroll
+            for (int g = 0; g < 4; g++) xn[g] = (g * 32 + lane < b2.w) ? __ldcg(x2 + g * 32 + lane) : 0.;
+            havex = true;
           }
           const double2* tb = reinterpret_cast<const double2*>(st) + lane;
           const int ncc = min(RING_CH, nc - q * RING_CH);
@@ -681,14 +711,15 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
               a0 += v.x * xc;
               a1 += v.y * xc;
             }
+          ccount++;
         }
         const int r = 2 * lane;
         if (r < nrows) {
-          if (r < kd) atomicAdd(Y + (S.xoff + it.ydiag + r), a0);
+          if (r < kd) atomicAdd(Y + (S.xoff + ydiag + r), a0);
           else atomicAdd(X + (S.xoff + row0), -a0);
         }
         if (r + 1 < nrows) {
-          if (r + 1 < kd) atomicAdd(Y + (S.xoff + it.ydiag + r + 1), a1);
+          if (r + 1 < kd) atomicAdd(Y + (S.xoff + ydiag + r + 1), a1);
           else atomicAdd(X + (S.xoff + row1), -a1);
         }
       } else {
@@ -702,10 +733,7 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
 #pragma unroll
           for (int cq = 0; cq < RING_BWD_COLS / RING_CH; cq++) {
             if (cq < Q) {  // warp-uniform
-              produce_one();
-              cp_async_wait<RING_S - 1>();
-              const unsigned char* st = wmem + (ccount % RING_S) * RING_STAGE;
-              ccount++;
+              const unsigned char* st = acquire();
               if (cq == 0) {
                 const int r = t * 64 + 2 * lane;
                 const int2 ri = *reinterpret_cast<const int2*>(st + RING_TILE + 8 * lane);
@@ -720,6 +748,7 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
                   const double2 v = tb[u * 32];
                   acc[cq * RING_CH + u] += v.x * y0 + v.y * y1;
                 }
+              ccount++;
             }
           }
         }
@@ -735,9 +764,10 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
             acc[i2] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
-        if (lane < RING_BWD_COLS && lane < nc) atomicAdd(&Y[S.xoff + it.xcol + lane], -acc[0]);
+        if (lane < RING_BWD_COLS && lane < nc) atomicAdd(&Y[S.xoff + xcol + lane], -acc[0]);
       }
     }
+    if (!(flags & 4)) top_up();  // idle warps keep scanning ahead / prefetching here, off everybody's critical path
     if (p + 1 < nph) {
       grid.sync();
       if (tstamp && blockIdx.x == 0 && threadIdx.x == 0) tstamp[p + 1] = gtimer();
@@ -1022,7 +1052,7 @@ void SolveForest::build_ring() {
         bytes += 8. * F.m() * F.k;
       }
     }
-    const int rspan = 64 * pow2_floor(tiles / (4 * nw), 1, 8);
+    const int rspan = 64 * pow2_floor(tiles / (2 * nw), 1, 8);
     ranges[2 * nlev + l] = (int64_t)items.size();
     for (int s = 0; s < ns; s++) {
       const Symbolic& S = plans_[s]->sym;
@@ -1047,6 +1077,11 @@ void SolveForest::build_ring() {
   CUDA_CHECK(::geneo::sync_stream(0));
 }
 
+static int ring_flags() {  // experiment switches of the ring kernel (GENEO_RING_FLAGS)
+  const char* e = getenv("GENEO_RING_FLAGS");
+  return e ? atoi(e) : 0;
+}
+
 void SolveForest::set_factors(const std::vector<const double*>& L, cudaStream_t st) {
   GENEO_CHECK(L.size() == hSubs.size(), "forest: wrong number of factors");
   for (size_t s = 0; s < L.size(); s++) hSubs[s].L = L[s];
@@ -1067,7 +1102,8 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
     const RingItem* ritems = dRing.p;
     const int64_t* rranges = dRingRanges.p;
     long long* ts = nullptr;
-    void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ts};
+    int flags = ring_flags();
+    void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ts, (void*)&flags};
     (void)GENEO_TICK(0);
     CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, RING_SMEM, st));
     return;
@@ -1096,7 +1132,8 @@ void SolveForest::solve_profile(double* X, double* Y, std::vector<double>& us, s
   int64_t nt = ntot;
   DevBuf<long long> dts((size_t)2 * nlev + 1);
   long long* ts = dts.p;
-  void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&X, (void*)&Y, (void*)&ts};
+  int flags = ring_flags();
+  void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&X, (void*)&Y, (void*)&ts, (void*)&flags};
   (void)GENEO_TICK(0);
   CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, RING_SMEM, 0));
   CUDA_CHECK(::geneo::sync_stream(0));
