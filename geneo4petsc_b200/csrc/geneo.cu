@@ -499,7 +499,7 @@ void GeneoPC::level_profile(std::vector<double>& us, std::vector<double>& bytes,
   CUDA_CHECK(::geneo::sync_stream(st));
   Xall.zero(st);
   CUDA_CHECK(::geneo::sync_stream(st));
-  forest.solve_profile(Xall.p, Yall.p, us, bytes, nitems);
+  forest.solve_profile(Xall.p, Yall.p, 1, us, bytes, nitems);
 }
 
 void GeneoPC::kernel_time(double* ms, int64_t* launches) {

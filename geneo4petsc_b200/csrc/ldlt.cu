@@ -494,7 +494,8 @@ k_solve_forest(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// NR = 1 (the preconditioner application): ring-buffered streaming solve.
+// Ring-buffered streaming solve: NR = 1 (the preconditioner application) and NR = 8 (block solves of the eigen-solver
+// and of the coarse operator).
 //
 // The factor does not depend on the sweep (only x / y do), so its tiles are moved by cp.async into a warp-private ring
 // of shared-memory stages that runs AHEAD of the arithmetic -- across item boundaries and across the grid barriers that
@@ -502,7 +503,7 @@ k_solve_forest(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* 
 // values of the next level are fetched from L2; the barrier only gates the consumption of a stage, never its transfer.
 //
 //   item (RingItem)  forward : 64 rows x nc columns (nc <= 128: a span of 32-column groups chosen per level on the host)
-//                    backward: up to 512 rows x nc <= 16 columns (row span chosen per level on the host)
+//                    backward: up to 512 rows x nc <= 16 (NR = 1) / 32 (NR = 8) columns (row span chosen per level)
 //   chunk            64 rows x 8 columns = one ring stage: 8 x 16-byte cp.async per lane (4 KB per warp) plus the 64 row
 //                    indices of the tile (first column chunk of a row tile only)
 //   ring             RING_S stages per warp; RING_S-1 chunks (8 KB) in flight per warp, 128 KB per SM, 19 MB per chip
@@ -510,15 +511,23 @@ k_solve_forest(const ForestSub* __restrict__ subs, int nsubs, const ForestItem* 
 //   schedule         static: item j of phase p belongs to warp (j mod #warps); the producer side of a warp walks the same
 //                    sequence RING_S-1 chunks ahead of its consumer side and hands the item records over through a small
 //                    shared-memory record ring, so no thread ever waits on an item record.
+//   NR = 1           FP64 FMA, x broadcast by shuffles, one butterfly transpose-reduction per backward item
+//   NR = 8           the 8 right-hand sides are the N dimension of mma.sync.m8n8k4.f64 (FP64 tensor pipe): forward
+//                    C[8 rows x 8 rhs] += L[8 rows x 4 cols] X[4 cols x 8 rhs], backward C[8 cols x 8 rhs] += L^T Y2;
+//                    the stage keeps a column stride of 68 doubles so that both fragment reads are bank-conflict free.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int RING_S = 3;                      // stages per warp
 constexpr int RING_CH = 8;                     // columns per chunk
-constexpr int RING_TILE = RING_CH * 32 * 16;   // bytes of factor data per stage
-constexpr int RING_STAGE = RING_TILE + 256;    // + 64 row indices
-constexpr int RING_RS = 4;                     // item records in flight per warp (>= RING_S + 1 .. power of two)
-constexpr int RING_WARP_BYTES = RING_S * RING_STAGE + RING_RS * 48;
-constexpr int RING_SMEM = (SOLVE_THREADS / 32) * RING_WARP_BYTES;
-constexpr int RING_BWD_COLS = 16;
+constexpr int RING_RS = 8;                     // item records in flight per warp (> stages, power of two)
+constexpr int RING_MAXPH = 512;                // phases whose (offset, count) are kept in shared memory
+template <int W, int STAGES, int CSTRIDE, int BC> struct RingCfgT {
+  static constexpr int WARPS = W, S = STAGES, CS = CSTRIDE, BWD_COLS = BC;  // CS: column stride of a stage in doubles
+  static constexpr int STAGE = RING_CH * CSTRIDE * 8 + 256;                 // tile + 64 row indices
+  static constexpr int WARP_BYTES = STAGES * STAGE + RING_RS * 48;
+  static constexpr int SMEM = W * WARP_BYTES;
+};
+template <int NR> struct RingCfg;
+template <> struct RingCfg<1> : RingCfgT<16, 3, 64, 16> {};  // 16 warps x 3 stages: 128 KB in flight per SM, <= 128 registers
+template <> struct RingCfg<8> : RingCfgT<12, 4, 68, 32> {};  // 12 warps x 4 stages: 144 KB in flight per SM, <= 168 registers
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -541,16 +550,20 @@ __device__ __forceinline__ RingRec load_ring_item(const RingItem* p) {
 }
 __device__ __forceinline__ int64_t rec_i64(int lo, int hi) { return (int64_t)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
 
-constexpr int RING_MAXPH = 1024;               // phases whose (offset, count) are kept in shared memory
-
-__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+template <int NR>
+__global__ void __launch_bounds__(RingCfg<NR>::WARPS * 32, 1)
 k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __restrict__ items,
              const int64_t* __restrict__ ranges, int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y,
-             long long* __restrict__ tstamp, int flags) {
+             int ldx, long long* __restrict__ tstamp, int flags) {
+  constexpr int CS = RingCfg<NR>::CS;
+  constexpr int RING_S = RingCfg<NR>::S;
+  constexpr int TILE_BYTES = RING_CH * CS * 8;
+  constexpr int STAGE = RingCfg<NR>::STAGE;
+  constexpr int BWD_COLS = RingCfg<NR>::BWD_COLS;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char ringmem[];
   __shared__ ForestSub sSubs[MAX_SMEM_SUBS];
-  __shared__ int64_t sOff[RING_MAXPH];
+  __shared__ unsigned sOff[RING_MAXPH];  // item lists are far below 2^32 records
   __shared__ int sCnt[RING_MAXPH];
   const int nph = 2 * nlev;
   const bool phSmem = nph <= RING_MAXPH;
@@ -559,17 +572,20 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
     for (int p = threadIdx.x; p < nph; p += blockDim.x) {  // phases 0..nlev-1 forward (level p), then backward from the root
       const bool b = p >= nlev;
       const int l = b ? (2 * nlev - 1 - p) : p;
-      sOff[p] = ranges[(b ? 2 * nlev : 0) + l];
+      sOff[p] = (unsigned)ranges[(b ? 2 * nlev : 0) + l];
       sCnt[p] = (int)ranges[(b ? 3 * nlev : nlev) + l];
     }
+  if (NR > 1)  // fragments read whole stages: never let a NaN pattern of uninitialised shared memory into a product
+    for (int t = threadIdx.x; t < RingCfg<NR>::SMEM / 16; t += blockDim.x) reinterpret_cast<int4*>(ringmem)[t] = make_int4(0, 0, 0, 0);
   const bool inSmem = nsubs <= MAX_SMEM_SUBS;
   const int lane = threadIdx.x & 31;
-  unsigned char* wmem = ringmem + (threadIdx.x >> 5) * RING_WARP_BYTES;
-  int4* recRing = reinterpret_cast<int4*>(wmem + RING_S * RING_STAGE);
+  unsigned char* wmem = ringmem + (threadIdx.x >> 5) * RingCfg<NR>::WARP_BYTES;
+  int4* recRing = reinterpret_cast<int4*>(wmem + RING_S * STAGE);
   // consecutive items of a phase go to different SMs: a level with few items still uses every SM's LSU / L1 / RED path
   const int64_t gw = (flags & 1) ? ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5 : (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (int64_t)gridDim.x * blockDim.x) Y[t] = 0.;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntot * NR; t += (int64_t)gridDim.x * blockDim.x)
+    Y[(t / NR) * ldx + (t % NR)] = 0.;
   __syncthreads();
   auto phase_range = [&](int p, int64_t& off, int64_t& cnt) {
     if (phSmem) { off = sOff[p]; cnt = sCnt[p]; return; }
@@ -598,13 +614,14 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
       pi = gw;
     }
   };
-  const double* psrc = nullptr;  // per lane: first element of this lane's two rows in the item's first column
+  const double* psrc = nullptr;  // per lane: first element of this lane's two rows in the current column chunk
   const int* pidx = nullptr;
-  int pld = 0, pnrows = 0, pnc = 0, pQ = 1, pnq = 0, pq = 0;
+  int pld = 0, pnrows = 0, pnc = 0, pQ = 1, pT = 0, pt = 0, pcq = 0;
   bool pactive = false;
   unsigned pm = 0;              // records handed over so far
   unsigned pcount = 0;          // chunks produced so far
   unsigned ccount = 0;          // chunks consumed so far
+  int pstage = 0, cstage = 0;   // = pcount % RING_S, ccount % RING_S
   auto top_up = [&]() {         // keep the ring full: RING_S stages in use, the current one included
     while (pcount - ccount < RING_S) {
       if (!pactive) {
@@ -614,42 +631,51 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
         pidx = S.rowIdx + rec_i64(nrec.a.z, nrec.a.w);
         pld = nrec.b.y; pnrows = nrec.b.z; pnc = nrec.b.w;
         pQ = (pnc + RING_CH - 1) / RING_CH;
-        pnq = pQ * ((pnrows + 63) >> 6);
-        pq = 0;
+        pT = (pnrows + 63) >> 6;
+        pt = 0; pcq = 0;
         pactive = true;
         if (lane < 3) recRing[(pm & (RING_RS - 1)) * 3 + lane] = lane == 0 ? nrec.a : lane == 1 ? nrec.b : nrec.c;
         pm++;
         nvalid = false;
         fetch_next(2);  // the following record travels while this item streams
       }
-      unsigned char* st = wmem + (pcount % RING_S) * RING_STAGE;
-      const int t = pq / pQ, cq = pq - t * pQ;
-      const int r = t * 64 + 2 * lane;
+      unsigned char* st = wmem + pstage * STAGE;
+      const int r = pt * 64 + 2 * lane;
       const bool rowok = r < pnrows;
-      const double* src = psrc + (size_t)(cq * RING_CH) * pld + (rowok ? r : 0);
-      double2* dst = reinterpret_cast<double2*>(st) + lane;
-      const int ncc = min(RING_CH, pnc - cq * RING_CH);
+      const double* src = psrc + (size_t)(pcq * RING_CH) * pld + (rowok ? r : 0);
+      double* dst = reinterpret_cast<double*>(st) + 2 * lane;
+      const int ncc = pnc - pcq * RING_CH;
+      if (ncc >= RING_CH) {
 #pragma unroll
-      for (int u = 0; u < RING_CH; u++)
-        if (u < ncc) cp_async16(dst + u * 32, src + (size_t)u * pld);  // warp-uniform predicate
-      if (cq == 0) {
-        int* di = reinterpret_cast<int*>(st + RING_TILE) + 2 * lane;
+        for (int u = 0; u < RING_CH; u++) cp_async16(dst + u * CS, src + (size_t)u * pld);
+      } else {
+#pragma unroll
+        for (int u = 0; u < RING_CH - 1; u++)
+          if (u < ncc) cp_async16(dst + u * CS, src + (size_t)u * pld);  // warp-uniform predicate
+      }
+      if (pcq == 0) {
+        int* di = reinterpret_cast<int*>(st + TILE_BYTES) + 2 * lane;
         if (rowok) cp_async4(di, pidx + r);
         if (r + 1 < pnrows) cp_async4(di + 1, pidx + r + 1);
       }
       cp_async_commit();
       pcount++;
-      if (++pq == pnq) pactive = false;
+      pstage = pstage + 1 == RING_S ? 0 : pstage + 1;
+      if (++pcq == pQ) { pcq = 0; if (++pt == pT) pactive = false; }
     }
   };
   auto acquire = [&]() -> const unsigned char* {  // next chunk of this warp's stream, landed
+    if (NR > 1) __syncwarp();                     // every lane is done with the stage that is about to be refilled
     do top_up(); while (pcount == ccount);
     const unsigned ahead = pcount - ccount - 1;   // groups committed after the one needed now
-    if (ahead >= 2) cp_async_wait<2>();
+    if (RING_S > 3 && ahead >= 3) cp_async_wait<3>();
+    else if (ahead >= 2) cp_async_wait<2>();
     else if (ahead == 1) cp_async_wait<1>();
     else cp_async_wait<0>();
-    return wmem + (ccount % RING_S) * RING_STAGE;
+    if (NR > 1) __syncwarp();                     // fragments read what OTHER lanes copied
+    return wmem + cstage * STAGE;
   };
+  auto release = [&]() { ccount++; cstage = cstage + 1 == RING_S ? 0 : cstage + 1; };
   top_up();
 
   // ---------------- consumer side ----------------
@@ -660,7 +686,7 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
     const bool bwd = p >= nlev;
     int64_t off, cnt;
     phase_range(p, off, cnt);
-    double xn[4];          // x1 of the NEXT forward item of this phase, fetched during the last chunk of the current one
+    double xn[NR == 1 ? 4 : 8];  // x1 of the NEXT forward item of this phase, fetched during the last chunk of the current one
     bool havex = false;
     for (int64_t i = gw; i < cnt; i += nw) {
       while (pm == cm) top_up();  // (only after a long idle stretch can a warp find its record not handed over yet)
@@ -671,100 +697,219 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
       const ForestSub& S = inSmem ? sSubs[rb.x] : subs[rb.x];
       const int nc = rb.w, nrows = rb.z, kd = rc.x, xcol = rc.y, ydiag = rc.z;
       const int Q = (nc + RING_CH - 1) / RING_CH;
-      if (!bwd) {
-        // [ y1 ; x2 ] (+,-)= P[r0:r0+64, c0:c0+nc] * x1
-        double xv[4];
-        if (havex) {
+      if constexpr (NR == 1) {
+        if (!bwd) {
+          // [ y1 ; x2 ] (+,-)= P[r0:r0+64, c0:c0+nc] * x1
+          double xv[4];
+          if (havex) {
 #pragma unroll
-          for (int g = 0; g < 4; g++) xv[g] = xn[g];
-        } else {
-          const double* x1 = X + (S.xoff + xcol);
+            for (int g = 0; g < 4; g++) xv[g] = xn[g];
+          } else {
+            const double* x1 = X + (S.xoff + xcol);
 #pragma unroll
-          for (int g = 0; g < 4; g++) xv[g] = (g * 32 + lane < nc) ? __ldcg(x1 + g * 32 + lane) : 0.;
-        }
-        havex = false;
-        double a0 = 0., a1 = 0.;
-        int row0 = 0, row1 = 0;
-        for (int q = 0; q < Q; q++) {
-          const unsigned char* st = acquire();
-          if (q == 0) {
-            const int2 ri = *reinterpret_cast<const int2*>(st + RING_TILE + 8 * lane);
-            row0 = ri.x; row1 = ri.y;
+            for (int g = 0; g < 4; g++) xv[g] = (g * 32 + lane < nc) ? __ldcg(x1 + g * 32 + lane) : 0.;
           }
-          if (q == Q - 1 && i + nw < cnt && !(flags & 2)) {  // the next item's record has been handed over by now (RING_S >= 2)
-            __syncwarp();
-            const int4* r2 = recRing + (cm & (RING_RS - 1)) * 3;
-            const int4 b2 = r2[1], c2 = r2[2];
-            const double* x2 = X + ((inSmem ? sSubs[b2.x] : subs[b2.x]).xoff + c2.y);
-#pragma unroll
-            for (int g = 0; g < 4; g++) xn[g] = (g * 32 + lane < b2.w) ? __ldcg(x2 + g * 32 + lane) : 0.;
-            havex = true;
-          }
-          const double2* tb = reinterpret_cast<const double2*>(st) + lane;
-          const int ncc = min(RING_CH, nc - q * RING_CH);
-          const double xg = (q >> 2) == 0 ? xv[0] : (q >> 2) == 1 ? xv[1] : (q >> 2) == 2 ? xv[2] : xv[3];
-#pragma unroll
-          for (int u = 0; u < RING_CH; u++)
-            if (u < ncc) {
-              const double2 v = tb[u * 32];
-              const double xc = __shfl_sync(0xffffffffu, xg, (q * RING_CH + u) & 31);
-              a0 += v.x * xc;
-              a1 += v.y * xc;
+          havex = false;
+          double a0 = 0., a1 = 0.;
+          int row0 = 0, row1 = 0;
+          for (int q = 0; q < Q; q++) {
+            const unsigned char* st = acquire();
+            if (q == 0) {
+              const int2 ri = *reinterpret_cast<const int2*>(st + TILE_BYTES + 8 * lane);
+              row0 = ri.x; row1 = ri.y;
             }
-          ccount++;
-        }
-        const int r = 2 * lane;
-        if (r < nrows) {
-          if (r < kd) atomicAdd(Y + (S.xoff + ydiag + r), a0);
-          else atomicAdd(X + (S.xoff + row0), -a0);
-        }
-        if (r + 1 < nrows) {
-          if (r + 1 < kd) atomicAdd(Y + (S.xoff + ydiag + r + 1), a1);
-          else atomicAdd(X + (S.xoff + row1), -a1);
-        }
-      } else {
-        // y1[c0:c0+nc] -= L21[rows, c0:c0+nc]^T * y2[rows]      (nc <= 16, rows in tiles of 64)
-        double acc[RING_BWD_COLS];
+            if (q == Q - 1 && i + nw < cnt && !(flags & 2)) {  // the next item's record has been handed over by now (RING_S >= 2)
+              __syncwarp();
+              const int4* r2 = recRing + (cm & (RING_RS - 1)) * 3;
+              const int4 b2 = r2[1], c2 = r2[2];
+              const double* x2 = X + ((inSmem ? sSubs[b2.x] : subs[b2.x]).xoff + c2.y);
 #pragma unroll
-        for (int u = 0; u < RING_BWD_COLS; u++) acc[u] = 0.;
-        const int T = (nrows + 63) >> 6;
-        for (int t = 0; t < T; t++) {
-          double y0 = 0., y1 = 0.;
+              for (int g = 0; g < 4; g++) xn[g] = (g * 32 + lane < b2.w) ? __ldcg(x2 + g * 32 + lane) : 0.;
+              havex = true;
+            }
+            const double2* tb = reinterpret_cast<const double2*>(st) + lane;
+            const int ncc = nc - q * RING_CH;
+            const double xg = (q >> 2) == 0 ? xv[0] : (q >> 2) == 1 ? xv[1] : (q >> 2) == 2 ? xv[2] : xv[3];
+            const int cb = (q & 3) * RING_CH;
+            if (ncc >= RING_CH) {
 #pragma unroll
-          for (int cq = 0; cq < RING_BWD_COLS / RING_CH; cq++) {
-            if (cq < Q) {  // warp-uniform
-              const unsigned char* st = acquire();
-              if (cq == 0) {
-                const int r = t * 64 + 2 * lane;
-                const int2 ri = *reinterpret_cast<const int2*>(st + RING_TILE + 8 * lane);
-                if (r >= kd && r < nrows) y0 = __ldcg(Y + (S.xoff + ri.x));
-                if (r + 1 >= kd && r + 1 < nrows) y1 = __ldcg(Y + (S.xoff + ri.y));
+              for (int u = 0; u < RING_CH; u++) {
+                const double2 v = tb[u * 32];
+                const double xc = __shfl_sync(0xffffffffu, xg, cb + u);
+                a0 += v.x * xc;
+                a1 += v.y * xc;
               }
-              const double2* tb = reinterpret_cast<const double2*>(st) + lane;
-              const int ncc = min(RING_CH, nc - cq * RING_CH);
+            } else {
 #pragma unroll
-              for (int u = 0; u < RING_CH; u++)
+              for (int u = 0; u < RING_CH - 1; u++)
                 if (u < ncc) {
                   const double2 v = tb[u * 32];
-                  acc[cq * RING_CH + u] += v.x * y0 + v.y * y1;
+                  const double xc = __shfl_sync(0xffffffffu, xg, cb + u);
+                  a0 += v.x * xc;
+                  a1 += v.y * xc;
                 }
-              ccount++;
+            }
+            release();
+          }
+          const int r = 2 * lane;
+          if (r < nrows) {
+            if (r < kd) atomicAdd(Y + (S.xoff + ydiag + r), a0);
+            else atomicAdd(X + (S.xoff + row0), -a0);
+          }
+          if (r + 1 < nrows) {
+            if (r + 1 < kd) atomicAdd(Y + (S.xoff + ydiag + r + 1), a1);
+            else atomicAdd(X + (S.xoff + row1), -a1);
+          }
+        } else {
+          // y1[c0:c0+nc] -= L21[rows, c0:c0+nc]^T * y2[rows]      (nc <= 16, rows in tiles of 64)
+          double acc[BWD_COLS];
+#pragma unroll
+          for (int u = 0; u < BWD_COLS; u++) acc[u] = 0.;
+          const int T = (nrows + 63) >> 6;
+          for (int t = 0; t < T; t++) {
+            double y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int cq = 0; cq < BWD_COLS / RING_CH; cq++) {
+              if (cq < Q) {  // warp-uniform
+                const unsigned char* st = acquire();
+                if (cq == 0) {
+                  const int r = t * 64 + 2 * lane;
+                  const int2 ri = *reinterpret_cast<const int2*>(st + TILE_BYTES + 8 * lane);
+                  if (r >= kd && r < nrows) y0 = __ldcg(Y + (S.xoff + ri.x));
+                  if (r + 1 >= kd && r + 1 < nrows) y1 = __ldcg(Y + (S.xoff + ri.y));
+                }
+                const double2* tb = reinterpret_cast<const double2*>(st) + lane;
+                const int ncc = nc - cq * RING_CH;
+#pragma unroll
+                for (int u = 0; u < RING_CH; u++)
+                  if (u < ncc) {
+                    const double2 v = tb[u * 32];
+                    acc[cq * RING_CH + u] += v.x * y0 + v.y * y1;
+                  }
+                release();
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < BWD_COLS; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+#pragma unroll
+          for (int o = BWD_COLS / 2; o >= 1; o >>= 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int i2 = 0; i2 < o; i2++) {
+              const double send = upper ? acc[i2] : acc[i2 + o];
+              const double keep = upper ? acc[i2 + o] : acc[i2];
+              acc[i2] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          if (lane < BWD_COLS && lane < nc) atomicAdd(&Y[S.xoff + xcol + lane], -acc[0]);
+        }
+      } else {
+        // ---------------- NR = 8: FP64 tensor-core fragments; lane = 4 g + t ----------------
+        const int g = lane >> 2, t4 = lane & 3;
+        if (!bwd) {
+          // C[row rb*8+g][rhs 2 t4 + e] += sum_cols L[row][col] X[col][rhs];  B fragment: X[col 4 ks + t4][rhs g]
+          auto load_x = [&](const ForestSub& S2, int xc2, int nc2, int grp, double (&xf)[8]) {
+            const double* xb = X + (size_t)(S2.xoff + xc2 + grp * 32) * ldx + g;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+              const int c = grp * 32 + ks * 4 + t4;
+              xf[ks] = c < nc2 ? __ldcg(xb + (size_t)(ks * 4 + t4) * ldx) : 0.;
+            }
+          };
+          double xf[8];
+          if (havex) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) xf[ks] = xn[ks];
+          } else load_x(S, xcol, nc, 0, xf);
+          havex = false;
+          double acc[8][2];
+#pragma unroll
+          for (int b8 = 0; b8 < 8; b8++) acc[b8][0] = acc[b8][1] = 0.;
+          int ridx[8];
+          for (int q = 0; q < Q; q++) {
+            if (q > 0 && (q & 3) == 0) load_x(S, xcol, nc, q >> 2, xf);  // next group of 32 columns
+            const unsigned char* st = acquire();
+            if (q == 0) {
+              const int* ip = reinterpret_cast<const int*>(st + TILE_BYTES);
+#pragma unroll
+              for (int b8 = 0; b8 < 8; b8++) ridx[b8] = ip[b8 * 8 + g];
+            }
+            if (q == Q - 1 && i + nw < cnt) {
+              const int4* r2 = recRing + (cm & (RING_RS - 1)) * 3;
+              const int4 b2 = r2[1], c2 = r2[2];
+              load_x(inSmem ? sSubs[b2.x] : subs[b2.x], c2.y, b2.w, 0, xn);
+              havex = true;
+            }
+            const double* tb = reinterpret_cast<const double*>(st);
+            const int ncc = nc - q * RING_CH;
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++) {
+              const int col = ks * 4 + t4;
+              const double bfrag = (q & 1) ? ((q & 2) ? xf[6 + ks] : xf[2 + ks]) : ((q & 2) ? xf[4 + ks] : xf[ks]);
+              const double* ap = tb + col * CS + g;
+              const bool ok = col < ncc;
+#pragma unroll
+              for (int b8 = 0; b8 < 8; b8++) {
+                const double a = ok ? ap[b8 * 8] : 0.;
+                dmma8x8x4(acc[b8][0], acc[b8][1], a, bfrag);
+              }
+            }
+            release();
+          }
+#pragma unroll
+          for (int b8 = 0; b8 < 8; b8++) {
+            const int r = b8 * 8 + g;
+            if (r < nrows) {
+              if (r < kd) {
+                double* d = Y + (size_t)(S.xoff + ydiag + r) * ldx + 2 * t4;
+                atomicAdd(d, acc[b8][0]);
+                atomicAdd(d + 1, acc[b8][1]);
+              } else {
+                double* d = X + (size_t)(S.xoff + ridx[b8]) * ldx + 2 * t4;
+                atomicAdd(d, -acc[b8][0]);
+                atomicAdd(d + 1, -acc[b8][1]);
+              }
+            }
+          }
+        } else {
+          // C[col cq*8+g][rhs 2 t4 + e] += sum_rows L[row][col] Y2[row][rhs];  A fragment: L[row 4 ks + t4][col g],
+          // B fragment: Y2[row 4 ks + t4][rhs g]
+          double acc[BWD_COLS / 8][2];
+#pragma unroll
+          for (int c8 = 0; c8 < BWD_COLS / 8; c8++) acc[c8][0] = acc[c8][1] = 0.;
+          const int T = (nrows + 63) >> 6;
+          for (int t = 0; t < T; t++) {
+            double yf[16];
+#pragma unroll
+            for (int cq = 0; cq < BWD_COLS / RING_CH; cq++) {
+              if (cq < Q) {  // warp-uniform
+                const unsigned char* st = acquire();
+                if (cq == 0) {
+                  const int* ip = reinterpret_cast<const int*>(st + TILE_BYTES);
+#pragma unroll
+                  for (int ks = 0; ks < 16; ks++) {
+                    const int r = t * 64 + ks * 4 + t4;
+                    yf[ks] = (r >= kd && r < nrows) ? __ldcg(Y + (size_t)(S.xoff + ip[ks * 4 + t4]) * ldx + g) : 0.;
+                  }
+                }
+                const double* ap = reinterpret_cast<const double*>(st) + g * CS + t4;
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++) dmma8x8x4(acc[cq][0], acc[cq][1], ap[ks * 4], yf[ks]);
+                release();
+              }
+            }
+          }
+#pragma unroll
+          for (int c8 = 0; c8 < BWD_COLS / 8; c8++) {
+            const int c = c8 * 8 + g;
+            if (c < nc) {
+              double* d = Y + (size_t)(S.xoff + xcol + c) * ldx + 2 * t4;
+              atomicAdd(d, -acc[c8][0]);
+              atomicAdd(d + 1, -acc[c8][1]);
             }
           }
         }
-#pragma unroll
-        for (int q = 0; q < RING_BWD_COLS; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
-#pragma unroll
-        for (int o = RING_BWD_COLS / 2; o >= 1; o >>= 1) {
-          const bool upper = (lane & o) != 0;
-#pragma unroll
-          for (int i2 = 0; i2 < o; i2++) {
-            const double send = upper ? acc[i2] : acc[i2 + o];
-            const double keep = upper ? acc[i2 + o] : acc[i2];
-            acc[i2] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
-        }
-        if (lane < RING_BWD_COLS && lane < nc) atomicAdd(&Y[S.xoff + xcol + lane], -acc[0]);
       }
     }
     if (!(flags & 4)) top_up();  // idle warps keep scanning ahead / prefetching here, off everybody's critical path
@@ -989,22 +1134,28 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   }
   {
     int nb = 0;
-    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring, SOLVE_THREADS, RING_SMEM));
-    gridBlocks1 = std::max(1, nb) * nsm;
+    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<1>::SMEM));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<1>, RingCfg<1>::WARPS * 32, RingCfg<1>::SMEM));
+    ringGrid[0] = std::max(1, nb) * nsm;
+    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<8>::SMEM));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<8>, RingCfg<8>::WARPS * 32, RingCfg<8>::SMEM));
+    ringGrid[1] = std::max(1, nb) * nsm;
   }
-  build_ring();
 }
 
 // Item lists of the ring kernel.  Per level the host picks the span of an item from the amount of work in the level: a
 // level with many tiles per warp gets wide (forward: up to all 128 columns of a panel) / tall (backward: up to 512 rows)
 // items -- fewer records, x / y fetches and atomics per byte --, a level near the root gets the finest tiles so that every
 // warp of the chip has something to stream.
-void SolveForest::build_ring() {
+void SolveForest::build_ring(int which) const {
   const int ns = (int)plans_.size();
-  const int64_t nw = (int64_t)gridBlocks1 * (SOLVE_THREADS / 32);
+  const int warps = which == 0 ? RingCfg<1>::WARPS : RingCfg<8>::WARPS;
+  const int RING_BWD_COLS = which == 0 ? RingCfg<1>::BWD_COLS : RingCfg<8>::BWD_COLS;
+  const int64_t nw = (int64_t)ringGrid[which] * warps;
   std::vector<RingItem> items;
   std::vector<int64_t> ranges(4 * (size_t)nlev, 0);
+  std::vector<double>& ringBytes = ringBytes_[which];
+  std::vector<int64_t>& ringCount = ringCount_[which];
   ringBytes.assign(2 * (size_t)nlev, 0.);
   ringCount.assign(2 * (size_t)nlev, 0);
   auto by_size = [](const RingItem& a, const RingItem& b) { return (int64_t)a.nrows * a.nc > (int64_t)b.nrows * b.nc; };
@@ -1072,9 +1223,10 @@ void SolveForest::build_ring() {
     ringBytes[2 * nlev - 1 - l] = bytes;  // phase order: backward runs from the root down
     ringCount[2 * nlev - 1 - l] = ranges[3 * nlev + l];
   }
-  dRing.upload(items);
-  dRingRanges.upload(ranges);
+  dRing[which].upload(items);
+  dRingRanges[which].upload(ranges);
   CUDA_CHECK(::geneo::sync_stream(0));
+  ringBuilt[which] = true;
 }
 
 static int ring_flags() {  // experiment switches of the ring kernel (GENEO_RING_FLAGS)
@@ -1098,14 +1250,20 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   const int64_t* ranges = dRanges.p;
   int nl = nlev;
   int64_t nt = ntot;
-  if (nr == 1 && ldx == 1 && !getenv("GENEO_SOLVE_GENERIC")) {
-    const RingItem* ritems = dRing.p;
-    const int64_t* rranges = dRingRanges.p;
+  if (((nr == 1 && ldx == 1) || nr == 8) && !getenv("GENEO_SOLVE_GENERIC")) {
+    const int which = nr == 1 ? 0 : 1;
+    if (!ringBuilt[which]) build_ring(which);
+    const RingItem* ritems = dRing[which].p;
+    const int64_t* rranges = dRingRanges[which].p;
     long long* ts = nullptr;
     int flags = ring_flags();
-    void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ts, (void*)&flags};
+    void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp,
+                  (void*)&ldx, (void*)&ts, (void*)&flags};
     (void)GENEO_TICK(0);
-    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, RING_SMEM, st));
+    if (which == 0)
+      CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<1>, dim3(ringGrid[0]), dim3(RingCfg<1>::WARPS * 32), a1, RingCfg<1>::SMEM, st));
+    else
+      CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<8>, dim3(ringGrid[1]), dim3(RingCfg<8>::WARPS * 32), a1, RingCfg<8>::SMEM, st));
     return;
   }
   void* args[] = {(void*)&subs, (void*)&nsubs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ldx};
@@ -1122,26 +1280,34 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(SOLVE_THREADS), args, 0, st));
 }
 
-void SolveForest::solve_profile(double* X, double* Y, std::vector<double>& us, std::vector<double>& bytes,
+void SolveForest::solve_profile(double* X, double* Y, int nr, std::vector<double>& us, std::vector<double>& bytes,
                                 std::vector<int64_t>& nitems) const {
+  GENEO_CHECK(nr == 1 || nr == 8, "solve_profile: nr must be 1 or 8");
+  const int which = nr == 1 ? 0 : 1;
+  if (!ringBuilt[which]) build_ring(which);
   const ForestSub* subs = dSubs.p;
   int nsubs = (int)hSubs.size();
-  const RingItem* ritems = dRing.p;
-  const int64_t* rranges = dRingRanges.p;
+  const RingItem* ritems = dRing[which].p;
+  const int64_t* rranges = dRingRanges[which].p;
   int nl = nlev;
   int64_t nt = ntot;
+  int ldx = nr;
   DevBuf<long long> dts((size_t)2 * nlev + 1);
   long long* ts = dts.p;
   int flags = ring_flags();
-  void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&X, (void*)&Y, (void*)&ts, (void*)&flags};
+  void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&X, (void*)&Y,
+                (void*)&ldx, (void*)&ts, (void*)&flags};
   (void)GENEO_TICK(0);
-  CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring, dim3(gridBlocks1), dim3(SOLVE_THREADS), a1, RING_SMEM, 0));
+  if (which == 0)
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<1>, dim3(ringGrid[0]), dim3(RingCfg<1>::WARPS * 32), a1, RingCfg<1>::SMEM, 0));
+  else
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<8>, dim3(ringGrid[1]), dim3(RingCfg<8>::WARPS * 32), a1, RingCfg<8>::SMEM, 0));
   CUDA_CHECK(::geneo::sync_stream(0));
   std::vector<long long> h = dts.to_host();
   us.resize(2 * (size_t)nlev);
   for (int p = 0; p < 2 * nlev; p++) us[p] = 1e-3 * (double)(h[p + 1] - h[p]);
-  bytes = ringBytes;
-  nitems = ringCount;
+  bytes = ringBytes_[which];
+  nitems = ringCount_[which];
 }
 
 // Synthetic streaming benchmark of the solve kernel: nf independent h x k panels at ONE level (no level effects, no

@@ -54,23 +54,25 @@ class SolveForest {
   void solve(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const;
   // NR = 1 solve with a device timestamp after every level barrier: us[p] = duration of phase p (forward levels bottom-up,
   // then backward levels top-down), bytes[p] = factor bytes streamed in it, nitems[p] = ring items
-  void solve_profile(double* X, double* Y, std::vector<double>& us, std::vector<double>& bytes, std::vector<int64_t>& nitems) const;
+  void solve_profile(double* X, double* Y, int nr, std::vector<double>& us, std::vector<double>& bytes, std::vector<int64_t>& nitems) const;
   int nlev = 0;
   int64_t ntot = 0;
  private:
-  void build_ring();
+  void build_ring(int which) const;  // which = 0: NR = 1 item lists, 1: NR = 8 (built on first use)
   std::vector<const LdltPlan*> plans_;
   std::vector<int64_t> xoff_;
   std::vector<ForestSub> hSubs;
   DevBuf<ForestSub> dSubs;
   DevBuf<ForestItem> dItems;
   DevBuf<int64_t> dRanges;
-  DevBuf<RingItem> dRing;       // NR = 1 ring kernel: its own item lists (spans chosen per level) and ranges
-  DevBuf<int64_t> dRingRanges;
-  std::vector<double> ringBytes;  // per phase (2 * nlev)
-  std::vector<int64_t> ringCount;
+  // ring kernels (NR = 1 and NR = 8): their own item lists (spans chosen per level) and ranges, built on first use
+  mutable DevBuf<RingItem> dRing[2];
+  mutable DevBuf<int64_t> dRingRanges[2];
+  mutable std::vector<double> ringBytes_[2];  // per phase (2 * nlev)
+  mutable std::vector<int64_t> ringCount_[2];
+  mutable bool ringBuilt[2] = {false, false};
+  int ringGrid[2] = {1, 1};
   int gridBlocks[4] = {1, 1, 1, 1};
-  int gridBlocks1 = 1;
 };
 
 struct FactorStats { int neg = 0, perturbed = 0; double seconds = 0.; };
