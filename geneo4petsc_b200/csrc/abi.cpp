@@ -611,6 +611,19 @@ int geneo_microbench(int kind, int n, int reps, double result[2]) {
     double gb = 0.;
     result[1] = solve_stream_bench(reps, std::max(n, 128), 128, 5, &gb, nlev, nr);
     result[0] = gb;
+  } else if (kind == 3) {  // the Schur-update shape: C (n x n) -= A (n x 128) B (n x 128)^T, C streamed from HBM
+    const int K = 128;
+    DevBuf<double> A((size_t)n * K), B((size_t)n * K), C((size_t)n * n);
+    A.zero(); B.zero(); C.zero();
+    dgemm_nt_device(n, n, K, A.p, n, B.p, n, C.p, n, 1, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; r++) dgemm_nt_device(n, n, K, A.p, n, B.p, n, C.p, n, 1, 0);
+    CUDA_CHECK(cudaEventRecord(e1));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    result[0] = 2. * (double)n * n * K * reps / (ms * 1e-3) / 1e12;
+    result[1] = ms / reps;
   } else if (kind == 0) {
     std::vector<double> hA((size_t)n * n), hB((size_t)n * n);
     for (size_t i = 0; i < hA.size(); i++) { hA[i] = (double)((i * 2654435761u) % 1000) / 1000. - 0.5; hB[i] = (double)((i * 40503u) % 1000) / 1000. - 0.5; }

@@ -44,10 +44,22 @@ extern bool g_profile;
 void profile_tick(const char* file, int line);
 // every host wait of the library goes through here: in profile mode a marker event closes the interval of the last
 // kernel, so that the idle gap while the host works is accounted to "host" and not to that kernel
+extern double g_sync_wait_s;  // host time spent waiting for the device (what is left of a phase is host-side work)
 inline cudaError_t sync_stream(cudaStream_t s) {
   if (g_profile) profile_tick("<host wait / idle>", 0);
-  return cudaStreamSynchronize(s);
+  const double t0 = now_s();
+  const cudaError_t e = cudaStreamSynchronize(s);
+  g_sync_wait_s += now_s() - t0;
+  return e;
 }
+// GENEO_HOSTPROF=1: named host-side stopwatches (seconds, calls), printed by host_prof_report()
+void host_prof_add(const char* name, double seconds);
+void host_prof_report(const char* title);
+struct HostProfScope {
+  const char* name; double t0;
+  explicit HostProfScope(const char* n) : name(n), t0(now_s()) {}
+  ~HostProfScope() { host_prof_add(name, now_s() - t0); }
+};
 #define GENEO_TICK(g) ((::geneo::g_profile ? ::geneo::profile_tick(__FILE__, __LINE__) : (void)0), ::geneo::launch_tick(g))
 
 // The product has NO CPU fallback: every numeric entry point calls this first.
@@ -59,28 +71,36 @@ inline void require_device() {
                 std::string(cudaGetErrorString(e)) + ")");
 }
 
+// Device memory goes through a small stream-ordered block cache: every kernel and copy of the library runs on ONE in-order
+// stream, so a released block can be handed to the next request without the implicit device synchronisation (and the
+// page-table work) of cudaFree / cudaMalloc -- which otherwise sit between the factorizations of a re-setup.
+void* dev_alloc(size_t bytes, size_t* cap);
+void dev_free(void* p, size_t cap);
+void dev_cache_flush();  // give every cached block back to the driver
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  size_t cap = 0;  // bytes of the underlying block
   DevBuf() {}
   explicit DevBuf(size_t n_) { alloc(n_); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = 0; o.cap = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = 0; o.cap = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
+    if (p) dev_free(p, cap);
+    p = nullptr; n = 0; cap = 0;
   }
   void alloc(size_t n_) {
     release();
     n = n_;
-    if (n) CUDA_CHECK(cudaMalloc((void**)&p, n * sizeof(T)));
+    if (n) p = static_cast<T*>(dev_alloc(n * sizeof(T), &cap));
   }
   void zero(cudaStream_t s = 0) { if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const T* h, size_t cnt, cudaStream_t s = 0) {

@@ -58,9 +58,17 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     maxDim = std::max(b, maxDim / b * b);
   }
   const int bp = (b + 7) / 8 * 8;
-  DevBuf<double> Q((size_t)n * maxDim), BQ((size_t)n * maxDim), W((size_t)n * bp), W2((size_t)n * bp), BW((size_t)n * bp),
-      BW2((size_t)n * bp), Xs((size_t)n * bp), dC((size_t)maxDim * std::max(bp, nev));
+  HostProfScope hpAll("lanczos: all");
+  const double tAlloc0 = now_s();
+  EigWorkspace localWs;
+  EigWorkspace& E = opt.ws ? *opt.ws : localWs;
+  auto need = [](DevBuf<double>& d, size_t cnt) { if (d.n < cnt) d.alloc(cnt); };
+  need(E.Q, (size_t)n * maxDim); need(E.BQ, (size_t)n * maxDim);
+  need(E.W, (size_t)n * bp); need(E.W2, (size_t)n * bp); need(E.BW, (size_t)n * bp); need(E.BW2, (size_t)n * bp);
+  need(E.Xs, (size_t)n * bp); need(E.dC, (size_t)maxDim * std::max(bp, nev));
+  DevBuf<double>&Q = E.Q, &BQ = E.BQ, &W = E.W, &W2 = E.W2, &BW = E.BW, &BW2 = E.BW2, &Xs = E.Xs, &dC = E.dC;
   double* w = W.p; double* w2 = W2.p; double* bw = BW.p; double* bw2 = BW2.p;
+  host_prof_add("lanczos: alloc", now_s() - tAlloc0);
 
   auto spmmB = [&](const double* X, double* Y) {  // Y = B X for ld = bp blocks
     for (int j0 = 0; j0 < bp; j0 += 8) csr_spmm(n, ptr, idx, valB, X + j0, bp, Y + j0, bp, 8, st);
@@ -103,7 +111,10 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
   int dim = 0, steps = 0;
   bool done = false;
   bool prefetched = false;  // the solve of this step was already queued behind the previous step's device work
+  int nextRR = 0, prevRRstep = -1;
+  double prevWorst = 0.;
   auto launch_solve = [&](int jj) {  // W = F^-1 (B Q_jj)
+    HostProfScope hp("lanczos: launch_solve");
     k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)jj * b, maxDim, Xs.p, bp, b, bp);
     for (int j0 = 0; j0 < bp; j0 += 8) F.solve_permuted(Xs.p, w, bp, j0, 8, st);
   };
@@ -213,8 +224,15 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     // have converged: the O(dim^3) host eigen-solve is the one serial piece of a step)
     const int want = std::min(nev, dim);
     int nconv = 0;
-    const bool doRR = !(canContinue && dim < nev + b);
+    // The O(dim^3) host eigen-solve is the one serial piece of a step and, once the factor streams at HBM speed, the
+    // most expensive one: it runs when the basis can hold nev converged pairs and then only at the steps where the
+    // residual of the slowest wanted pair is PREDICTED to reach the tolerance (geometric decay fitted through the last
+    // two Rayleigh-Ritz steps, at most 6 steps ahead).  A step too many costs one block solve; the result is the same
+    // Rayleigh-Ritz of the final basis either way.
+    bool doRR = !(canContinue && dim < nev + b);
+    if (doRR && canContinue && steps < nextRR) doRR = false;
     if (doRR) {
+    HostProfScope hpRR("lanczos: rayleigh-ritz");
     T.assign((size_t)dim * dim, 0.);
     for (int i = 0; i < dim; i++)
       for (int c = 0; c < dim; c++) T[(size_t)i * dim + c] = 0.5 * (Hm[(size_t)i * maxDim + c] + Hm[(size_t)c * maxDim + i]);
@@ -233,6 +251,19 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       ritzVal[q] = theta[col];
       ritzRes[q] = std::sqrt(s2) / std::max(std::fabs(theta[col]), 1e-300);
       if (ritzRes[q] <= opt.tol) nconv++;
+    }
+    {
+      double worst = 0.;
+      for (int q = 0; q < want; q++) worst = std::max(worst, ritzRes[q]);
+      int ahead = 1;
+      if (want == nev && prevRRstep >= 0 && worst > opt.tol && worst < prevWorst && prevWorst > 0.) {
+        const double rate = std::log(worst / prevWorst) / (double)(steps - prevRRstep);  // < 0 per step
+        ahead = (int)std::floor(std::log(opt.tol / worst) / rate);
+        ahead = std::max(1, std::min(ahead, 6));
+      } else if (want == nev && prevRRstep < 0) ahead = 2;  // second sample for the fit
+      prevWorst = worst;
+      prevRRstep = steps;
+      nextRR = steps + ahead;
     }
     }
     steps++;

@@ -14,11 +14,19 @@
 
 namespace geneo {
 
+// Device buffers of the block Lanczos iteration (basis Q, B Q, work blocks).  Grow-only: one instance serves every
+// subdomain of every (re-)setup, so no multi-GB cudaMalloc / cudaFree sits between two eigen-solves.
+struct EigWorkspace {
+  DevBuf<double> Q, BQ, W, W2, BW, BW2, Xs, dC;
+  void release() { Q.release(); BQ.release(); W.release(); W2.release(); BW.release(); BW2.release(); Xs.release(); dC.release(); }
+};
+
 struct EigOptions {
   int block = 8;
   double tol = 1e-4;      // ||T x - theta x||_B <= tol * |theta|
   int maxDim = 0;         // 0: automatic
   bool invert = true;     // report lambda = 1/theta
+  EigWorkspace* ws = nullptr;  // optional persistent buffers
 };
 
 struct EigResult {

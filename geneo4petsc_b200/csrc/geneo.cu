@@ -30,6 +30,82 @@ void profile_tick(const char* file, int line) {
   cudaEventRecord(r.ev, 0);
   g_prof.push_back(r);
 }
+// ---- stream-ordered device block cache (common.hpp) -------------------------------------------------------------------
+namespace {
+struct CachedBlock { void* p; size_t cap; };
+// (never destroyed: DevBufs with static storage duration may be released after any other static object)
+std::vector<CachedBlock>& g_dev_cache = *new std::vector<CachedBlock>();
+size_t g_dev_cache_bytes = 0;
+std::mutex& g_dev_cache_mtx = *new std::mutex();
+size_t dev_cache_limit() {
+  static const size_t lim = [] { const char* e = getenv("GENEO_CACHE_GB"); return (size_t)((e ? atof(e) : 16.) * 1073741824.); }();
+  return lim;
+}
+}  // namespace
+void dev_cache_flush() {
+  std::lock_guard<std::mutex> lk(g_dev_cache_mtx);
+  for (auto& b : g_dev_cache) cudaFree(b.p);
+  g_dev_cache.clear();
+  g_dev_cache_bytes = 0;
+}
+void* dev_alloc(size_t bytes, size_t* cap) {
+  const size_t want = (bytes + 511) & ~(size_t)511;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_cache_mtx);
+    int best = -1;
+    for (int i = 0; i < (int)g_dev_cache.size(); i++) {
+      const size_t c = g_dev_cache[i].cap;
+      if (c >= want && c <= want + want / 4 + (1u << 20) && (best < 0 || c < g_dev_cache[best].cap)) best = i;
+    }
+    if (best >= 0) {
+      void* p = g_dev_cache[best].p;
+      *cap = g_dev_cache[best].cap;
+      g_dev_cache_bytes -= *cap;
+      g_dev_cache[best] = g_dev_cache.back();
+      g_dev_cache.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {  // out of memory with blocks parked in the cache: give them back and try again
+    cudaGetLastError();
+    dev_cache_flush();
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) throw Error(std::string("geneo_b200: cudaMalloc of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+  *cap = want;
+  return p;
+}
+void dev_free(void* p, size_t cap) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_dev_cache_mtx);
+  if (cap > dev_cache_limit() / 2 || g_dev_cache_bytes + cap > dev_cache_limit() || g_dev_cache.size() >= 256) {
+    cudaFree(p);
+    return;
+  }
+  g_dev_cache.push_back(CachedBlock{p, cap});
+  g_dev_cache_bytes += cap;
+}
+
+double g_sync_wait_s = 0.;
+namespace {
+const bool g_hostprof = getenv("GENEO_HOSTPROF") != nullptr;
+struct HostProfRec { std::string name; double s = 0.; long n = 0; };
+std::vector<HostProfRec> g_hostprof_recs;
+}  // namespace
+void host_prof_add(const char* name, double seconds) {
+  if (!g_hostprof) return;
+  for (auto& r : g_hostprof_recs) if (r.name == name) { r.s += seconds; r.n++; return; }
+  g_hostprof_recs.push_back(HostProfRec{name, seconds, 1});
+}
+void host_prof_report(const char* title) {
+  if (!g_hostprof) return;
+  fprintf(stderr, "HOSTPROF %s: sync-wait %.3f s\n", title, g_sync_wait_s);
+  for (auto& r : g_hostprof_recs) fprintf(stderr, "HOSTPROF   %-28s %9.3f s  %7ld calls\n", r.name.c_str(), r.s, r.n);
+  g_hostprof_recs.clear();
+  g_sync_wait_s = 0.;
+}
 int profile_dump(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) return 1;
@@ -105,6 +181,7 @@ int GeneoOptions::parse(int argc, const char* const* argv, std::string& err) {
     else if (o == "-geneo_gamma") { const char* v = need(a, "-geneo_gamma"); if (!v || !num(v, gamma, "-geneo_gamma")) return 1; a++; }
     else if (o == "-geneo_cut") { double c; const char* v = need(a, "-geneo_cut"); if (!v || !num(v, c, "-geneo_cut")) return 1; cut = (int)c; a++; }
     else if (o == "-geneo_cst") cst = true;
+    else if (o == "-geneo_release_workspace") releaseWorkspace = true;
     else if (o == "-geneo_no_syl") noSyl = true;
     else if (o == "-geneo_offload") offload = true;
     else if (o == "-geneo_dbg") {
@@ -380,7 +457,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
 
 
   numeric_begin();
-  LdltWorkspace ws;
+  LdltWorkspace& ws = factorWs;
   std::vector<int> gAll((size_t)nAll);
   std::vector<double> dA((size_t)nAll);
   double waitHost = 0., tUp = 0., tNum = 0.;
@@ -417,7 +494,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     numeric_subdomain(s, ws);
     tNum += now_s() - tn;
   }
-  ws = LdltWorkspace();
+  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); }
   symbolicTime = waitHost;  // time this thread spent WAITING for the host analysis (the rest of it was hidden behind the device)
   uploadTime = tUp;
 
@@ -459,6 +536,7 @@ void GeneoPC::numeric_begin() {
 }
 
 void GeneoPC::numeric_end() {
+  HostProfScope hpEnd("numeric_end");
   if (comm.active()) {  // the driver prints GLOBAL dimensions (src/geneo4PETSc.cpp:971-986 reduces them over the ranks)
     double g[3] = {(double)estimDimE, (double)realDimE, (double)nicolaides};
     comm.allreduce_sum_host(g, 3, st);
@@ -488,11 +566,12 @@ void GeneoPC::numeric_end() {
 void GeneoPC::numeric_setup() {
   const double tNum0 = now_s();
   numeric_begin();
-  LdltWorkspace ws;
-  for (auto& s : subs) numeric_subdomain(s, ws);
-  ws = LdltWorkspace();
+  for (auto& s : subs) numeric_subdomain(s, factorWs);
+  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); }
   numeric_end();
   numericTime = now_s() - tNum0;
+  host_prof_add("numeric_setup total", numericTime);
+  host_prof_report("numeric_setup");
 }
 
 void GeneoPC::level_profile(std::vector<double>& us, std::vector<double>& bytes, std::vector<int64_t>& nitems) {
@@ -517,6 +596,7 @@ void GeneoPC::kernel_time(double* ms, int64_t* launches) {
 
 // every factorization and eigen-solve of one subdomain (level 2 first: its factors are transient)
 void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
+  HostProfScope hpSub("numeric_subdomain");
   {
     const double anorm = s.anorm;
     // pivot threshold
@@ -530,6 +610,7 @@ void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
       if (opt.lvl2 == 2 && cut >= 2) cut = cut / 2;  // src/geneo.cpp:1275
       const int savedCut = opt.cut;
       opt.cut = cut;
+      HostProfScope hpL2("numeric_subdomain: level 2");
       DevBuf<double> vB((size_t)s.pat.nnz);
       csr_scale_sym(s.n, s.pat.ptr.p, s.pat.idx.p, s.pat.val.p, s.d.p, vB.p, st);  // D A_dir D, src/geneo.cpp:1243-1246
       if (opt.lvl2 == 1) {
@@ -575,7 +656,7 @@ void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
           const int nc = counts[b];
           if (nc == 0) continue;
           // copy block b (n x nc, ld nc) into columns c0.. of Z (ld nev) scaled by d: reuse ts_update with identity? simple 2D copy + scale
-          CUDA_CHECK(cudaMemcpy2DAsync(s.Z.p + c0, sizeof(double) * nev, vecs[b].p, sizeof(double) * nc, sizeof(double) * nc, s.n, cudaMemcpyDeviceToDevice, st));
+          copy_cols(s.n, vecs[b].p, nc, s.Z.p + c0, nev, nc, st);
           c0 += nc;
         }
         rows_scale(s.n, nev, s.d.p, s.Z.p, st);  // Z = D V
@@ -588,6 +669,7 @@ void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
     // level 1: factor A_dir (or A_rob), src/geneo.cpp:126-148
     const double tl1 = now_s();
     if (!s.L1) s.L1.reset(new LdltFactor(s.plan));  // a re-factorization overwrites the resident factor in place
+    HostProfScope hp("lvl1 factorize");
     FactorStats fs = s.L1->factorize(opt.lvl1ORAS ? s.vRob.p : s.pat.val.p, pivTol, ws, st);
     s.negL1 = fs.neg;
     s.perturbed = fs.perturbed;
@@ -605,6 +687,7 @@ void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
 int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb,
                                  LdltWorkspace& ws, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs,
                                  std::vector<int>& counts) {
+  HostProfScope hpElp("eigen_local_problem");
   const int n = s.n;
   const int64_t nnz = s.pat.nnz;
   const double anorm = s.anorm;
@@ -617,6 +700,7 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     const double t0 = now_s();
     DevBuf<double> vS((size_t)nnz);
     vals_axpby(nnz, vA, param, vB, vS.p, st);  // A - param B, src/geneo.cpp:511-515
+    HostProfScope hp("syl factorize");
     FactorStats fs = tmp.factorize(vS.p, pivTol, ws, st);
     est = tauPb ? fs.neg : (n - fs.neg);  // #eigenvalues below tau / above gamma (Sylvester)
     if (est > n) est = n;
@@ -639,9 +723,11 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     const int guard = (!opt.noSyl && (opt.cut <= 0 || nev < opt.cut)) ? 2 : 0;
     EigOptions eo;
     eo.block = opt.epsBlock; eo.tol = opt.epsTol; eo.maxDim = opt.epsMaxDim; eo.invert = tauPb;
+    eo.ws = &eigWs;
     EigResult er;
     if (tauPb) {  // A x = lambda B x, smallest: T = A^-1 B
-      tmp.factorize(vA, pivTol, ws, st);
+      { HostProfScope hp("eig factorize"); tmp.factorize(vA, pivTol, ws, st); }
+      HostProfScope hp("eig block_lanczos");
       block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vB, std::min(nev + guard, n), eo, er, st);
     } else {      // A x = lambda B x, largest: T = B^-1 A, self-adjoint in the A inner product
       tmp.factorize(vB, pivTol, ws, st);
@@ -662,8 +748,7 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     got = (int)lam.size();
     if (got > 0) {
       X.alloc((size_t)n * got);
-      CUDA_CHECK(cudaMemcpy2DAsync(X.p, sizeof(double) * got, er.vecs.p, sizeof(double) * er.lambda.size(),
-                                   sizeof(double) * got, n, cudaMemcpyDeviceToDevice, st));
+      copy_cols(n, er.vecs.p, (int)er.lambda.size(), X.p, got, got, st);
       CUDA_CHECK(::geneo::sync_stream(st));
     }
     const double dt = now_s() - t0;

@@ -30,6 +30,7 @@ struct GeneoOptions {
   int ordering = 1;      // 1 METIS NodeND, 0 natural
   double epsTol = 1e-4;  // -els2_eps_tol (block Lanczos residual tolerance; reference default 1e-3, src/geneo.cpp:658)
   int epsBlock = 8;
+  bool releaseWorkspace = false;  // free the factorization / eigen-solver workspaces after every setup
   int epsMaxDim = 0;     // -els2_eps_ncv like bound on the Krylov dimension (0 = automatic)
   double pivRel = 1e-14; // static pivot threshold relative to max |a_ij| (stands for MUMPS CNTL(1/3), ICNTL(24))
   bool timing = false;   // synchronise and time every apply phase (reference timers hdr/geneo.hpp:115-123)
@@ -131,6 +132,9 @@ class GeneoPC {
   void build_coarse();
   void level1(const double* xin, double* yout, bool addQ);
   SolveForest forest;
+  // workspaces kept between (re-)setups: update arenas + transient factor, block-Lanczos buffers (-geneo_release_workspace frees them)
+  LdltWorkspace factorWs;
+  EigWorkspace eigWs;
   std::vector<char> connectivity;  // nbPart x nbPart: 1 when the intersection of two subdomains is EMPTY (src/geneo.cpp:1143-1145)
   std::vector<cudaEvent_t> ktEvents;  // kernelTiming: pairs
   size_t ktUsed = 0;

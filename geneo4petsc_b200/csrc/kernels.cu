@@ -524,6 +524,18 @@ void dense_gemv(int m, int n, const double* A, int lda, const double* x, double*
   k_dense_gemv<<<GENEO_TICK((m + 7) / 8), 256, 0, st>>>(m, n, A, lda, x, y);
   CUDA_CHECK(cudaGetLastError());
 }
+__global__ void k_copy_cols(int64_t n, const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int ncols) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * ncols; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / ncols;
+    const int j = (int)(t % ncols);
+    dst[r * ldd + j] = src[r * lds + j];
+  }
+}
+void copy_cols(int64_t n, const double* src, int lds, double* dst, int ldd, int ncols, cudaStream_t st) {
+  if (n * ncols == 0) return;
+  k_copy_cols<<<GENEO_TICK(grid_for(n * ncols, 256)), 256, 0, st>>>(n, src, lds, dst, ldd, ncols);
+  CUDA_CHECK(cudaGetLastError());
+}
 void vec_pointwise(int64_t n, const double* d, double* x, cudaStream_t st) { k_pointwise<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, d, x); }
 void rows_scale(int n, int ld, const double* d, double* Z, cudaStream_t st) {
   const int64_t tot = (int64_t)n * ld;

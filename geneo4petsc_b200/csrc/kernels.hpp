@@ -71,6 +71,8 @@ void ts_update(int n, const double* Q, int ldq, int p, const double* C, int ldc,
 void zt_x(int n, int nev, const double* Z, int ldz, const double* x, double* w, cudaStream_t st);
 void z_w_add(int n, int nev, const double* Z, int ldz, const double* w, const double* d, double* t, cudaStream_t st);
 void dense_gemv(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t st);  // y = A x (row-major A)
+// dst[r*ldd + j] = src[r*lds + j], j < ncols (row-major blocks; replaces pitched cudaMemcpy2D, which moves 8*ncols bytes per DMA row)
+void copy_cols(int64_t n, const double* src, int lds, double* dst, int ldd, int ncols, cudaStream_t st);
 void vec_pointwise(int64_t n, const double* d, double* x, cudaStream_t st);                   // x *= d
 void rows_scale(int n, int ld, const double* d, double* Z, cudaStream_t st);                  // Z[k*ld + c] *= d[k]
 // values of B = D A D on the pattern of A: out[nz] = d[row] * val[nz] * d[col] ; and out = a - tau*b

@@ -48,6 +48,14 @@ __device__ void gemm_tile_nt(const double* __restrict__ A, int lda, int M, const
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.;
 
+  if (mode == 1) {  // the C tile is read-modify-written at the very end: pull it into L2 now, behind the whole product
+    const int col = tid >> 1;
+    if (col < N) {
+      const double* cp = C + (size_t)col * ldc + (tid & 1) * 32;
+      if ((tid & 1) * 32 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp));
+      if ((tid & 1) * 32 + 16 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + 16));
+    }
+  }
   double ra[8], rb[8];
   const int nch = (K + KC - 1) / KC;
   auto gload = [&](int ch) {
@@ -126,7 +134,8 @@ __global__ void k_assemble(int64_t cnt, const int64_t* __restrict__ src, const i
     L[dst[t]] = vals[src[t]];
 }
 
-constexpr int EADD_COLS = 8;
+constexpr int EADD_COLS = 8;     // columns per item: 8 independent loads / updates in flight per thread
+constexpr int EADD_ROWS = 256;   // one row per thread
 __global__ void __launch_bounds__(256) k_extend_add(const WorkItem* __restrict__ items, const FrontDev* __restrict__ fr,
                                                     const int* __restrict__ relArr, double* __restrict__ L,
                                                     const double* __restrict__ Uchild, double* __restrict__ Upar) {
@@ -134,22 +143,28 @@ __global__ void __launch_bounds__(256) k_extend_add(const WorkItem* __restrict__
   const FrontDev F = fr[it.f];
   const FrontDev P = fr[F.parent];
   const int m = F.h - F.k, pk = P.k, ph = P.ld, pm = P.h - P.k;
-  const double* Uc = Uchild + F.uOff;
+  const int r = it.b * EADD_ROWS + threadIdx.x;
+  const int c0 = it.a * EADD_COLS;
+  if (r >= m || r < c0) return;  // lower triangle of the child's update matrix
+  const double* Uc = Uchild + F.uOff + r + (size_t)c0 * m;
   double* Up = Upar + P.uOff;
   double* Lp = L + P.lOff;
   const int* rel = F.relOff >= 0 ? relArr + F.relOff : nullptr;
   const bool atomic = P.nchild > 1;
-  const int c1 = min(m, (it.a + 1) * EADD_COLS);
-  for (int c = it.a * EADD_COLS; c < c1; c++) {
-    const int pc = rel ? rel[c] : c;
-    for (int r = c + threadIdx.x; r < m; r += blockDim.x) {
-      const int pr = rel ? rel[r] : r;
-      const double v = Uc[r + (size_t)c * m];
+  const int pr = rel ? rel[r] : r;
+  const int nc = min(EADD_COLS, min(m, r + 1) - c0);  // columns c0 .. min(r, m-1)
+  double v[EADD_COLS];
+#pragma unroll
+  for (int c = 0; c < EADD_COLS; c++)
+    if (c < nc) v[c] = __ldg(Uc + (size_t)c * m);
+#pragma unroll
+  for (int c = 0; c < EADD_COLS; c++)
+    if (c < nc) {
+      const int pc = rel ? rel[c0 + c] : c0 + c;
       double* dst = (pc < pk) ? (Lp + pr + (size_t)pc * ph) : (Up + (pr - pk) + (size_t)(pc - pk) * pm);
-      if (atomic) atomicAdd(dst, v);
-      else *dst += v;
+      if (atomic) atomicAdd(dst, v[c]);
+      else *dst += v[c];
     }
-  }
 }
 
 // One CTA (TD*TD threads) per front.  Thread (ti,tj) owns the strided E x E sub-block i = ti+TD*ii, j = tj+TD*jj of the
@@ -243,17 +258,25 @@ __global__ void __launch_bounds__(TD * TD) k_diag_invert(const WorkItem* __restr
   }
 }
 
-constexpr int COPY_ROWS = 1024;
+constexpr int COPY_ROWS = 256;   // one row per thread
+constexpr int COPY_COLS = 16;    // independent loads in flight per thread; a tall thin panel near the root still fills the chip
 __global__ void __launch_bounds__(256) k_copy_panel(const WorkItem* __restrict__ items, const FrontDev* __restrict__ fr,
                                                     const double* __restrict__ L, double* __restrict__ W) {
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const int m = F.h - F.k, k = F.k, h = F.ld;
-  const double* src = L + F.lOff + k;
-  double* dst = W + F.wOff;
-  const int r1 = min(m, (it.a + 1) * COPY_ROWS);
-  for (int c = 0; c < k; c++)
-    for (int r = it.a * COPY_ROWS + threadIdx.x; r < r1; r += blockDim.x) dst[r + (size_t)c * m] = src[r + (size_t)c * h];
+  const int r = it.a * COPY_ROWS + threadIdx.x;
+  if (r >= m) return;
+  const int c0 = it.b * COPY_COLS;
+  const double* src = L + F.lOff + k + r + (size_t)c0 * h;
+  double* dst = W + F.wOff + r + (size_t)c0 * m;
+  double v[COPY_COLS];
+#pragma unroll
+  for (int c = 0; c < COPY_COLS; c++)
+    if (c0 + c < k) v[c] = __ldg(src + (size_t)c * h);
+#pragma unroll
+  for (int c = 0; c < COPY_COLS; c++)
+    if (c0 + c < k) dst[(size_t)c * m] = v[c];
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS) k_panel(const WorkItem* __restrict__ items,
@@ -968,7 +991,8 @@ void LdltPlan::build_device() {
       const int cc = sym.levelPtr[l] - sym.levelPtr[l - 1];
       for (int t = 0; t < cc; t++) {
         const Front& C = sym.fronts[cf[t]];
-        for (int cb = 0; cb * EADD_COLS < C.m(); cb++) items.push_back(WorkItem{cf[t], cb, 0});
+        for (int cb = 0; cb * EADD_COLS < C.m(); cb++)
+          for (int rb = (cb * EADD_COLS) / EADD_ROWS; rb * EADD_ROWS < C.m(); rb++) items.push_back(WorkItem{cf[t], cb, rb});
       }
     }
     end(eaddItems[l]);
@@ -982,7 +1006,8 @@ void LdltPlan::build_device() {
     end(diagSmallItems[l]);
     begin(copyItems[l]);
     for (int t = 0; t < cnt; t++)
-      for (int rb = 0; rb * COPY_ROWS < sym.fronts[lf[t]].m(); rb++) items.push_back(WorkItem{lf[t], rb, 0});
+      for (int rb = 0; rb * COPY_ROWS < sym.fronts[lf[t]].m(); rb++)
+        for (int cb = 0; cb * COPY_COLS < sym.fronts[lf[t]].k; cb++) items.push_back(WorkItem{lf[t], rb, cb});
     end(copyItems[l]);
     begin(panelItems[l]);
     for (int t = 0; t < cnt; t++) {
@@ -1029,8 +1054,12 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   const Symbolic& S = P.sym;
   FactorStats stats;
   const double t0 = now_s();
-  ws.ensure(S);
-  if ((int64_t)L.n < S.lSize) L.alloc((size_t)S.lSize);  // a recycled (larger) buffer is fine
+  HostProfScope hp("factorize: host side total");
+  {
+    HostProfScope hpA("factorize: alloc");
+    ws.ensure(S);
+    if ((int64_t)L.n < S.lSize) L.alloc((size_t)S.lSize);  // a recycled (larger) buffer is fine
+  }
   CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)S.lSize * sizeof(double), st));
   ws.counters.zero(st);
   {
@@ -1077,6 +1106,35 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   nlev = 0;
   ntot = 0;
   for (int s = 0; s < ns; s++) { nlev = std::max(nlev, plans[s]->sym.nlevels); ntot = std::max<int64_t>(ntot, xoff[s] + plans[s]->sym.n); }
+  genericBuilt = ringBuilt[0] = ringBuilt[1] = false;
+  hSubs.assign(ns, ForestSub{nullptr, nullptr, nullptr, 0});
+  for (int s = 0; s < ns; s++) { hSubs[s].fronts = plans[s]->dFronts.p; hSubs[s].rowIdx = plans[s]->dRowIdx.p; hSubs[s].xoff = xoff[s]; }
+  dSubs.alloc(ns);
+  CUDA_CHECK(::geneo::sync_stream(0));
+  int dev = 0, nsm = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const void* fns[4] = {(const void*)k_solve_forest<1>, (const void*)k_solve_forest<2>, (const void*)k_solve_forest<4>, (const void*)k_solve_forest<8>};
+  for (int q = 0; q < 4; q++) {
+    int nb = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fns[q], SOLVE_THREADS, 0));
+    gridBlocks[q] = std::max(1, nb) * nsm;
+  }
+  {
+    int nb = 0;
+    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<1>::SMEM));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<1>, RingCfg<1>::WARPS * 32, RingCfg<1>::SMEM));
+    ringGrid[0] = std::max(1, nb) * nsm;
+    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<8>::SMEM));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<8>, RingCfg<8>::WARPS * 32, RingCfg<8>::SMEM));
+    ringGrid[1] = std::max(1, nb) * nsm;
+  }
+}
+
+void SolveForest::build_generic() const {
+  HostProfScope hp("forest build (generic)");
+  const int ns = (int)plans_.size();
+  const std::vector<const LdltPlan*>& plans = plans_;
   std::vector<ForestItem> items;
   std::vector<int64_t> ranges(4 * (size_t)nlev, 0);
   auto by_size = [](const ForestItem& a, const ForestItem& b) {  // big tiles first: the tail of a level is made of small ones
@@ -1119,28 +1177,8 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   }
   dItems.upload(items);
   dRanges.upload(ranges);
-  hSubs.assign(ns, ForestSub{nullptr, nullptr, nullptr, 0});
-  for (int s = 0; s < ns; s++) { hSubs[s].fronts = plans[s]->dFronts.p; hSubs[s].rowIdx = plans[s]->dRowIdx.p; hSubs[s].xoff = xoff[s]; }
-  dSubs.alloc(ns);
   CUDA_CHECK(::geneo::sync_stream(0));
-  int dev = 0, nsm = 0;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  const void* fns[4] = {(const void*)k_solve_forest<1>, (const void*)k_solve_forest<2>, (const void*)k_solve_forest<4>, (const void*)k_solve_forest<8>};
-  for (int q = 0; q < 4; q++) {
-    int nb = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fns[q], SOLVE_THREADS, 0));
-    gridBlocks[q] = std::max(1, nb) * nsm;
-  }
-  {
-    int nb = 0;
-    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<1>::SMEM));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<1>, RingCfg<1>::WARPS * 32, RingCfg<1>::SMEM));
-    ringGrid[0] = std::max(1, nb) * nsm;
-    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<8>::SMEM));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<8>, RingCfg<8>::WARPS * 32, RingCfg<8>::SMEM));
-    ringGrid[1] = std::max(1, nb) * nsm;
-  }
+  genericBuilt = true;
 }
 
 // Item lists of the ring kernel.  Per level the host picks the span of an item from the amount of work in the level: a
@@ -1148,6 +1186,7 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
 // items -- fewer records, x / y fetches and atomics per byte --, a level near the root gets the finest tiles so that every
 // warp of the chip has something to stream.
 void SolveForest::build_ring(int which) const {
+  HostProfScope hp("forest build (ring)");
   const int ns = (int)plans_.size();
   const int warps = which == 0 ? RingCfg<1>::WARPS : RingCfg<8>::WARPS;
   const int RING_BWD_COLS = which == 0 ? RingCfg<1>::BWD_COLS : RingCfg<8>::BWD_COLS;
@@ -1266,6 +1305,9 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
       CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<8>, dim3(ringGrid[1]), dim3(RingCfg<8>::WARPS * 32), a1, RingCfg<8>::SMEM, st));
     return;
   }
+  if (!genericBuilt) build_generic();
+  items = dItems.p;
+  ranges = dRanges.p;
   void* args[] = {(void*)&subs, (void*)&nsubs, (void*)&items, (void*)&ranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp, (void*)&ldx};
   const void* fn = nullptr;
   int q = 0;
@@ -1360,12 +1402,14 @@ double solve_stream_bench(int nf, int h, int k, int reps, double* gbps, int nlev
 
 void LdltFactor::solve_permuted(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const {
   GENEO_CHECK(L.p != nullptr, "solve before factorize");
-  if (!self_) {
-    self_.reset(new SolveForest());
-    self_->build({plan_.get()}, {0});
+  const LdltPlan& P = *plan_;
+  if (!P.selfForest) {
+    P.selfForest = std::make_shared<SolveForest>();
+    P.selfForest->build({plan_.get()}, {0});
+    P.selfL = nullptr;
   }
-  if (selfL_ != L.p) { self_->set_factors({L.p}, st); selfL_ = L.p; }
-  self_->solve(X, Y, ldx, j0, nr, st);
+  if (P.selfL != L.p) { P.selfForest->set_factors({L.p}, st); P.selfL = L.p; }
+  P.selfForest->solve(X, Y, ldx, j0, nr, st);
 }
 
 }  // namespace geneo

@@ -13,6 +13,7 @@ struct FrontDev {  // device copy of what the kernels need from symbolic.hpp:Fro
 };
 
 struct WorkItem { int f, a, b; };
+class SolveForest;
 
 // Pattern-level object: symbolic analysis + device work lists.  Shared by every numeric factorization that uses
 // the same sparsity pattern (A_dir, A_neu expanded to the A_dir pattern, A_neu - tau*B).
@@ -31,6 +32,10 @@ class LdltPlan {
   std::vector<int64_t> levelU;                                                 // doubles of update arena used per level
   DevBuf<int> dPerm;                                                           // new -> old
   size_t plan_bytes() const;
+  // single-factor solve forest (eigen-solver, coarse operator): a property of the PATTERN, built once and shared by
+  // every numeric factor of this plan (the transient factors of a re-setup reuse it: no item lists are rebuilt)
+  mutable std::shared_ptr<SolveForest> selfForest;
+  mutable const double* selfL = nullptr;
  private:
   void build_device();
  public:
@@ -59,12 +64,14 @@ class SolveForest {
   int64_t ntot = 0;
  private:
   void build_ring(int which) const;  // which = 0: NR = 1 item lists, 1: NR = 8 (built on first use)
+  void build_generic() const;        // item lists of the generic kernels (nr = 2, 4; built on first use)
   std::vector<const LdltPlan*> plans_;
   std::vector<int64_t> xoff_;
   std::vector<ForestSub> hSubs;
   DevBuf<ForestSub> dSubs;
-  DevBuf<ForestItem> dItems;
-  DevBuf<int64_t> dRanges;
+  mutable DevBuf<ForestItem> dItems;
+  mutable DevBuf<int64_t> dRanges;
+  mutable bool genericBuilt = false;
   // ring kernels (NR = 1 and NR = 8): their own item lists (spans chosen per level) and ranges, built on first use
   mutable DevBuf<RingItem> dRing[2];
   mutable DevBuf<int64_t> dRingRanges[2];
@@ -96,11 +103,9 @@ class LdltFactor {
   const LdltPlan& plan() const { return *plan_; }
   std::shared_ptr<LdltPlan> plan_ptr() const { return plan_; }
   DevBuf<double> L;
-  void release() { L.release(); selfL_ = nullptr; }
+  void release() { if (plan_->selfL == L.p) plan_->selfL = nullptr; L.release(); }
  private:
   std::shared_ptr<LdltPlan> plan_;
-  mutable std::unique_ptr<SolveForest> self_;  // single-factor forest (eigen-solver, coarse operator)
-  mutable const double* selfL_ = nullptr;
 };
 
 double solve_stream_bench(int nf, int h, int k, int reps, double* gbps, int nlev = 1, int nr = 1);  // ms per solve; synthetic one-level forest
