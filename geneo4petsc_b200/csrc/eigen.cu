@@ -113,15 +113,16 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
   bool prefetched = false;  // the solve of this step was already queued behind the previous step's device work
   int nextRR = 0, prevRRstep = -1;
   double prevWorst = 0.;
-  auto launch_solve = [&](int jj) {  // W = F^-1 (B Q_jj)
+  auto launch_solve = [&](int col0) {  // W = F^-1 (B Q[:, col0 : col0+b])
     HostProfScope hp("lanczos: launch_solve");
-    k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)jj * b, maxDim, Xs.p, bp, b, bp);
+    k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)col0, maxDim, Xs.p, bp, b, bp);
     for (int j0 = 0; j0 < bp; j0 += 8) F.solve_permuted(Xs.p, w, bp, j0, 8, st);
   };
+  dim = b;           // basis columns, the newest block included
+  int restarts = 0;
   while (!done) {
-    const int j = steps;
-    dim = (j + 1) * b;
-    if (!prefetched) launch_solve(j);
+    const int c0 = dim - b;  // the newest block: columns c0 .. dim-1
+    if (!prefetched) launch_solve(c0);
     prefetched = false;
     // two passes of block classical Gram-Schmidt against Q[:, 0:dim] in the B inner product
     hC1.assign((size_t)dim * b, 0.);
@@ -135,7 +136,7 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
       for (size_t t = 0; t < hC1.size(); t++) hC1[t] += hC2[t];
     }
     for (int i = 0; i < dim; i++)
-      for (int c = 0; c < b; c++) Hm[(size_t)i * maxDim + j * b + c] = hC1[(size_t)i * b + c];
+      for (int c = 0; c < b; c++) Hm[(size_t)i * maxDim + c0 + c] = hC1[(size_t)i * b + c];
     const bool room = (dim + b <= maxDim);
     // ---- next block: rank-revealing B-orthonormalisation of W (SVQB + random completion + CholQR) -----------------------
     // As Ritz pairs converge the residual block W loses numerical rank; plain CholQR would break down.  Directions
@@ -210,14 +211,14 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     if (breakdown) std::fill(hR.begin(), hR.end(), 0.);
     if (room)  // T Q_j = Q_{0..j} C_j + Q_{j+1} R : the sub-diagonal block of the projected matrix
       for (int r = 0; r < b; r++)
-        for (int c = 0; c < b; c++) Hm[(size_t)(dim + r) * maxDim + j * b + c] = hR[(size_t)r * b + c];
+        for (int c = 0; c < b; c++) Hm[(size_t)(dim + r) * maxDim + c0 + c] = hR[(size_t)r * b + c];
     // The next block is known: queue its copy into the basis and its solve NOW, so that the device streams the factor
     // while the host does the Rayleigh-Ritz below (if that says "converged" the extra solve is simply dropped).
     const bool canContinue = !breakdown && room && dim + b <= n;
     if (canContinue) {
-      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, w, bp, Q.p + (size_t)(j + 1) * b, maxDim, b, b);
-      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)(j + 1) * b, maxDim, b, b);
-      launch_solve(j + 1);
+      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, w, bp, Q.p + (size_t)dim, maxDim, b, b);
+      k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)dim, maxDim, b, b);
+      launch_solve(dim);
       prefetched = true;
     }
     // Rayleigh-Ritz on the symmetrised leading dim x dim block (skipped while the basis is too small for nev pairs to
@@ -268,7 +269,47 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
     }
     steps++;
     res.nconv = nconv;
-    if ((nconv == want && want == nev) || breakdown || !room || dim + b > n) done = true;
+    if ((nconv == want && want == nev) || breakdown || dim + b > n) done = true;
+    else if (!room) {
+      // ---- thick restart (block Krylov-Schur): the basis is full and wanted pairs are still missing.  Keep the leading
+      //      Ritz vectors X = Q Y_k (they span the converged and the nearly converged directions) plus the block that was
+      //      about to be appended; in the new basis the projected matrix is diag(theta_k) bordered by S = R Y_k[last b rows].
+      const int keep = std::min(dim - b, std::max(nev + b, (maxDim - b) / 2));
+      if (restarts >= 40 || keep + 2 * b > maxDim) done = true;
+      else {
+        restarts++;
+        Ysel.assign((size_t)dim * keep, 0.);
+        for (int q = 0; q < keep; q++)
+          for (int i = 0; i < dim; i++) Ysel[(size_t)i * keep + q] = T[(size_t)i * dim + (dim - 1 - q)];
+        need(E.dC, (size_t)maxDim * std::max(std::max(bp, nev), keep));
+        need(E.Tmp, (size_t)n * keep);
+        CUDA_CHECK(cudaMemcpyAsync(dC.p, Ysel.data(), sizeof(double) * Ysel.size(), cudaMemcpyHostToDevice, st));
+        for (int which = 0; which < 2; which++) {  // Q <- Q Y_k, B Q <- B Q Y_k
+          DevBuf<double>& src = which == 0 ? Q : BQ;
+          CUDA_CHECK(cudaMemsetAsync(E.Tmp.p, 0, sizeof(double) * (size_t)n * keep, st));
+          ts_update(n, src.p, maxDim, dim, dC.p, keep, keep, E.Tmp.p, keep, 1., 0., st);
+          k_copy_block<<<GENEO_TICK(gridn((int64_t)n * keep)), 256, 0, st>>>(n, E.Tmp.p, keep, src.p, maxDim, keep, keep);
+        }
+        // the pending block (already B-orthonormal to everything) becomes columns keep .. keep+b-1
+        k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, w, bp, Q.p + (size_t)keep, maxDim, b, b);
+        k_copy_block<<<GENEO_TICK(gridn((int64_t)n * b)), 256, 0, st>>>(n, bw, bp, BQ.p + (size_t)keep, maxDim, b, b);
+        CUDA_CHECK(::geneo::sync_stream(st));
+        std::vector<double> Snew((size_t)b * keep, 0.);
+        for (int r = 0; r < b; r++)
+          for (int q = 0; q < keep; q++) {
+            double sv = 0.;
+            for (int c = 0; c < b; c++) sv += hR[(size_t)r * b + c] * T[(size_t)(dim - b + c) * dim + (dim - 1 - q)];
+            Snew[(size_t)r * keep + q] = sv;
+          }
+        std::fill(Hm.begin(), Hm.end(), 0.);
+        for (int q = 0; q < keep; q++) Hm[(size_t)q * maxDim + q] = theta[dim - 1 - q];
+        for (int r = 0; r < b; r++)
+          for (int q = 0; q < keep; q++) Hm[(size_t)(keep + r) * maxDim + q] = Hm[(size_t)q * maxDim + keep + r] = Snew[(size_t)r * keep + q];
+        dim = keep;  // + b below
+        nextRR = 0; prevRRstep = -1; prevWorst = 0.;
+      }
+    }
+    if (!done) dim += b;
     if (done) {
       // Ritz vectors X = Q[:, 0:dim] Y
       const int got = want;

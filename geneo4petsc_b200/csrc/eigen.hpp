@@ -17,8 +17,8 @@ namespace geneo {
 // Device buffers of the block Lanczos iteration (basis Q, B Q, work blocks).  Grow-only: one instance serves every
 // subdomain of every (re-)setup, so no multi-GB cudaMalloc / cudaFree sits between two eigen-solves.
 struct EigWorkspace {
-  DevBuf<double> Q, BQ, W, W2, BW, BW2, Xs, dC;
-  void release() { Q.release(); BQ.release(); W.release(); W2.release(); BW.release(); BW2.release(); Xs.release(); dC.release(); }
+  DevBuf<double> Q, BQ, W, W2, BW, BW2, Xs, dC, Tmp;
+  void release() { Tmp.release(); Q.release(); BQ.release(); W.release(); W2.release(); BW.release(); BW2.release(); Xs.release(); dC.release(); }
 };
 
 struct EigOptions {

@@ -165,3 +165,35 @@ def test_predecomposed_input_gives_the_same_preconditioner(lap3d):
     x = np.random.default_rng(5).standard_normal(mesh.nb_node)
     y = [g.GeneoPC(["-geneo_lvl", "ASM,1", "-geneo_tau", "0.3", "-els2_eps_tol", "1e-10"]).setup(pr).apply(x) for pr in (p, q)]
     assert np.linalg.norm(y[0] - y[1]) <= 1e-8 * np.linalg.norm(y[0])
+
+
+def test_thick_restart_reaches_the_same_eigenpairs():
+    """A Krylov basis far too small for the wanted pairs (-els2_eps_ncv) forces several thick restarts (block
+    Krylov-Schur); counts and eigenvalues must not change (oracle: dense eigh of the pencil, src/geneo.cpp:626-744)."""
+    mesh, nparts = go.gen_grid(3, 16, 1e-4, 2.0, "lin"), 2
+    p = _problem(mesh, nparts)
+    base = ["-geneo_lvl", "ASM,1", "-geneo_tau", "0.45", "-els2_eps_tol", "1e-9"]
+    pc_ref = g.GeneoPC(base).setup(p)
+    pc_small = g.GeneoPC(base + ["-els2_eps_ncv", "80"]).setup(p)  # 36 + 2 guard pairs wanted from an 80-column basis
+    rep = _oracle(mesh, p, nparts, go.GenEOOptions(lvl1="ASM", lvl2="1", tau=0.45), ksp="cg", rtol=1e-6)
+    for s in range(nparts):
+        a, bb = pc_ref.sub_info(s), pc_small.sub_info(s)
+        assert a["nev"] == bb["nev"] == rep.pc.sub[s].z.shape[1] and a["nev"] >= 20, (a, bb)
+        assert bb["eigDim"] <= 80 and bb["eigSteps"] > a["eigSteps"]  # the small basis really restarted
+        ref = np.sort(np.array(rep.pc.sub[s].eigvals))
+        np.testing.assert_allclose(np.sort(pc_small.sub_eigenvalues(s)), ref, rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(np.sort(pc_ref.sub_eigenvalues(s)), ref, rtol=1e-6, atol=1e-12)
+    x = np.random.default_rng(1).standard_normal(mesh.nb_node)
+    y, yo = pc_small.apply(x), rep.pc.apply(x)
+    assert np.linalg.norm(y - yo) <= 1e-7 * np.linalg.norm(yo)
+
+
+def test_level_profile_covers_the_whole_factor():
+    """geneo_pc_level_profile: one timestamped PC-apply solve; the per-phase bytes add up to the factor read twice."""
+    mesh = go.gen_grid(3, 14, 1e-4, 2.0, "lin")
+    p = _problem(mesh, 4)
+    pc = g.GeneoPC(["-geneo_lvl", "ASM,0"]).setup(p)
+    us, by, it = pc.level_profile()
+    assert len(us) == len(by) == len(it) and len(us) % 2 == 0 and (us >= 0).all() and it.sum() > 0
+    st = pc.stats()
+    assert by.sum() <= st["trisolve_bytes"] and by.sum() >= 0.8 * st["trisolve_bytes"]  # (the rest: row indices, vectors)
