@@ -269,6 +269,12 @@ def run_b200(a):
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     ach = st["trisolve_bytes"] / (kms / max(1, klaunch)) / 1e6 if klaunch else 0.0
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of THIS workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tr.get(workload_config(a, 1)["workload"])
+    except (OSError, ValueError):
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -277,10 +283,10 @@ def run_b200(a):
         "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "seconds": e2e_s,
                 "symbolic_s": tm2["symbolic"], "upload_s": tm2["upload"], "numeric_s": tm2["numeric"]},
         "gpu_launches": c1["launches"] - c0["launches"],
-        "roofline": {"kernel": "k_solve_forest<1> (level-1 triangular sweeps of all subdomains, one launch per PC apply)",
+        "roofline": {"kernel": "k_solve_ring<1> (level-1 triangular sweeps of all subdomains, one launch per PC apply)",
                      "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650",
-                     "traffic": None, "algorithmic_bytes_per_launch": st["trisolve_bytes"], "launches_timed": klaunch,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": st["trisolve_bytes"], "launches_timed": klaunch,
                      "avg_launch_ms": kms / max(1, klaunch)},
         "detail": {"n_dof": n, "iterations": r["its"], "reason": r["reason_name"], "rnorm": r["rnorm"], "max_rel_err_vs_1..N": err,
                    "setup_numeric_s": setup_s / a.steps, "iter_s": iter_s / a.steps, "dimE": pc.info()["nE"],

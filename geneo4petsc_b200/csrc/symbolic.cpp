@@ -1,6 +1,8 @@
 // symbolic.cpp -- see symbolic.hpp.  Host only.
 #include "symbolic.hpp"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -18,6 +20,42 @@ extern "C" int METIS_NodeND(midx_t* nvtxs, midx_t* xadj, midx_t* adjncy, midx_t*
 
 extern "C" int METIS_ComputeVertexSeparator(midx_t* nvtxs, midx_t* xadj, midx_t* adjncy, midx_t* vwgt, midx_t* options,
                                            midx_t* sepsize, midx_t* part);
+
+// ---------------------------------------------------------------------------------------------------------------------
+// METIS draws its random permutations from rand(): glibc serialises rand() behind one process-wide lock, so nested
+// dissections of different subdomains running on different threads spend most of their time in futex calls (measured:
+// 8 concurrent orderings of 10^6-vertex graphs take as long as 8 serial ones, 64 % system time) -- and they perturb each
+// other's random streams.  Inside the nested-dissection calls of THIS library rand()/srand() resolve (hidden visibility,
+// bound at link time, nothing exported) to a thread-local generator; everywhere else -- in particular in the k-way mesh
+// partition whose result is pinned by the reference's goldens -- they forward to the C library.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+thread_local bool t_nd_rng = false;
+thread_local uint64_t t_nd_state = 0x9E3779B97F4A7C15ull;
+struct NdRngScope {
+  bool old;
+  NdRngScope() : old(t_nd_rng) { t_nd_rng = true; }
+  ~NdRngScope() { t_nd_rng = old; }
+};
+}  // namespace
+extern "C" __attribute__((visibility("hidden"))) int rand(void) {
+  if (!t_nd_rng) {
+    static int (*real)(void) = reinterpret_cast<int (*)(void)>(dlsym(RTLD_DEFAULT, "rand"));
+    return real();
+  }
+  uint64_t x = t_nd_state;  // xorshift64*
+  x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+  t_nd_state = x;
+  return (int)((x * 2685821657736338717ull) >> 33);  // 31 bits, like RAND_MAX = 2^31 - 1
+}
+extern "C" __attribute__((visibility("hidden"))) void srand(unsigned seed) {
+  if (!t_nd_rng) {
+    static void (*real)(unsigned) = reinterpret_cast<void (*)(unsigned)>(dlsym(RTLD_DEFAULT, "srand"));
+    real(seed);
+    return;
+  }
+  t_nd_state = ((uint64_t)seed + 1) * 0x9E3779B97F4A7C15ull;
+}
 
 namespace {
 
@@ -42,6 +80,7 @@ void metis_opts(midx_t* options) {
 // Nested dissection with the top `depth` levels done here so that the two halves can be ordered concurrently
 // (METIS_NodeND is serial; its own recursion does exactly this: separator last, halves recursively).  order: new -> old.
 void nd_recursive(NdGraph& g, int depth, std::vector<int>& order) {
+  NdRngScope rngScope;
   const int n = g.n();
   midx_t options[40];
   metis_opts(options);

@@ -247,7 +247,7 @@ def run_bench(a, rank, world, local, METRIC, UNIT, config, ClockSampler):
             "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "seconds": e2e_s,
                     "symbolic_s": tm2["symbolic"], "upload_s": tm2["upload"], "numeric_s": tm2["numeric"]},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_solve_forest<1> (rank 0)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_solve_ring<1> (rank 0)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": st["trisolve_bytes"],
                          "launches_timed": klaunch, "avg_launch_ms": kavg,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
