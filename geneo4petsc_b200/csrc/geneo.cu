@@ -393,7 +393,10 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     comm.allreduce_sum_host(c.data(), (int)c.size(), st);
     for (size_t t = 0; t < c.size(); t++) connectivity[t] = c[t] > 0.5 ? 1 : 0;
   }
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  // host threads of THIS process: all cores, divided by the ranks sharing the node (torchrun exports LOCAL_WORLD_SIZE)
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  if (const char* e = getenv("GENEO_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  else if (const char* e2 = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1u, hw / (unsigned)std::max(1, atoi(e2)));
   const int inFlight = std::max(1, std::min(P, hw >= 8 ? 2 : 1));  // subdomains analysed concurrently
   int ndDepth = 0;
   while ((unsigned)(inFlight << (ndDepth + 1)) <= hw && ndDepth < 4) ndDepth++;

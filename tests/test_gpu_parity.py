@@ -197,3 +197,31 @@ def test_level_profile_covers_the_whole_factor():
     assert len(us) == len(by) == len(it) and len(us) % 2 == 0 and (us >= 0).all() and it.sum() > 0
     st = pc.stats()
     assert by.sum() <= st["trisolve_bytes"] and by.sum() >= 0.8 * st["trisolve_bytes"]  # (the rest: row indices, vectors)
+
+
+@pytest.mark.parametrize("lvl,ksp", [("ASM,1", "gmres"), ("SORAS,2", "gmres"), ("ASM,1", "cg")])
+def test_graph_laplacian_matches_oracle(lvl, ksp):
+    """BASELINE configs[3]: the irregular graph Laplacian of tst/graph (the reference's OWN generator, compiled into
+    oracle/_ref by oracle/Makefile; arguments of tst/graph/graphRun.sh:144), METIS partition, GenEO + GMRES / CG."""
+    try:
+        mesh = go.ref_generator("graph", "--size 400 --level 3 --noGround --inpEps 0.0001")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libgengraph.so not built (needs /root/reference at build time)")
+    nparts = 4
+    p = _problem(mesh, nparts)
+    l1, l2 = lvl.split(",")
+    argv = ["-geneo_lvl", lvl, "-geneo_tau", "0.1"]
+    if l2 == "2":
+        argv += ["-geneo_optim", "0.02", "-els2_eps_tol", "1e-8"]
+    pc = g.GeneoPC(argv).setup(p)
+    rep = _oracle(mesh, p, nparts, go.GenEOOptions(lvl1=l1, lvl2=l2, tau=0.1, optim=0.02 if l2 == "2" else 0.0), ksp=ksp, rtol=1e-6, atol=1e-6)
+    x = np.random.default_rng(5).standard_normal(mesh.nb_node)
+    np.testing.assert_allclose(pc.mult(x), rep.a @ x, rtol=1e-12, atol=1e-12)
+    assert pc.info()["nE"] == rep.pc.e.shape[0]
+    for s in range(nparts):
+        si = pc.sub_info(s)
+        assert si["nev"] == rep.pc.sub[s].z.shape[1] and si["estim"] == rep.pc.sub[s].estim
+        np.testing.assert_allclose(np.sort(pc.sub_eigenvalues(s)), np.sort(np.array(rep.pc.sub[s].eigvals)), rtol=1e-6, atol=1e-12)
+    r = pc.ksp_solve(pc.make_rhs(), ksp=ksp, rtol=1e-6, atol=1e-6)
+    assert r["reason"] > 0 and abs(r["its"] - rep.ksp.its) <= 1, (r["its"], rep.ksp.its)
+    assert np.linalg.norm(r["x"] - rep.ksp.x) <= 1e-4 * np.linalg.norm(rep.ksp.x)
