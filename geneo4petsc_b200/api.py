@@ -326,13 +326,13 @@ class Symbolic:
         self.h = C.c_void_p()
         _chk(lib.geneo_symbolic_create(C.c_int(self.n), _p(ptr, _i64p), _p(idx, _i32p), C.c_int(nb), C.c_int(ordering),
                                        C.c_int(1 if amalgamate else 0), C.byref(self.h)))
-        i, r = np.zeros(10, dtype=np.int64), np.zeros(1)
+        i, r = np.zeros(11, dtype=np.int64), np.zeros(1)
         _chk(lib.geneo_symbolic_info(self.h, _p(i, _i64p), _p(r, _f64p)))
-        keys = ["n", "nfronts", "nlevels", "lSize", "uArena", "wArena", "nRowIdx", "nRel", "nAsm", "nsuper"]
+        keys = ["n", "nfronts", "nlevels", "lSize", "uArena", "wArena", "nRowIdx", "nRel", "nAsm", "nsuper", "cArena"]
         self.info = {k: int(v) for k, v in zip(keys, i)}
         self.info["flops"] = float(r[0])
         self.perm = np.zeros(self.n, dtype=np.int32)
-        self.fronts = np.zeros((self.info["nfronts"], 13), dtype=np.int64)
+        self.fronts = np.zeros((self.info["nfronts"], 16), dtype=np.int64)
         self.row_idx = np.zeros(self.info["nRowIdx"], dtype=np.int32)
         self.rel = np.zeros(max(1, self.info["nRel"]), dtype=np.int32)
         self.asm_src = np.zeros(self.info["nAsm"], dtype=np.int64)

@@ -561,13 +561,13 @@ int geneo_symbolic_create(int n, const int64_t* ptr, const int32_t* idx, int nb,
   ABI_CATCH
 }
 int geneo_symbolic_destroy(geneo_symbolic_t s) { ABI_TRY delete s; ABI_CATCH }
-int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[10], double reals[1]) {
+int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[11], double reals[1]) {
   ABI_TRY
   ABI_REQ(s, "null argument");
   const Symbolic& S = s->s;
-  const int64_t v[10] = {S.n, (int64_t)S.fronts.size(), S.nlevels, S.lSize, S.uArena, S.wArena, (int64_t)S.rowIdx.size(),
-                         (int64_t)S.rel.size(), (int64_t)S.asmSrc.size(), S.nsuper};
-  for (int i = 0; i < 10; i++) ints[i] = v[i];
+  const int64_t v[11] = {S.n, (int64_t)S.fronts.size(), S.nlevels, S.lSize, S.uArena, S.wArena, (int64_t)S.rowIdx.size(),
+                         (int64_t)S.rel.size(), (int64_t)S.asmSrc.size(), S.nsuper, S.cArena};
+  for (int i = 0; i < 11; i++) ints[i] = v[i];
   if (reals) reals[0] = S.flops;
   ABI_CATCH
 }
@@ -580,8 +580,9 @@ int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32
   if (fronts)
     for (size_t f = 0; f < S.fronts.size(); f++) {
       const Front& F = S.fronts[f];
-      const int64_t v[13] = {F.col0, F.k, F.h, F.parent, F.level, F.chain, F.nchild, F.rowOff, F.lOff, F.uOff, F.wOff, F.relOff, F.ld};
-      std::copy(v, v + 13, fronts + 13 * f);
+      const int64_t v[16] = {F.col0, F.k, F.h, F.parent, F.level, F.chain, F.nchild, F.rowOff, F.lOff, F.uOff, F.wOff, F.relOff, F.ld,
+                             F.uLd, F.uArena, F.inplace};
+      std::copy(v, v + 16, fronts + 16 * f);
     }
   if (rowIdx) std::copy(S.rowIdx.begin(), S.rowIdx.end(), rowIdx);
   if (rel) std::copy(S.rel.begin(), S.rel.end(), rel);

@@ -137,31 +137,33 @@ __global__ void k_assemble(int64_t cnt, const int64_t* __restrict__ src, const i
 constexpr int EADD_COLS = 8;     // columns per item: 8 independent loads / updates in flight per thread
 constexpr int EADD_ROWS = 256;   // one row per thread
 __global__ void __launch_bounds__(256) k_extend_add(const WorkItem* __restrict__ items, const FrontDev* __restrict__ fr,
-                                                    const int* __restrict__ relArr, double* __restrict__ L,
-                                                    const double* __restrict__ Uchild, double* __restrict__ Upar) {
+                                                    const int* __restrict__ relArr, double* __restrict__ L, UArenas ua) {
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const FrontDev P = fr[F.parent];
-  const int m = F.h - F.k, pk = P.k, ph = P.ld, pm = P.h - P.k;
+  const int m = F.h - F.k, pk = P.k, ph = P.ld;
   const int r = it.b * EADD_ROWS + threadIdx.x;
   const int c0 = it.a * EADD_COLS;
   if (r >= m || r < c0) return;  // lower triangle of the child's update matrix
-  const double* Uc = Uchild + F.uOff + r + (size_t)c0 * m;
-  double* Up = Upar + P.uOff;
+  const int cld = F.uLd, pld = P.uLd;
+  const double* Uc = ua.a[F.uArena] + F.uOff + r + (size_t)c0 * cld;
+  double* Up = ua.a[P.uArena] + P.uOff;
   double* Lp = L + P.lOff;
   const int* rel = F.relOff >= 0 ? relArr + F.relOff : nullptr;
   const bool atomic = P.nchild > 1;
+  const bool panelOnly = P.inplace != 0;  // the parent's update matrix IS the trailing block of this one: nothing to move
   const int pr = rel ? rel[r] : r;
   const int nc = min(EADD_COLS, min(m, r + 1) - c0);  // columns c0 .. min(r, m-1)
   double v[EADD_COLS];
 #pragma unroll
   for (int c = 0; c < EADD_COLS; c++)
-    if (c < nc) v[c] = __ldg(Uc + (size_t)c * m);
+    if (c < nc) v[c] = __ldg(Uc + (size_t)c * cld);
 #pragma unroll
   for (int c = 0; c < EADD_COLS; c++)
     if (c < nc) {
       const int pc = rel ? rel[c0 + c] : c0 + c;
-      double* dst = (pc < pk) ? (Lp + pr + (size_t)pc * ph) : (Up + (pr - pk) + (size_t)(pc - pk) * pm);
+      if (pc >= pk && panelOnly) continue;
+      double* dst = (pc < pk) ? (Lp + pr + (size_t)pc * ph) : (Up + (pr - pk) + (size_t)(pc - pk) * pld);
       if (atomic) atomicAdd(dst, v[c]);
       else *dst += v[c];
     }
@@ -294,14 +296,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_panel(const WorkItem* __restri
 
 __global__ void __launch_bounds__(GEMM_THREADS) k_schur(const WorkItem* __restrict__ items,
                                                         const FrontDev* __restrict__ fr, const double* __restrict__ L,
-                                                        const double* __restrict__ W, double* __restrict__ U) {
+                                                        const double* __restrict__ W, UArenas ua) {
   __shared__ double sA[2 * KC * SLD], sB[2 * KC * SLD];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const int m = F.h - F.k, k = F.k, h = F.ld;
   // U[ti, tj] -= L21[ti rows, :] * W[tj rows, :]^T   (lower triangle of tiles only)
   gemm_tile_nt(L + F.lOff + k + it.a * TS, h, min(TS, m - it.a * TS), W + F.wOff + it.b * TS, m,
-               min(TS, m - it.b * TS), k, U + F.uOff + it.a * TS + (size_t)it.b * TS * m, m, 1, sA, sB);
+               min(TS, m - it.b * TS), k, ua.a[F.uArena] + F.uOff + it.a * TS + (size_t)it.b * TS * F.uLd, F.uLd, 1, sA, sB);
 }
 
 // =====================================================================================================================
@@ -968,7 +970,7 @@ void LdltPlan::build_device() {
   std::vector<FrontDev> fd(nf);
   for (int f = 0; f < nf; f++) {
     const Front& F = sym.fronts[f];
-    fd[f] = FrontDev{F.lOff, F.uOff, F.wOff, F.rowOff, F.relOff, F.k, F.h, F.ld, F.parent, F.nchild};
+    fd[f] = FrontDev{F.lOff, F.uOff, F.wOff, F.rowOff, F.relOff, F.k, F.h, F.ld, F.parent, F.nchild, F.uLd, F.uArena, F.inplace, 0};
   }
   std::vector<WorkItem> items;
   auto begin = [&](Range& r) { r.off = (int64_t)items.size(); };
@@ -976,13 +978,17 @@ void LdltPlan::build_device() {
   const int nl = sym.nlevels;
   eaddItems.resize(nl); diagItems.resize(nl); diagSmallItems.resize(nl); copyItems.resize(nl); panelItems.resize(nl); schurItems.resize(nl);
   levelU.assign(nl, 0);
+  levelChainZero.assign(nl, {});
   for (int l = 0; l < nl; l++) {
     const int* lf = &sym.levelFronts[sym.levelPtr[l]];
     const int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
     for (int t = 0; t < cnt; t++) {
       const Front& F = sym.fronts[lf[t]];
       const int64_t m = F.m();
-      if (m > 0) levelU[l] = std::max(levelU[l], F.uOff + m * m);
+      if (m > 0 && !F.inplace) {
+        if (F.uArena == 2) levelChainZero[l].emplace_back(F.uOff, m * m);
+        else levelU[l] = std::max(levelU[l], F.uOff + m * m);
+      }
     }
     // extend-add: children are the fronts of level l-1 (their parents are all at level l)
     begin(eaddItems[l]);
@@ -991,7 +997,9 @@ void LdltPlan::build_device() {
       const int cc = sym.levelPtr[l] - sym.levelPtr[l - 1];
       for (int t = 0; t < cc; t++) {
         const Front& C = sym.fronts[cf[t]];
-        for (int cb = 0; cb * EADD_COLS < C.m(); cb++)
+        // a chain link only adds its first k_parent columns to the parent's panel (the rest stays in place)
+        const int ncols = (C.parent >= 0 && sym.fronts[C.parent].inplace) ? std::min(C.m(), sym.fronts[C.parent].k) : C.m();
+        for (int cb = 0; cb * EADD_COLS < ncols; cb++)
           for (int rb = (cb * EADD_COLS) / EADD_ROWS; rb * EADD_ROWS < C.m(); rb++) items.push_back(WorkItem{cf[t], cb, rb});
       }
     }
@@ -1045,6 +1053,7 @@ size_t LdltPlan::plan_bytes() const {
 
 void LdltWorkspace::ensure(const Symbolic& s) {
   if ((int64_t)u0.n < s.uArena) { u0.alloc((size_t)s.uArena); u1.alloc((size_t)s.uArena); }
+  if ((int64_t)uc.n < s.cArena) uc.alloc((size_t)s.cArena);
   if ((int64_t)w.n < s.wArena) w.alloc((size_t)s.wArena);
   if (counters.n < 2) counters.alloc(2);
 }
@@ -1069,12 +1078,13 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
     CUDA_CHECK(cudaGetLastError());
   }
   const WorkItem* items = P.dItems.p;
+  const UArenas ua{{ws.u0.p, ws.u1.p, ws.uc.p}};
   for (int l = 0; l < S.nlevels; l++) {
     double* Ucur = (l & 1) ? ws.u1.p : ws.u0.p;
-    double* Uprev = (l & 1) ? ws.u0.p : ws.u1.p;
     if (P.levelU[l] > 0) CUDA_CHECK(cudaMemsetAsync(Ucur, 0, (size_t)P.levelU[l] * sizeof(double), st));
+    for (auto& z : P.levelChainZero[l]) CUDA_CHECK(cudaMemsetAsync(ws.uc.p + z.first, 0, (size_t)z.second * sizeof(double), st));
     if (P.eaddItems[l].cnt)
-      k_extend_add<<<GENEO_TICK(P.eaddItems[l].cnt), 256, 0, st>>>(items + P.eaddItems[l].off, P.dFronts.p, P.dRel.p, L.p, Uprev, Ucur);
+      k_extend_add<<<GENEO_TICK(P.eaddItems[l].cnt), 256, 0, st>>>(items + P.eaddItems[l].off, P.dFronts.p, P.dRel.p, L.p, ua);
     if (P.diagItems[l].cnt)
       k_diag_invert<128, 16><<<GENEO_TICK(P.diagItems[l].cnt), 256, 0, st>>>(items + P.diagItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
     if (P.diagSmallItems[l].cnt)
@@ -1084,7 +1094,7 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
     if (P.panelItems[l].cnt)
       k_panel<<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, 0, st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
     if (P.schurItems[l].cnt)
-      k_schur<<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, 0, st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, Ucur);
+      k_schur<<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, 0, st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, ua);
     CUDA_CHECK(cudaGetLastError());
   }
   int h[2] = {0, 0};

@@ -431,14 +431,49 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
     S.maxH = std::max(S.maxH, F.h);
   }
   S.lSize = lOff;
+  // Update matrices.  91 % of the update volume of a 3-D problem sits in supernode CHAINS (panel p+1 of a supernode is the
+  // only parent of panel p, identity relative indices): there the parent's update matrix is the trailing block of the
+  // child's, so it stays where it is (in the chain arena, for the life of the chain) -- no extend-add, no memset, one
+  // read-modify-write per panel instead of four passes.  Everything else ping-pongs between two arenas by level parity.
+  struct Live { int64_t off, size; int lEnd; };
+  std::vector<Live> live;
   for (int l = 0; l < S.nlevels; l++) {
     int64_t u = 0, w = 0;
+    live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& b) { return b.lEnd < l; }), live.end());
     for (int t = S.levelPtr[l]; t < S.levelPtr[l + 1]; t++) {
-      Front& F = S.fronts[S.levelFronts[t]];
+      const int f = S.levelFronts[t];
+      Front& F = S.fronts[f];
       const int64_t m = F.m();
-      if (m > 0) { F.uOff = u; u += m * m; F.wOff = w; w += m * F.k; }
-      u = (u + 15) & ~(int64_t)15;  // 128-byte alignment of every update matrix / scratch panel
-      w = (w + 15) & ~(int64_t)15;
+      if (m > 0) {
+        F.wOff = w; w += m * F.k;
+        w = (w + 15) & ~(int64_t)15;  // 128-byte alignment of every scratch panel / fresh update matrix
+        const bool inplace = opt.chainInplace && f > 0 && S.fronts[f - 1].chain && S.fronts[f - 1].parent == f;
+        if (inplace) {
+          const Front& C = S.fronts[f - 1];
+          F.inplace = 1;
+          F.uArena = C.uArena;
+          F.uLd = C.uLd;
+          F.uOff = C.uOff + (int64_t)F.k * ((int64_t)C.uLd + 1);
+        } else if (opt.chainInplace && F.chain) {  // first panel of a chain: lives until the tree parent of the last panel
+          int last = f;
+          while (S.fronts[last].chain) last++;
+          const int lEnd = S.fronts[last].level + 1;
+          const int64_t size = (m * m + 15) & ~(int64_t)15;
+          std::sort(live.begin(), live.end(), [](const Live& a, const Live& b) { return a.off < b.off; });
+          int64_t off = 0;
+          for (const Live& b : live) {
+            if (b.off - off >= size) break;
+            off = std::max(off, b.off + b.size);
+          }
+          live.push_back(Live{off, size, lEnd});
+          F.uArena = 2; F.uLd = (int)m; F.uOff = off;
+          S.cArena = std::max(S.cArena, off + size);
+        } else {
+          F.uArena = l & 1; F.uLd = (int)m; F.uOff = u;
+          u += m * m;
+          u = (u + 15) & ~(int64_t)15;
+        }
+      }
     }
     S.uArena = std::max(S.uArena, u);
     S.wArena = std::max(S.wArena, w);

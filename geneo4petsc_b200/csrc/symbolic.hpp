@@ -28,7 +28,12 @@ struct Front {
   int nchild = 0;
   int64_t rowOff = 0;  // into Symbolic::rowIdx (h entries, ascending, first k = own columns)
   int64_t lOff = 0;    // into the factor value array (ld*k doubles)
-  int64_t uOff = -1;   // into the ping-pong update arena of parity (level & 1); m*m doubles, ld = m
+  int64_t uOff = -1;   // into update arena `uArena`; the update matrix is m x m (lower triangle used) with leading dimension uLd
+  int uLd = 0;         // leading dimension of the update matrix storage
+  int uArena = 0;      // 0/1: ping-pong arena of parity (level & 1) -- consumed by the next level; 2: chain arena
+  int inplace = 0;     // 1: non-first panel of a supernode -- its update matrix IS the trailing block of its (only)
+                       // child's update matrix (same storage, uOff = child.uOff + k (uLd + 1)): nothing is copied or
+                       // zeroed along a supernode chain, the child only adds its first k columns to this panel
   int64_t wOff = -1;   // into the per-level scratch holding the unscaled panel F21 (m*k doubles, ld = m)
   int64_t relOff = -1; // into Symbolic::rel (m entries: position of update row i in the parent's row list); -1 if chain
   int m() const { return h - k; }
@@ -46,7 +51,8 @@ struct Symbolic {
   std::vector<int> levelPtr;    // [nlevels+1] into levelFronts
   std::vector<int> levelFronts; // fronts sorted by level
   int64_t lSize = 0;            // doubles in the factor
-  int64_t uArena = 0;           // doubles in EACH of the two update arenas
+  int64_t uArena = 0;           // doubles in EACH of the two ping-pong update arenas
+  int64_t cArena = 0;           // doubles in the chain arena (update matrices that live for a whole supernode chain)
   int64_t wArena = 0;           // doubles in the per-level panel scratch
   // scatter of the input values into the factor array: for t < asmSrc.size(): L[asmDst[t]] = val[asmSrc[t]]
   std::vector<int64_t> asmSrc;  // index into the input CSR value array (lower triangle entries after permutation)
@@ -62,6 +68,7 @@ struct SymbolicOptions {
   int nb = 128;        // panel width
   int ordering = 1;    // 0 natural, 1 METIS NodeND
   bool amalgamate = true;
+  bool chainInplace = true;  // update matrices of supernode chains stay in place (see Front::inplace)
   int subtreeCols = 64; // subtrees of the assembly tree with at most this many columns are merged into one dense front
   int ndDepth = 0;     // top levels of the nested dissection done here (METIS_ComputeVertexSeparator) with the two halves
                        // ordered by concurrent threads: 2^ndDepth threads per matrix; 0 = plain METIS_NodeND

@@ -3,7 +3,16 @@ the CUDA kernels consume (geneo4petsc_b200/csrc/symbolic.cpp).  Test infrastruct
 relative indices, levels and arena offsets on a CPU-only box."""
 import numpy as np
 
-F_COL0, F_K, F_H, F_PARENT, F_LEVEL, F_CHAIN, F_NCHILD, F_ROWOFF, F_LOFF, F_UOFF, F_WOFF, F_RELOFF, F_LD = range(13)
+(F_COL0, F_K, F_H, F_PARENT, F_LEVEL, F_CHAIN, F_NCHILD, F_ROWOFF, F_LOFF, F_UOFF, F_WOFF, F_RELOFF, F_LD, F_ULD, F_UARENA,
+ F_INPLACE) = range(16)
+
+
+def _umat(arenas, fr, f):
+    """View of the update matrix of front f: m x m inside arena uArena with leading dimension uLd (symbolic.hpp:Front)."""
+    m, ld, off = fr[f, F_H] - fr[f, F_K], fr[f, F_ULD], fr[f, F_UOFF]
+    a = arenas[fr[f, F_UARENA]]
+    assert off >= 0 and off + (m - 1) * ld + m <= len(a), "update matrix outside its arena"
+    return np.lib.stride_tricks.as_strided(a[off:], shape=(m, m), strides=(a.itemsize, ld * a.itemsize))
 
 
 def _panel(L, fr, f):
@@ -17,13 +26,18 @@ def factorize(sym, vals):
     fr = sym.fronts
     L = np.zeros(sym.info["lSize"])
     L[sym.asm_dst] = vals[sym.asm_src]
-    arenas = [np.zeros(max(1, sym.info["uArena"])), np.zeros(max(1, sym.info["uArena"]))]
+    # ping-pong arenas 0/1 and the chain arena 2, poisoned with NaN: whatever is read must have been zeroed or written
+    arenas = [np.full(max(1, sym.info["uArena"]), np.nan), np.full(max(1, sym.info["uArena"]), np.nan),
+              np.full(max(1, sym.info["cArena"]), np.nan)]
     neg = 0
     order = np.argsort(fr[:, F_LEVEL], kind="stable")
     levels = fr[:, F_LEVEL]
     for lvl in range(sym.info["nlevels"]):
-        cur, prev = arenas[lvl & 1], arenas[(lvl & 1) ^ 1]
-        cur[:] = 0.0
+        arenas[lvl & 1][:] = 0.0
+        for f in order[levels[order] == lvl]:  # chain blocks are zeroed where they are born
+            if fr[f, F_H] > fr[f, F_K] and fr[f, F_UARENA] == 2 and not fr[f, F_INPLACE]:
+                m = fr[f, F_H] - fr[f, F_K]
+                arenas[2][fr[f, F_UOFF]: fr[f, F_UOFF] + m * m] = 0.0
         W = np.zeros(max(1, sym.info["wArena"]))
         if lvl > 0:  # extend-add children (level lvl-1) into their parents
             for c in order[levels[order] == lvl - 1]:
@@ -34,17 +48,22 @@ def factorize(sym, vals):
                 assert par >= 0 and fr[par, F_LEVEL] == lvl
                 pk, ph = fr[par, F_K], fr[par, F_H]
                 pm = ph - pk
-                U = prev[fr[c, F_UOFF]: fr[c, F_UOFF] + m * m].reshape(m, m, order="F")
+                U = _umat(arenas, fr, c)
                 rel = np.arange(m) if fr[c, F_RELOFF] < 0 else sym.rel[fr[c, F_RELOFF]: fr[c, F_RELOFF] + m]
                 Pp = _panel(L, fr, par)
-                Up = cur[fr[par, F_UOFF]: fr[par, F_UOFF] + pm * pm].reshape(pm, pm, order="F") if pm > 0 else None
+                Up = _umat(arenas, fr, par) if pm > 0 else None
+                inplace = bool(fr[par, F_INPLACE])
+                if inplace:  # the parent's update matrix IS the trailing block of the child's
+                    assert fr[c, F_CHAIN] == 1 and fr[par, F_NCHILD] == 1 and fr[c, F_RELOFF] < 0
+                    assert fr[par, F_UARENA] == fr[c, F_UARENA] and fr[par, F_ULD] == fr[c, F_ULD]
+                    assert fr[par, F_UOFF] == fr[c, F_UOFF] + pk * (fr[c, F_ULD] + 1) and pm == m - pk
                 for cc in range(m):
                     pc = rel[cc]
                     rr = np.arange(cc, m)
                     pr = rel[rr]
                     if pc < pk:
                         Pp[pr, pc] += U[rr, cc]
-                    else:
+                    elif not inplace:
                         Up[pr - pk, pc - pk] += U[rr, cc]
         for f in order[levels[order] == lvl]:
             k, h = fr[f, F_K], fr[f, F_H]
@@ -69,8 +88,10 @@ def factorize(sym, vals):
                 Wf = W[fr[f, F_WOFF]: fr[f, F_WOFF] + m * k].reshape(m, k, order="F")
                 Wf[:, :] = F21
                 P[k:, :] = F21 @ Dinv
-                U = cur[fr[f, F_UOFF]: fr[f, F_UOFF] + m * m].reshape(m, m, order="F")
-                U -= P[k:, :] @ F21.T
+                U = _umat(arenas, fr, f)
+                upd = P[k:, :] @ F21.T
+                il = np.tril_indices(m)
+                U[il] -= upd[il]  # the device writes whole 64x64 tiles; only the lower triangle is ever read
     return L, neg
 
 
