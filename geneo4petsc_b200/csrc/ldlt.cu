@@ -550,9 +550,11 @@ template <int W, int STAGES, int CSTRIDE, int BC> struct RingCfgT {
   static constexpr int WARP_BYTES = STAGES * STAGE + RING_RS * 48;
   static constexpr int SMEM = W * WARP_BYTES;
 };
-template <int NR> struct RingCfg;
-template <> struct RingCfg<1> : RingCfgT<16, 3, 64, 16> {};  // 16 warps x 3 stages: 128 KB in flight per SM, <= 128 registers
-template <> struct RingCfg<8> : RingCfgT<12, 4, 68, 32> {};  // 12 warps x 4 stages: 144 KB in flight per SM, <= 168 registers
+template <int NR, int VAR> struct RingCfg;   // VAR: tuning variant (GENEO_RING_VAR, default 0)
+template <> struct RingCfg<1, 0> : RingCfgT<16, 3, 64, 16> {};  // 16 warps x 3 stages: 128 KB in flight per SM, <= 128 registers
+template <> struct RingCfg<1, 1> : RingCfgT<12, 4, 64, 16> {};  // 12 warps x 4 stages: 144 KB in flight per SM, <= 168 registers
+template <> struct RingCfg<8, 0> : RingCfgT<12, 4, 68, 32> {};  // 12 warps x 4 stages: 144 KB in flight per SM, <= 168 registers
+template <> struct RingCfg<8, 1> : RingCfgT<12, 4, 68, 32> {};
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -575,16 +577,16 @@ __device__ __forceinline__ RingRec load_ring_item(const RingItem* p) {
 }
 __device__ __forceinline__ int64_t rec_i64(int lo, int hi) { return (int64_t)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
 
-template <int NR>
-__global__ void __launch_bounds__(RingCfg<NR>::WARPS * 32, 1)
+template <int NR, int VAR>
+__global__ void __launch_bounds__(RingCfg<NR, VAR>::WARPS * 32, 1)
 k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __restrict__ items,
              const int64_t* __restrict__ ranges, int nlev, int64_t ntot, double* __restrict__ X, double* __restrict__ Y,
              int ldx, long long* __restrict__ tstamp, int flags) {
-  constexpr int CS = RingCfg<NR>::CS;
-  constexpr int RING_S = RingCfg<NR>::S;
+  constexpr int CS = RingCfg<NR, VAR>::CS;
+  constexpr int RING_S = RingCfg<NR, VAR>::S;
   constexpr int TILE_BYTES = RING_CH * CS * 8;
-  constexpr int STAGE = RingCfg<NR>::STAGE;
-  constexpr int BWD_COLS = RingCfg<NR>::BWD_COLS;
+  constexpr int STAGE = RingCfg<NR, VAR>::STAGE;
+  constexpr int BWD_COLS = RingCfg<NR, VAR>::BWD_COLS;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char ringmem[];
   __shared__ ForestSub sSubs[MAX_SMEM_SUBS];
@@ -601,10 +603,10 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
       sCnt[p] = (int)ranges[(b ? 3 * nlev : nlev) + l];
     }
   if (NR > 1)  // fragments read whole stages: never let a NaN pattern of uninitialised shared memory into a product
-    for (int t = threadIdx.x; t < RingCfg<NR>::SMEM / 16; t += blockDim.x) reinterpret_cast<int4*>(ringmem)[t] = make_int4(0, 0, 0, 0);
+    for (int t = threadIdx.x; t < RingCfg<NR, VAR>::SMEM / 16; t += blockDim.x) reinterpret_cast<int4*>(ringmem)[t] = make_int4(0, 0, 0, 0);
   const bool inSmem = nsubs <= MAX_SMEM_SUBS;
   const int lane = threadIdx.x & 31;
-  unsigned char* wmem = ringmem + (threadIdx.x >> 5) * RingCfg<NR>::WARP_BYTES;
+  unsigned char* wmem = ringmem + (threadIdx.x >> 5) * RingCfg<NR, VAR>::WARP_BYTES;
   int4* recRing = reinterpret_cast<int4*>(wmem + RING_S * STAGE);
   // consecutive items of a phase go to different SMs: a level with few items still uses every SM's LSU / L1 / RED path
   const int64_t gw = (flags & 1) ? ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5 : (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
@@ -1106,6 +1108,20 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   return stats;
 }
 
+static int ring_var() {  // tuning variant of the ring kernels: read when a forest is built, fixed for that forest
+  const char* e = getenv("GENEO_RING_VAR");
+  return e ? (atoi(e) != 0 ? 1 : 0) : 0;
+}
+struct RingLaunch { const void* fn; int warps, smem, bwdCols; };
+static RingLaunch ring_launch(int which, int v) {
+  if (which == 0) {
+    if (v == 0) return RingLaunch{(const void*)k_solve_ring<1, 0>, RingCfg<1, 0>::WARPS, RingCfg<1, 0>::SMEM, RingCfg<1, 0>::BWD_COLS};
+    return RingLaunch{(const void*)k_solve_ring<1, 1>, RingCfg<1, 1>::WARPS, RingCfg<1, 1>::SMEM, RingCfg<1, 1>::BWD_COLS};
+  }
+  if (v == 0) return RingLaunch{(const void*)k_solve_ring<8, 0>, RingCfg<8, 0>::WARPS, RingCfg<8, 0>::SMEM, RingCfg<8, 0>::BWD_COLS};
+  return RingLaunch{(const void*)k_solve_ring<8, 1>, RingCfg<8, 1>::WARPS, RingCfg<8, 1>::SMEM, RingCfg<8, 1>::BWD_COLS};
+}
+
 // =====================================================================================================================
 // SolveForest
 // =====================================================================================================================
@@ -1132,12 +1148,13 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   }
   {
     int nb = 0;
-    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<1>::SMEM));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<1>, RingCfg<1>::WARPS * 32, RingCfg<1>::SMEM));
-    ringGrid[0] = std::max(1, nb) * nsm;
-    CUDA_CHECK(cudaFuncSetAttribute((const void*)k_solve_ring<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingCfg<8>::SMEM));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_solve_ring<8>, RingCfg<8>::WARPS * 32, RingCfg<8>::SMEM));
-    ringGrid[1] = std::max(1, nb) * nsm;
+    ringVar = ring_var();
+    for (int which = 0; which < 2; which++) {
+      const RingLaunch rl = ring_launch(which, ringVar);
+      CUDA_CHECK(cudaFuncSetAttribute(rl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.smem));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rl.fn, rl.warps * 32, rl.smem));
+      ringGrid[which] = std::max(1, nb) * nsm;
+    }
   }
 }
 
@@ -1198,8 +1215,8 @@ void SolveForest::build_generic() const {
 void SolveForest::build_ring(int which) const {
   HostProfScope hp("forest build (ring)");
   const int ns = (int)plans_.size();
-  const int warps = which == 0 ? RingCfg<1>::WARPS : RingCfg<8>::WARPS;
-  const int RING_BWD_COLS = which == 0 ? RingCfg<1>::BWD_COLS : RingCfg<8>::BWD_COLS;
+  const int warps = ring_launch(which, ringVar).warps;
+  const int RING_BWD_COLS = ring_launch(which, ringVar).bwdCols;
   const int64_t nw = (int64_t)ringGrid[which] * warps;
   std::vector<RingItem> items;
   std::vector<int64_t> ranges(4 * (size_t)nlev, 0);
@@ -1309,10 +1326,8 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
     void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp,
                   (void*)&ldx, (void*)&ts, (void*)&flags};
     (void)GENEO_TICK(0);
-    if (which == 0)
-      CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<1>, dim3(ringGrid[0]), dim3(RingCfg<1>::WARPS * 32), a1, RingCfg<1>::SMEM, st));
-    else
-      CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<8>, dim3(ringGrid[1]), dim3(RingCfg<8>::WARPS * 32), a1, RingCfg<8>::SMEM, st));
+    const RingLaunch rl = ring_launch(which, ringVar);
+    CUDA_CHECK(cudaLaunchCooperativeKernel(rl.fn, dim3(ringGrid[which]), dim3(rl.warps * 32), a1, rl.smem, st));
     return;
   }
   if (!genericBuilt) build_generic();
@@ -1350,10 +1365,8 @@ void SolveForest::solve_profile(double* X, double* Y, int nr, std::vector<double
   void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&X, (void*)&Y,
                 (void*)&ldx, (void*)&ts, (void*)&flags};
   (void)GENEO_TICK(0);
-  if (which == 0)
-    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<1>, dim3(ringGrid[0]), dim3(RingCfg<1>::WARPS * 32), a1, RingCfg<1>::SMEM, 0));
-  else
-    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_solve_ring<8>, dim3(ringGrid[1]), dim3(RingCfg<8>::WARPS * 32), a1, RingCfg<8>::SMEM, 0));
+  const RingLaunch rl = ring_launch(which, ringVar);
+  CUDA_CHECK(cudaLaunchCooperativeKernel(rl.fn, dim3(ringGrid[which]), dim3(rl.warps * 32), a1, rl.smem, 0));
   CUDA_CHECK(::geneo::sync_stream(0));
   std::vector<long long> h = dts.to_host();
   us.resize(2 * (size_t)nlev);

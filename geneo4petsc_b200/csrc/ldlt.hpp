@@ -82,6 +82,7 @@ class SolveForest {
   mutable std::vector<int64_t> ringCount_[2];
   mutable bool ringBuilt[2] = {false, false};
   int ringGrid[2] = {1, 1};
+  int ringVar = 0;  // tuning variant of the ring kernels (GENEO_RING_VAR when the forest was built)
   int gridBlocks[4] = {1, 1, 1, 1};
 };
 
