@@ -35,19 +35,27 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
                : "d"(a), "d"(b));
 }
 
-// All 128 threads of the CTA call this with identical arguments.
+constexpr int gemm_smem(int stages) { return stages * 2 * KC * SLD * 8; }  // bytes of dynamic shared memory per CTA
+
+// 8-byte asynchronous copy global -> shared; srcBytes = 0 zero-fills (rows / columns outside the matrix)
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem, int srcBytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(srcBytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_g() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// C (+)= A B^T on one 64x64 tile.  All 128 threads of the CTA call this with identical arguments.  The operands travel
+// global -> shared with cp.async through a GEMM_STAGES-deep ring (no register staging: 4-5 CTAs per SM keep the DMMA pipe
+// fed while another CTA is in its prologue or read-modify-writing its C tile); one __syncthreads per K chunk.
+template <int GEMM_STAGES>
 __device__ void gemm_tile_nt(const double* __restrict__ A, int lda, int M, const double* __restrict__ B, int ldb,
-                             int N, int K, double* __restrict__ C, int ldc, int mode, double* sA, double* sB) {
+                             int N, int K, double* __restrict__ C, int ldc, int mode, double* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 1, wn = warp >> 1;
   const int lr = tid & 63;   // row loaded by this thread
   const int lk = tid >> 6;   // first k column loaded by this thread (0/1), stride 2
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.;
-
   if (mode == 1) {  // the C tile is read-modify-written at the very end: pull it into L2 now, behind the whole product
     const int col = tid >> 1;
     if (col < N) {
@@ -56,32 +64,39 @@ __device__ void gemm_tile_nt(const double* __restrict__ A, int lda, int M, const
       if ((tid & 1) * 32 + 16 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + 16));
     }
   }
-  double ra[8], rb[8];
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.;
+
   const int nch = (K + KC - 1) / KC;
-  auto gload = [&](int ch) {
+  const bool aok = lr < M, bok = lr < N;
+  const double* Ar = A + (aok ? lr : 0);
+  const double* Br = B + (bok ? lr : 0);
+  auto issue = [&](int ch) {  // chunk ch -> stage ch % GEMM_STAGES
+    double* a = smem + (ch % GEMM_STAGES) * (2 * KC * SLD);
+    double* b = a + KC * SLD;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const int kk = ch * KC + lk + 2 * i;
-      ra[i] = (lr < M && kk < K) ? __ldg(A + lr + (size_t)kk * lda) : 0.;
-      rb[i] = (lr < N && kk < K) ? __ldg(B + lr + (size_t)kk * ldb) : 0.;
+      const int kl = lk + 2 * i, kk = ch * KC + kl;
+      const bool kok = kk < K;
+      cp_async8(a + kl * SLD + lr, Ar + (size_t)(kok ? kk : 0) * lda, (aok && kok) ? 8 : 0);
+      cp_async8(b + kl * SLD + lr, Br + (size_t)(kok ? kk : 0) * ldb, (bok && kok) ? 8 : 0);
     }
   };
-  auto sstore = [&](int buf) {
-    double* a = sA + buf * KC * SLD;
-    double* b = sB + buf * KC * SLD;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      a[(lk + 2 * i) * SLD + lr] = ra[i];
-      b[(lk + 2 * i) * SLD + lr] = rb[i];
-    }
-  };
-  gload(0);
-  sstore(0);
-  __syncthreads();
+  for (int s = 0; s < GEMM_STAGES - 1; s++) {
+    if (s < nch) issue(s);
+    cp_async_commit_g();
+  }
   for (int ch = 0; ch < nch; ch++) {
-    if (ch + 1 < nch) gload(ch + 1);
-    const double* a = sA + (ch & 1) * KC * SLD;
-    const double* b = sB + (ch & 1) * KC * SLD;
+    cp_async_wait_g<GEMM_STAGES - 2>();  // chunk ch has landed (this thread's copies) ...
+    __syncthreads();                     // ... everybody's; and everybody is done with the stage refilled below
+    if (ch + GEMM_STAGES - 1 < nch) issue(ch + GEMM_STAGES - 1);
+    cp_async_commit_g();
+    const double* a = smem + (ch % GEMM_STAGES) * (2 * KC * SLD);
+    const double* b = a + KC * SLD;
 #pragma unroll
     for (int k4 = 0; k4 < KC / 4; k4++) {
       double fa[4], fb[4];
@@ -96,9 +111,8 @@ __device__ void gemm_tile_nt(const double* __restrict__ A, int lda, int M, const
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
     }
-    if (ch + 1 < nch) sstore((ch + 1) & 1);
-    __syncthreads();
   }
+  cp_async_wait_g<0>();
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -117,12 +131,13 @@ __device__ void gemm_tile_nt(const double* __restrict__ A, int lda, int M, const
     }
 }
 
+template <int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS) k_dgemm_nt(int M, int N, int K, const double* A, int lda,
                                                            const double* B, int ldb, double* C, int ldc, int mode) {
-  __shared__ double sA[2 * KC * SLD], sB[2 * KC * SLD];
+  extern __shared__ __align__(16) double gsm[];
   const int ti = blockIdx.x, tj = blockIdx.y;
-  gemm_tile_nt(A + ti * TS, lda, min(TS, M - ti * TS), B + tj * TS, ldb, min(TS, N - tj * TS), K,
-               C + ti * TS + (size_t)tj * TS * ldc, ldc, mode, sA, sB);
+  gemm_tile_nt<STAGES>(A + ti * TS, lda, min(TS, M - ti * TS), B + tj * TS, ldb, min(TS, N - tj * TS), K,
+                       C + ti * TS + (size_t)tj * TS * ldc, ldc, mode, gsm);
 }
 
 // =====================================================================================================================
@@ -281,29 +296,31 @@ __global__ void __launch_bounds__(256) k_copy_panel(const WorkItem* __restrict__
     if (c0 + c < k) dst[(size_t)c * m] = v[c];
 }
 
+template <int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS) k_panel(const WorkItem* __restrict__ items,
                                                         const FrontDev* __restrict__ fr, double* __restrict__ L,
                                                         const double* __restrict__ W) {
-  __shared__ double sA[2 * KC * SLD], sB[2 * KC * SLD];
+  extern __shared__ __align__(16) double gsm[];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const int m = F.h - F.k, k = F.k, h = F.ld;
   double* P = L + F.lOff;
   // L21[ti rows, tj cols] = W[ti rows, :] * Dinv[tj rows, :]^T   (Dinv symmetric)
-  gemm_tile_nt(W + F.wOff + it.a * TS, m, min(TS, m - it.a * TS), P + it.b * TS, h, min(TS, k - it.b * TS), k,
-               P + k + it.a * TS + (size_t)it.b * TS * h, h, 0, sA, sB);
+  gemm_tile_nt<STAGES>(W + F.wOff + it.a * TS, m, min(TS, m - it.a * TS), P + it.b * TS, h, min(TS, k - it.b * TS), k,
+               P + k + it.a * TS + (size_t)it.b * TS * h, h, 0, gsm);
 }
 
+template <int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS) k_schur(const WorkItem* __restrict__ items,
                                                         const FrontDev* __restrict__ fr, const double* __restrict__ L,
                                                         const double* __restrict__ W, UArenas ua) {
-  __shared__ double sA[2 * KC * SLD], sB[2 * KC * SLD];
+  extern __shared__ __align__(16) double gsm[];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const int m = F.h - F.k, k = F.k, h = F.ld;
   // U[ti, tj] -= L21[ti rows, :] * W[tj rows, :]^T   (lower triangle of tiles only)
-  gemm_tile_nt(L + F.lOff + k + it.a * TS, h, min(TS, m - it.a * TS), W + F.wOff + it.b * TS, m,
-               min(TS, m - it.b * TS), k, ua.a[F.uArena] + F.uOff + it.a * TS + (size_t)it.b * TS * F.uLd, F.uLd, 1, sA, sB);
+  gemm_tile_nt<STAGES>(L + F.lOff + k + it.a * TS, h, min(TS, m - it.a * TS), W + F.wOff + it.b * TS, m,
+               min(TS, m - it.b * TS), k, ua.a[F.uArena] + F.uOff + it.a * TS + (size_t)it.b * TS * F.uLd, F.uLd, 1, gsm);
 }
 
 // =====================================================================================================================
@@ -951,10 +968,30 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
 
 }  // namespace
 
+static int gemm_stages() {  // cp.async pipeline depth of the DMMA tile kernels: 3 (4 CTAs per SM) or 2 (5 CTAs per SM)
+  static const int v = [] {
+    const char* e = getenv("GENEO_GEMM_STAGES");
+    const int st = (e && atoi(e) == 3) ? 3 : 2;  // measured: 27.1 vs 24.6 TFLOP/s on the rank-128 update, occupancy beats depth
+    const int sm = gemm_smem(st);
+    if (st == 2) {
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_dgemm_nt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_panel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_schur<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    } else {
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_dgemm_nt<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_panel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_schur<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    }
+    return st;
+  }();
+  return v;
+}
+
 void dgemm_nt_device(int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                      int mode, cudaStream_t st) {
   dim3 grid((M + TS - 1) / TS, (N + TS - 1) / TS);
-  k_dgemm_nt<<<GENEO_TICK(grid), GEMM_THREADS, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, mode);
+  if (gemm_stages() == 2) k_dgemm_nt<2><<<GENEO_TICK(grid), GEMM_THREADS, gemm_smem(2), st>>>(M, N, K, A, lda, B, ldb, C, ldc, mode);
+  else k_dgemm_nt<3><<<GENEO_TICK(grid), GEMM_THREADS, gemm_smem(3), st>>>(M, N, K, A, lda, B, ldb, C, ldc, mode);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1066,6 +1103,7 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   FactorStats stats;
   const double t0 = now_s();
   HostProfScope hp("factorize: host side total");
+  const int gst = gemm_stages();
   {
     HostProfScope hpA("factorize: alloc");
     ws.ensure(S);
@@ -1093,10 +1131,14 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
       k_diag_invert<32, 8><<<GENEO_TICK(P.diagSmallItems[l].cnt), 64, 0, st>>>(items + P.diagSmallItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
     if (P.copyItems[l].cnt)
       k_copy_panel<<<GENEO_TICK(P.copyItems[l].cnt), 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, L.p, ws.w.p);
-    if (P.panelItems[l].cnt)
-      k_panel<<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, 0, st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
-    if (P.schurItems[l].cnt)
-      k_schur<<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, 0, st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, ua);
+    if (P.panelItems[l].cnt) {
+      if (gst == 2) k_panel<2><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
+      else k_panel<3><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
+    }
+    if (P.schurItems[l].cnt) {
+      if (gst == 2) k_schur<2><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, ua);
+      else k_schur<3><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, ua);
+    }
     CUDA_CHECK(cudaGetLastError());
   }
   int h[2] = {0, 0};
