@@ -116,7 +116,11 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
   auto launch_solve = [&](int col0) {  // W = F^-1 (B Q[:, col0 : col0+b])
     HostProfScope hp("lanczos: launch_solve");
     k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)col0, maxDim, Xs.p, bp, b, bp);
-    for (int j0 = 0; j0 < bp; j0 += 8) F.solve_permuted(Xs.p, w, bp, j0, 8, st);
+    for (int j0 = 0; j0 < bp;) {  // 16 right-hand sides per pass over the factor where the block allows it
+      const int nr = (bp - j0 >= 16) ? 16 : 8;
+      F.solve_permuted(Xs.p, w, bp, j0, nr, st);
+      j0 += nr;
+    }
   };
   dim = b;           // basis columns, the newest block included
   int restarts = 0;

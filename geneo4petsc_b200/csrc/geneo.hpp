@@ -29,7 +29,7 @@ struct GeneoOptions {
   int nb = 128;          // LDL^T panel width
   int ordering = 1;      // 1 METIS NodeND, 0 natural
   double epsTol = 1e-4;  // -els2_eps_tol (block Lanczos residual tolerance; reference default 1e-3, src/geneo.cpp:658)
-  int epsBlock = 8;
+  int epsBlock = 0;      // block size of the Lanczos eigen-solver (-els2_eps_block); 0: 8
   bool releaseWorkspace = false;  // free the factorization / eigen-solver workspaces after every setup
   int epsMaxDim = 0;     // -els2_eps_ncv like bound on the Krylov dimension (0 = automatic)
   double pivRel = 1e-14; // static pivot threshold relative to max |a_ij| (stands for MUMPS CNTL(1/3), ICNTL(24))

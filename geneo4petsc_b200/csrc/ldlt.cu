@@ -572,6 +572,11 @@ template <> struct RingCfg<1, 0> : RingCfgT<16, 3, 64, 16> {};  // 16 warps x 3 
 template <> struct RingCfg<1, 1> : RingCfgT<12, 4, 64, 16> {};  // 12 warps x 4 stages: 144 KB in flight per SM, <= 168 registers
 template <> struct RingCfg<8, 0> : RingCfgT<12, 4, 68, 32> {};  // 12 warps x 4 stages: 144 KB in flight per SM, <= 168 registers
 template <> struct RingCfg<8, 1> : RingCfgT<12, 4, 68, 32> {};
+// NR = 16 walks the item lists of NR = 8 with two DMMAs per L fragment.  8 warps = 2 per SM sub-partition: the register file
+// of a sub-partition (16 K registers) then allows 255 registers per thread (10 or 12 warps put 3 on one sub-partition: 168);
+// 6 stages keep 160 KB in flight per SM.
+template <> struct RingCfg<16, 0> : RingCfgT<8, 6, 68, 32> {};
+template <> struct RingCfg<16, 1> : RingCfgT<8, 6, 68, 32> {};
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -712,7 +717,9 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
     if (NR > 1) __syncwarp();                     // every lane is done with the stage that is about to be refilled
     do top_up(); while (pcount == ccount);
     const unsigned ahead = pcount - ccount - 1;   // groups committed after the one needed now
-    if (RING_S > 3 && ahead >= 3) cp_async_wait<3>();
+    if (RING_S > 5 && ahead >= 5) cp_async_wait<5>();
+    else if (RING_S > 4 && ahead >= 4) cp_async_wait<4>();
+    else if (RING_S > 3 && ahead >= 3) cp_async_wait<3>();
     else if (ahead >= 2) cp_async_wait<2>();
     else if (ahead == 1) cp_async_wait<1>();
     else cp_async_wait<0>();
@@ -849,40 +856,49 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
           if (lane < BWD_COLS && lane < nc) atomicAdd(&Y[S.xoff + xcol + lane], -acc[0]);
         }
       } else {
-        // ---------------- NR = 8: FP64 tensor-core fragments; lane = 4 g + t ----------------
+        // ---------------- NR = 8 H (H = 1, 2): FP64 tensor-core fragments; lane = 4 g + t ----------------
+        constexpr int H = NR / 8;  // groups of 8 right-hand sides: every L fragment read from shared memory feeds H DMMAs
         const int g = lane >> 2, t4 = lane & 3;
         if (!bwd) {
           // C[row rb*8+g][rhs 2 t4 + e] += sum_cols L[row][col] X[col][rhs];  B fragment: X[col 4 ks + t4][rhs g]
-          auto load_x = [&](const ForestSub& S2, int xc2, int nc2, int grp, double (&xf)[8]) {
-            const double* xb = X + (size_t)(S2.xoff + xc2 + grp * 32) * ldx + g;
+          auto load_x = [&](const ForestSub& S2, int xc2, int nc2, int grp, int hh, double (&xf)[8]) {
+            const double* xb = X + (size_t)(S2.xoff + xc2 + grp * 32) * ldx + 8 * hh + g;
 #pragma unroll
             for (int ks = 0; ks < 8; ks++) {
               const int c = grp * 32 + ks * 4 + t4;
               xf[ks] = c < nc2 ? __ldcg(xb + (size_t)(ks * 4 + t4) * ldx) : 0.;
             }
           };
-          double xf[8];
-          if (havex) {
+          double xf[H][8];
+          if (H == 1 && havex) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ks++) xf[ks] = xn[ks];
-          } else load_x(S, xcol, nc, 0, xf);
+            for (int ks = 0; ks < 8; ks++) xf[0][ks] = xn[ks];
+          } else {
+#pragma unroll
+            for (int hh = 0; hh < H; hh++) load_x(S, xcol, nc, 0, hh, xf[hh]);
+          }
           havex = false;
-          double acc[8][2];
+          double acc[H][8][2];
 #pragma unroll
-          for (int b8 = 0; b8 < 8; b8++) acc[b8][0] = acc[b8][1] = 0.;
+          for (int hh = 0; hh < H; hh++)
+#pragma unroll
+            for (int b8 = 0; b8 < 8; b8++) acc[hh][b8][0] = acc[hh][b8][1] = 0.;
           int ridx[8];
           for (int q = 0; q < Q; q++) {
-            if (q > 0 && (q & 3) == 0) load_x(S, xcol, nc, q >> 2, xf);  // next group of 32 columns
+            if (q > 0 && (q & 3) == 0) {  // next group of 32 columns
+#pragma unroll
+              for (int hh = 0; hh < H; hh++) load_x(S, xcol, nc, q >> 2, hh, xf[hh]);
+            }
             const unsigned char* st = acquire();
             if (q == 0) {
               const int* ip = reinterpret_cast<const int*>(st + TILE_BYTES);
 #pragma unroll
               for (int b8 = 0; b8 < 8; b8++) ridx[b8] = ip[b8 * 8 + g];
             }
-            if (q == Q - 1 && i + nw < cnt) {
+            if (H == 1 && q == Q - 1 && i + nw < cnt) {
               const int4* r2 = recRing + (cm & (RING_RS - 1)) * 3;
               const int4 b2 = r2[1], c2 = r2[2];
-              load_x(inSmem ? sSubs[b2.x] : subs[b2.x], c2.y, b2.w, 0, xn);
+              load_x(inSmem ? sSubs[b2.x] : subs[b2.x], c2.y, b2.w, 0, 0, xn);
               havex = true;
             }
             const double* tb = reinterpret_cast<const double*>(st);
@@ -890,13 +906,16 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
 #pragma unroll
             for (int ks = 0; ks < 2; ks++) {
               const int col = ks * 4 + t4;
-              const double bfrag = (q & 1) ? ((q & 2) ? xf[6 + ks] : xf[2 + ks]) : ((q & 2) ? xf[4 + ks] : xf[ks]);
               const double* ap = tb + col * CS + g;
               const bool ok = col < ncc;
+              double a[8];
 #pragma unroll
-              for (int b8 = 0; b8 < 8; b8++) {
-                const double a = ok ? ap[b8 * 8] : 0.;
-                dmma8x8x4(acc[b8][0], acc[b8][1], a, bfrag);
+              for (int b8 = 0; b8 < 8; b8++) a[b8] = ok ? ap[b8 * 8] : 0.;
+#pragma unroll
+              for (int hh = 0; hh < H; hh++) {
+                const double bfrag = (q & 1) ? ((q & 2) ? xf[hh][6 + ks] : xf[hh][2 + ks]) : ((q & 2) ? xf[hh][4 + ks] : xf[hh][ks]);
+#pragma unroll
+                for (int b8 = 0; b8 < 8; b8++) dmma8x8x4(acc[hh][b8][0], acc[hh][b8][1], a[b8], bfrag);
               }
             }
             release();
@@ -905,26 +924,26 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
           for (int b8 = 0; b8 < 8; b8++) {
             const int r = b8 * 8 + g;
             if (r < nrows) {
-              if (r < kd) {
-                double* d = Y + (size_t)(S.xoff + ydiag + r) * ldx + 2 * t4;
-                atomicAdd(d, acc[b8][0]);
-                atomicAdd(d + 1, acc[b8][1]);
-              } else {
-                double* d = X + (size_t)(S.xoff + ridx[b8]) * ldx + 2 * t4;
-                atomicAdd(d, -acc[b8][0]);
-                atomicAdd(d + 1, -acc[b8][1]);
+              double* d = (r < kd) ? Y + (size_t)(S.xoff + ydiag + r) * ldx + 2 * t4 : X + (size_t)(S.xoff + ridx[b8]) * ldx + 2 * t4;
+              const double sg = (r < kd) ? 1. : -1.;
+#pragma unroll
+              for (int hh = 0; hh < H; hh++) {
+                atomicAdd(d + 8 * hh, sg * acc[hh][b8][0]);
+                atomicAdd(d + 8 * hh + 1, sg * acc[hh][b8][1]);
               }
             }
           }
         } else {
           // C[col cq*8+g][rhs 2 t4 + e] += sum_rows L[row][col] Y2[row][rhs];  A fragment: L[row 4 ks + t4][col g],
           // B fragment: Y2[row 4 ks + t4][rhs g]
-          double acc[BWD_COLS / 8][2];
+          double acc[H][BWD_COLS / 8][2];
 #pragma unroll
-          for (int c8 = 0; c8 < BWD_COLS / 8; c8++) acc[c8][0] = acc[c8][1] = 0.;
+          for (int hh = 0; hh < H; hh++)
+#pragma unroll
+            for (int c8 = 0; c8 < BWD_COLS / 8; c8++) acc[hh][c8][0] = acc[hh][c8][1] = 0.;
           const int T = (nrows + 63) >> 6;
           for (int t = 0; t < T; t++) {
-            double yf[16];
+            double yf[H][16];
 #pragma unroll
             for (int cq = 0; cq < BWD_COLS / RING_CH; cq++) {
               if (cq < Q) {  // warp-uniform
@@ -934,12 +953,19 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
 #pragma unroll
                   for (int ks = 0; ks < 16; ks++) {
                     const int r = t * 64 + ks * 4 + t4;
-                    yf[ks] = (r >= kd && r < nrows) ? __ldcg(Y + (size_t)(S.xoff + ip[ks * 4 + t4]) * ldx + g) : 0.;
+                    const bool ok = r >= kd && r < nrows;
+                    const double* yp = Y + (size_t)(S.xoff + (ok ? ip[ks * 4 + t4] : 0)) * ldx + g;
+#pragma unroll
+                    for (int hh = 0; hh < H; hh++) yf[hh][ks] = ok ? __ldcg(yp + 8 * hh) : 0.;
                   }
                 }
                 const double* ap = reinterpret_cast<const double*>(st) + g * CS + t4;
 #pragma unroll
-                for (int ks = 0; ks < 16; ks++) dmma8x8x4(acc[cq][0], acc[cq][1], ap[ks * 4], yf[ks]);
+                for (int ks = 0; ks < 16; ks++) {
+                  const double a = ap[ks * 4];
+#pragma unroll
+                  for (int hh = 0; hh < H; hh++) dmma8x8x4(acc[hh][cq][0], acc[hh][cq][1], a, yf[hh][ks]);
+                }
                 release();
               }
             }
@@ -949,8 +975,11 @@ k_solve_ring(const ForestSub* __restrict__ subs, int nsubs, const RingItem* __re
             const int c = c8 * 8 + g;
             if (c < nc) {
               double* d = Y + (size_t)(S.xoff + xcol + c) * ldx + 2 * t4;
-              atomicAdd(d, -acc[c8][0]);
-              atomicAdd(d + 1, -acc[c8][1]);
+#pragma unroll
+              for (int hh = 0; hh < H; hh++) {
+                atomicAdd(d + 8 * hh, -acc[hh][c8][0]);
+                atomicAdd(d + 8 * hh + 1, -acc[hh][c8][1]);
+              }
             }
           }
         }
@@ -1160,6 +1189,10 @@ static RingLaunch ring_launch(int which, int v) {
     if (v == 0) return RingLaunch{(const void*)k_solve_ring<1, 0>, RingCfg<1, 0>::WARPS, RingCfg<1, 0>::SMEM, RingCfg<1, 0>::BWD_COLS};
     return RingLaunch{(const void*)k_solve_ring<1, 1>, RingCfg<1, 1>::WARPS, RingCfg<1, 1>::SMEM, RingCfg<1, 1>::BWD_COLS};
   }
+  if (which == 2) {  // NR = 16 (shares the item lists of NR = 8)
+    if (v == 0) return RingLaunch{(const void*)k_solve_ring<16, 0>, RingCfg<16, 0>::WARPS, RingCfg<16, 0>::SMEM, RingCfg<16, 0>::BWD_COLS};
+    return RingLaunch{(const void*)k_solve_ring<16, 1>, RingCfg<16, 1>::WARPS, RingCfg<16, 1>::SMEM, RingCfg<16, 1>::BWD_COLS};
+  }
   if (v == 0) return RingLaunch{(const void*)k_solve_ring<8, 0>, RingCfg<8, 0>::WARPS, RingCfg<8, 0>::SMEM, RingCfg<8, 0>::BWD_COLS};
   return RingLaunch{(const void*)k_solve_ring<8, 1>, RingCfg<8, 1>::WARPS, RingCfg<8, 1>::SMEM, RingCfg<8, 1>::BWD_COLS};
 }
@@ -1191,11 +1224,12 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
   {
     int nb = 0;
     ringVar = ring_var();
-    for (int which = 0; which < 2; which++) {
+    for (int which = 0; which < 3; which++) {
       const RingLaunch rl = ring_launch(which, ringVar);
       CUDA_CHECK(cudaFuncSetAttribute(rl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.smem));
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rl.fn, rl.warps * 32, rl.smem));
-      ringGrid[which] = std::max(1, nb) * nsm;
+      if (which < 2) ringGrid[which] = std::max(1, nb) * nsm;  // (NR = 16 walks the NR = 8 lists on the same grid: the warp
+                                                                 //  -> item mapping is computed in the kernel from its own block size)
     }
   }
 }
@@ -1358,7 +1392,7 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
   const int64_t* ranges = dRanges.p;
   int nl = nlev;
   int64_t nt = ntot;
-  if (((nr == 1 && ldx == 1) || nr == 8) && !getenv("GENEO_SOLVE_GENERIC")) {
+  if (((nr == 1 && ldx == 1) || nr == 8 || nr == 16) && !getenv("GENEO_SOLVE_GENERIC")) {
     const int which = nr == 1 ? 0 : 1;
     if (!ringBuilt[which]) build_ring(which);
     const RingItem* ritems = dRing[which].p;
@@ -1368,8 +1402,13 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
     void* a1[] = {(void*)&subs, (void*)&nsubs, (void*)&ritems, (void*)&rranges, (void*)&nl, (void*)&nt, (void*)&Xp, (void*)&Yp,
                   (void*)&ldx, (void*)&ts, (void*)&flags};
     (void)GENEO_TICK(0);
-    const RingLaunch rl = ring_launch(which, ringVar);
+    const RingLaunch rl = ring_launch(nr == 16 ? 2 : which, ringVar);
     CUDA_CHECK(cudaLaunchCooperativeKernel(rl.fn, dim3(ringGrid[which]), dim3(rl.warps * 32), a1, rl.smem, st));
+    return;
+  }
+  if (nr == 16) {  // (debug path GENEO_SOLVE_GENERIC: the generic kernels stop at 8 right-hand sides)
+    solve(X, Y, ldx, j0, 8, st);
+    solve(X, Y, ldx, j0 + 8, 8, st);
     return;
   }
   if (!genericBuilt) build_generic();
@@ -1383,7 +1422,7 @@ void SolveForest::solve(double* X, double* Y, int ldx, int j0, int nr, cudaStrea
     case 2: fn = (const void*)k_solve_forest<2>; q = 1; break;
     case 4: fn = (const void*)k_solve_forest<4>; q = 2; break;
     case 8: fn = (const void*)k_solve_forest<8>; q = 3; break;
-    default: GENEO_CHECK(false, "nrhs chunk must be 1, 2, 4 or 8");
+    default: GENEO_CHECK(false, "nrhs chunk must be 1, 2, 4, 8 or 16");
   }
   (void)GENEO_TICK(0);
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks[q]), dim3(SOLVE_THREADS), args, 0, st));

@@ -102,7 +102,7 @@ class LdltFactor {
   // vals: device array aligned with the plan's input CSR pattern.  pivTol: |pivot| below it is replaced by +-pivTol.
   FactorStats factorize(const double* dVals, double pivTol, LdltWorkspace& ws, cudaStream_t st);
   // Solve in the PERMUTED ordering: X (n x ldx row-major block, columns j0..j0+nr-1) is overwritten by the forward
-  // sweep, the result lands in Y (same layout).  nr in {1,2,4,8}.
+  // sweep, the result lands in Y (same layout).  nr in {1,2,4,8,16}.
   void solve_permuted(double* X, double* Y, int ldx, int j0, int nr, cudaStream_t st) const;
   const LdltPlan& plan() const { return *plan_; }
   std::shared_ptr<LdltPlan> plan_ptr() const { return plan_; }

@@ -225,3 +225,21 @@ def test_graph_laplacian_matches_oracle(lvl, ksp):
     r = pc.ksp_solve(pc.make_rhs(), ksp=ksp, rtol=1e-6, atol=1e-6)
     assert r["reason"] > 0 and abs(r["its"] - rep.ksp.its) <= 1, (r["its"], rep.ksp.its)
     assert np.linalg.norm(r["x"] - rep.ksp.x) <= 1e-4 * np.linalg.norm(rep.ksp.x)
+
+
+def test_block16_eigensolver_uses_the_16_rhs_solve(lap3d):
+    """-els2_eps_block 16: the Lanczos block goes through k_solve_ring<16> (two DMMAs per factor fragment); counts and
+    eigenvalues are those of the dense oracle, and the preconditioner is the one of the default block of 8."""
+    mesh, nparts = lap3d, 4
+    p = _problem(mesh, nparts)
+    base = ["-geneo_lvl", "ASM,1", "-geneo_tau", "0.3", "-els2_eps_tol", "1e-10"]
+    pc8 = g.GeneoPC(base + ["-els2_eps_block", "8"]).setup(p)
+    pc16 = g.GeneoPC(base + ["-els2_eps_block", "16"]).setup(p)
+    rep = _oracle(mesh, p, nparts, go.GenEOOptions(lvl1="ASM", lvl2="1", tau=0.3), ksp="cg", rtol=1e-6)
+    for s in range(nparts):
+        assert pc16.sub_info(s)["nev"] == rep.pc.sub[s].z.shape[1]
+        np.testing.assert_allclose(np.sort(pc16.sub_eigenvalues(s)), np.sort(np.array(rep.pc.sub[s].eigvals)), rtol=1e-6, atol=1e-12)
+    x = np.random.default_rng(2).standard_normal(mesh.nb_node)
+    y8, y16, yo = pc8.apply(x), pc16.apply(x), rep.pc.apply(x)
+    assert np.linalg.norm(y16 - yo) <= 1e-8 * np.linalg.norm(yo)
+    assert np.linalg.norm(y16 - y8) <= 1e-8 * np.linalg.norm(y8)

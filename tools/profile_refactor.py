@@ -6,7 +6,7 @@ import geneo4petsc_b200 as g
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/profile_refactor_%d.csv" % size
 prob = g.Problem().generate("laplacian", "--dim 3 --size %d --inpEps 0.0001" % size).decompose(8, True, 0)
-pc = g.GeneoPC(["-geneo_lvl", "ASM,1", "-geneo_tau", "0.1"]).setup(prob)
+pc = g.GeneoPC(["-geneo_lvl", "ASM,1", "-geneo_tau", "0.1"] + os.environ.get("GENEO_EXTRA_OPTS", "").split()).setup(prob)
 n = prob.sizes()["nb_node"]
 b = torch.zeros(n, dtype=torch.float64, device="cuda"); x = torch.zeros_like(b)
 ones = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
@@ -18,4 +18,5 @@ t = time.time(); pc.refactor(); torch.cuda.synchronize(); t1 = time.time()
 r = pc.ksp_solve_device(b.data_ptr(), x.data_ptr(), ksp="cg", rtol=1e-5, atol=1e-50, restart=30)
 torch.cuda.synchronize(); t2 = time.time()
 g.profile_dump(out)
+print("eig steps/dim per subdomain:", [(pc.sub_info(i)["eigSteps"], pc.sub_info(i)["eigDim"], pc.sub_info(i)["nev"]) for i in range(8)])
 print("refactor %.3f s, solve %.3f s (%d its)" % (t1 - t, t2 - t1, r["its"]), {k: round(v, 3) for k, v in pc.timers().items() if k.startswith("lvl")})
