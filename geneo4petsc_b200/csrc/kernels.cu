@@ -216,36 +216,51 @@ __global__ void k_pull_sum(int n, const int64_t* __restrict__ ptr, const int64_t
 // ---------------------------------------------------------------------------------------------------------------
 // tall-skinny dense
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int GR = 64;  // rows per smem tile
+// G (p x q) += X^T Y  for tall-skinny row-major blocks (the Gram products of the block Lanczos eigen-solver: X = B Q with up
+// to a few hundred columns, Y = one block of 8).  The long dimension is the K of mma.sync.m8n8k4.f64: a warp walks 4-row
+// steps of its CTA's row range, A fragment = X[4 rows][8 columns]^T straight from global memory (4 rows x 64 bytes per
+// load, 8 loads = 512 contiguous bytes per row), B fragment = Y[4 rows][8 columns]; 8 accumulator fragments per warp
+// (64 columns of X per CTA), summed over the 8 warps through shared memory, one atomicAdd per entry and CTA.
+constexpr int TG_PCOLS = 64;   // columns of X per CTA (8 fragments)
+__device__ __forceinline__ void dmma_f64(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 __global__ void __launch_bounds__(256) k_ts_gram(int n, const double* __restrict__ X, int ldx, int p,
                                                  const double* __restrict__ Y, int ldy, int q, double* G, int ldg,
                                                  int rowsPerCta) {
-  __shared__ double sx[GR][33], sy[GR][33];
-  const int p0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
-  const int pi = threadIdx.x & 31, qg = threadIdx.x >> 5;  // 8 groups x 4 columns
+  __shared__ double red[8][8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int p0 = blockIdx.x * TG_PCOLS, q0 = blockIdx.y * 8;
   const int64_t r0 = (int64_t)blockIdx.z * rowsPerCta;
   const int64_t r1 = min((int64_t)n, r0 + rowsPerCta);
-  double acc[4] = {0., 0., 0., 0.};
-  for (int64_t rb = r0; rb < r1; rb += GR) {
-    for (int e = threadIdx.x; e < GR * 32; e += 256) {
-      const int rr = e >> 5, cc = e & 31;
-      const int64_t r = rb + rr;
-      sx[rr][cc] = (r < r1 && p0 + cc < p) ? X[(size_t)r * ldx + p0 + cc] : 0.;
-      sy[rr][cc] = (r < r1 && q0 + cc < q) ? Y[(size_t)r * ldy + q0 + cc] : 0.;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int rr = 0; rr < GR; rr++) {
-      const double xv = sx[rr][pi];
+  double acc[8][2];
 #pragma unroll
-      for (int e = 0; e < 4; e++) acc[e] += xv * sy[rr][qg * 4 + e];
-    }
-    __syncthreads();
+  for (int pb = 0; pb < 8; pb++) acc[pb][0] = acc[pb][1] = 0.;
+  const bool qok = q0 + g < q;
+  for (int64_t r = r0 + 4 * warp; r < r1; r += 32) {
+    const int64_t row = r + t;
+    const bool rok = row < r1;
+    const double* xr = X + (size_t)(rok ? row : r0) * ldx + p0 + g;
+    const double yb = (rok && qok) ? __ldg(Y + (size_t)row * ldy + q0 + g) : 0.;
+    double a[8];
+#pragma unroll
+    for (int pb = 0; pb < 8; pb++) a[pb] = (rok && p0 + pb * 8 + g < p) ? __ldg(xr + pb * 8) : 0.;
+#pragma unroll
+    for (int pb = 0; pb < 8; pb++) dmma_f64(acc[pb][0], acc[pb][1], a[pb], yb);
   }
-  if (p0 + pi < p)
 #pragma unroll
-    for (int e = 0; e < 4; e++)
-      if (q0 + qg * 4 + e < q) atomicAdd(&G[(size_t)(p0 + pi) * ldg + q0 + qg * 4 + e], acc[e]);
+  for (int pb = 0; pb < 8; pb++) { red[warp][pb][2 * lane] = acc[pb][0]; red[warp][pb][2 * lane + 1] = acc[pb][1]; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 8 * 64; e += 256) {
+    const int pb = e >> 6, f = e & 63;  // fragment entry f of lane f/2: C[m = (f/2) >> 2][n = 2 ((f/2) & 3) + (f & 1)]
+    double sum = 0.;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sum += red[w][pb][f];
+    const int ln = f >> 1;
+    const int pc = p0 + pb * 8 + (ln >> 2), qc = q0 + 2 * (ln & 3) + (f & 1);
+    if (pc < p && qc < q && sum != 0.) atomicAdd(&G[(size_t)pc * ldg + qc], sum);
+  }
 }
 
 // W[r, 0:q] = beta W[r, 0:q] + alpha sum_p Q[r,p] C[p, 0:q],  q <= 8.  One thread per row (128 rows per CTA); Q tiles of
@@ -480,9 +495,10 @@ void pull_sum(int n, const int64_t* ptr, const int64_t* pos, const double* t, do
   k_pull_sum<<<GENEO_TICK(grid_for(n, 256)), 256, 0, st>>>(n, ptr, pos, t, y, accumulate);
 }
 void ts_gram(int n, const double* X, int ldx, int p, const double* Y, int ldy, int q, double* G, int ldg, cudaStream_t st) {
-  const int tp = (p + 31) / 32, tq = (q + 31) / 32;
-  int nz = std::max(1, std::min((n + 4 * GR - 1) / (4 * GR), std::max(1, NSM * 4 / (tp * tq))));
-  int rowsPerCta = ((n + nz - 1) / nz + GR - 1) / GR * GR;
+  if (n <= 0 || p <= 0 || q <= 0) return;
+  const int tp = (p + TG_PCOLS - 1) / TG_PCOLS, tq = (q + 7) / 8;
+  int nz = std::max(1, std::min((n + 255) / 256, std::max(1, NSM * 8 / (tp * tq))));
+  int rowsPerCta = ((n + nz - 1) / nz + 31) / 32 * 32;
   nz = (n + rowsPerCta - 1) / rowsPerCta;
   dim3 grid(tp, tq, nz);
   k_ts_gram<<<GENEO_TICK(grid), 256, 0, st>>>(n, X, ldx, p, Y, ldy, q, G, ldg, rowsPerCta);
