@@ -88,6 +88,34 @@ void dev_free(void* p, size_t cap) {
   g_dev_cache_bytes += cap;
 }
 
+void h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  constexpr size_t CH = (size_t)32 << 20;
+  if (bytes < ((size_t)4 << 20)) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  static std::mutex mtx;
+  static char* pin[2] = {nullptr, nullptr};
+  static cudaEvent_t ev[2];
+  static bool used[2] = {false, false};
+  std::lock_guard<std::mutex> lk(mtx);
+  if (!pin[0]) {
+    for (int i = 0; i < 2; i++) {
+      CUDA_CHECK(cudaHostAlloc((void**)&pin[i], CH, cudaHostAllocDefault));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+  }
+  int slot = 0;
+  for (size_t off = 0; off < bytes; off += CH, slot ^= 1) {
+    const size_t len = std::min(CH, bytes - off);
+    if (used[slot]) CUDA_CHECK(cudaEventSynchronize(ev[slot]));  // the DMA that last read this bounce buffer is done
+    memcpy(pin[slot], static_cast<const char*>(src) + off, len);
+    CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(dst) + off, pin[slot], len, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaEventRecord(ev[slot], st));
+    used[slot] = true;
+  }
+}
+
 double g_sync_wait_s = 0.;
 namespace {
 const bool g_hostprof = getenv("GENEO_HOSTPROF") != nullptr;
@@ -440,21 +468,44 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
           for (int64_t t = S->aNeu.ptr[l]; t < S->aNeu.ptr[l + 1]; t++) { ci[p] = S->nodes[S->aNeu.idx[t]]; cv[p] = S->aNeu.val[t]; p++; }
         }
     }
+    // sort + merge every row (a node shared by subdomains gets one partial row from each): rows are independent, so the
+    // pass is split over the host threads (it is on the critical path of the cold setup: the device waits for A)
     g.ptr.assign(nLoc + 1, 0);
-    g.idx.reserve(ci.size()); g.val.reserve(ci.size());
-    std::vector<std::pair<int, double>> row;
-    for (int i = 0; i < nLoc; i++) {
-      row.clear();
-      for (int64_t t = cnt[i]; t < cnt[i + 1]; t++) row.emplace_back(ci[t], cv[t]);
-      std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
-      for (size_t k = 0; k < row.size();) {
-        const int c = row[k].first;
-        double s = 0.;
-        while (k < row.size() && row[k].first == c) { s += row[k].second; k++; }
-        g.idx.push_back(c); g.val.push_back(s);
+    const int nth = (int)std::max(1u, std::min(hw, 32u));
+    auto for_rows = [&](auto&& fn) {
+      std::vector<std::thread> ths;
+      for (int t = 0; t < nth; t++)
+        ths.emplace_back([&, t]() {
+          const int i0 = (int)((int64_t)nLoc * t / nth), i1 = (int)((int64_t)nLoc * (t + 1) / nth);
+          fn(i0, i1);
+        });
+      for (auto& th : ths) th.join();
+    };
+    for_rows([&](int i0, int i1) {  // pass 1: sort each row segment in place, merge duplicates to its front, count
+      std::vector<std::pair<int, double>> row;
+      for (int i = i0; i < i1; i++) {
+        row.clear();
+        for (int64_t t = cnt[i]; t < cnt[i + 1]; t++) row.emplace_back(ci[t], cv[t]);
+        std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+        int64_t w = cnt[i];
+        for (size_t k = 0; k < row.size();) {
+          const int c = row[k].first;
+          double sum = 0.;
+          while (k < row.size() && row[k].first == c) { sum += row[k].second; k++; }
+          ci[w] = c; cv[w] = sum; w++;
+        }
+        g.ptr[i + 1] = w - cnt[i];
       }
-      g.ptr[i + 1] = (int64_t)g.idx.size();
-    }
+    });
+    for (int i = 0; i < nLoc; i++) g.ptr[i + 1] += g.ptr[i];
+    g.idx.resize((size_t)g.ptr[nLoc]); g.val.resize((size_t)g.ptr[nLoc]);
+    for_rows([&](int i0, int i1) {  // pass 2: compact
+      for (int i = i0; i < i1; i++) {
+        const int64_t len = g.ptr[i + 1] - g.ptr[i];
+        std::copy(ci.begin() + cnt[i], ci.begin() + cnt[i] + len, g.idx.begin() + g.ptr[i]);
+        std::copy(cv.begin() + cnt[i], cv.begin() + cnt[i] + len, g.val.begin() + g.ptr[i]);
+      }
+    });
     A.build(g, st);
   }
   operatorTime = now_s() - t0;
