@@ -277,6 +277,7 @@ namespace {
 
 struct HostPrep {  // everything the host prepares for one subdomain (worker thread)
   Symbolic sym;
+  std::shared_ptr<LdltPlan> plan;  // symbolic + the work lists of every level, not uploaded yet
   CsrHost patP;                 // permuted pattern of A_dir with its values
   std::vector<double> vNeuP, vRobP, dP;
   std::vector<int> gidx;
@@ -345,6 +346,8 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
           if (S.mult[perm[H.patP.idx[q]]] > 1) H.vRobP[q] += opt.optim * H.vNeuP[q];
       }
   }
+  // the work lists of every factorization level are host work too: built here, uploaded by the thread that owns the device
+  H.plan = std::make_shared<LdltPlan>(std::move(H.sym), LdltPlan::HostOnly{});
 }
 
 }  // namespace
@@ -536,7 +539,8 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     }
     s.maxMult = H.maxMult;
     s.anorm = H.anorm;
-    s.plan = std::make_shared<LdltPlan>(std::move(H.sym));
+    s.plan = H.plan;
+    s.plan->upload();
     s.pat.upload_pattern(H.patP, st);
     s.vNeu.upload(H.vNeuP, st);
     if (opt.lvl1ORAS) s.vRob.upload(H.vRobP, st);

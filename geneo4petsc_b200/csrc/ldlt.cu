@@ -1032,15 +1032,24 @@ LdltPlan::LdltPlan(int n, const int64_t* ptr, const int* idx, const SymbolicOpti
   build_device();
 }
 LdltPlan::LdltPlan(Symbolic&& s) : sym(std::move(s)) { build_device(); }
+LdltPlan::LdltPlan(Symbolic&& s, HostOnly) : sym(std::move(s)) { build_host(); }
 
 void LdltPlan::build_device() {
+  build_host();
+  upload();
+}
+
+// work lists of every level (host only: safe on a worker thread, no CUDA call)
+void LdltPlan::build_host() {
   const int nf = (int)sym.fronts.size();
-  std::vector<FrontDev> fd(nf);
+  std::vector<FrontDev>& fd = hostFronts_;
+  fd.assign(nf, FrontDev());
   for (int f = 0; f < nf; f++) {
     const Front& F = sym.fronts[f];
     fd[f] = FrontDev{F.lOff, F.uOff, F.wOff, F.rowOff, F.relOff, F.k, F.h, F.ld, F.parent, F.nchild, F.uLd, F.uArena, F.inplace, 0};
   }
-  std::vector<WorkItem> items;
+  std::vector<WorkItem>& items = hostItems_;
+  items.clear();
   auto begin = [&](Range& r) { r.off = (int64_t)items.size(); };
   auto end = [&](Range& r) { r.cnt = (int)((int64_t)items.size() - r.off); };
   const int nl = sym.nlevels;
@@ -1101,17 +1110,22 @@ void LdltPlan::build_device() {
     end(schurItems[l]);
   }
 
-  dFronts.upload(fd);
+}
+
+void LdltPlan::upload() {
+  dFronts.upload(hostFronts_);
   dRowIdx.upload(sym.rowIdx);
   if (!sym.rel.empty()) dRel.upload(sym.rel);
   dAsmSrc.upload(sym.asmSrc);
   dAsmDst.upload(sym.asmDst);
-  dItems.upload(items);
+  dItems.upload(hostItems_);
   dPerm.upload(sym.perm);
   CUDA_CHECK(::geneo::sync_stream(0));
-  // the host copies of the big symbolic arrays are no longer needed
+  // the host copies of the big arrays are no longer needed
   std::vector<int64_t>().swap(sym.asmSrc);
   std::vector<int64_t>().swap(sym.asmDst);
+  std::vector<WorkItem>().swap(hostItems_);
+  std::vector<FrontDev>().swap(hostFronts_);
 }
 
 size_t LdltPlan::plan_bytes() const {

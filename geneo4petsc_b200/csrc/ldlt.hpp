@@ -23,6 +23,9 @@ class LdltPlan {
  public:
   LdltPlan(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt);
   explicit LdltPlan(Symbolic&& s);  // symbolic analysis done elsewhere (e.g. on a host worker thread)
+  struct HostOnly {};
+  LdltPlan(Symbolic&& s, HostOnly);  // work lists built too, but nothing uploaded: no CUDA call (worker threads); then upload()
+  void upload();
   Symbolic sym;
   // device-resident schedule
   DevBuf<FrontDev> dFronts;
@@ -41,7 +44,9 @@ class LdltPlan {
   mutable const double* selfL = nullptr;
  private:
   void build_device();
- public:
+  void build_host();
+  std::vector<FrontDev> hostFronts_;
+  std::vector<WorkItem> hostItems_;
 };
 
 // ---- level-scheduled solves over a forest of factors (one persistent cooperative kernel) -----------------------------
