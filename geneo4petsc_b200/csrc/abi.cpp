@@ -238,7 +238,7 @@ int geneo_problem_sub_matrix(geneo_problem_t p, int s, int which, int64_t* ptr, 
 
 // ---- preconditioner ---------------------------------------------------------------------------------------------------
 int geneo_pc_create(geneo_pc_t* out) { ABI_TRY ABI_REQ(out, "null output"); *out = new geneo_pc_s(); ABI_CATCH }
-int geneo_pc_destroy(geneo_pc_t pc) { ABI_TRY delete pc; ABI_CATCH }
+int geneo_pc_destroy(geneo_pc_t pc) { ABI_TRY delete pc; dev_cache_flush(); /* parked device blocks go back to the driver */ ABI_CATCH }
 int geneo_pc_set_from_options(geneo_pc_t pc, int argc, const char* const* argv) {
   ABI_TRY
   ABI_REQ(pc, "GenEO preconditioner is invalid");

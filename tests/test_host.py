@@ -166,3 +166,45 @@ def test_predecomposed_input_matches_mesh_decomposition():
                 np.testing.assert_array_equal(q.sub_intersect(s, t), p.sub_intersect(s, t))
             d = (q.sub_matrix(s, 1) - p.sub_matrix(s, 1)).tocoo()
             assert d.nnz == 0 or np.abs(d.data).max() <= 1e-12 * np.abs(p.sub_matrix(s, 1).data).max()
+
+
+def test_nested_dissection_is_deterministic_across_threads():
+    """The library's ND calls use a thread-local rand() (glibc's is one locked, shared stream): orderings computed
+    concurrently on different threads must equal the one computed alone (symbolic.cpp)."""
+    import threading
+    import scipy.sparse as sp
+    from geneo4petsc_b200.api import Symbolic
+    s = 14
+    eye, t = sp.identity(s, format="csr"), sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(s, s), format="csr")
+    a = (sp.kron(sp.kron(t, eye), eye) + sp.kron(sp.kron(eye, t), eye) + sp.kron(sp.kron(eye, eye), t)).tocsr()
+    ref = Symbolic(a)
+    out = [None] * 4
+
+    def work(i):
+        out[i] = Symbolic(a)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [th.start() for th in ths]
+    [th.join() for th in ths]
+    for o in out:
+        assert np.array_equal(o.perm, ref.perm) and o.info["lSize"] == ref.info["lSize"]
+
+
+def test_chain_panels_share_the_update_matrix_of_their_child():
+    """Front::inplace: panel p+1 of a supernode works on the trailing block of panel p's update matrix (chain arena)."""
+    import scipy.sparse as sp
+    from geneo4petsc_b200.api import Symbolic
+    s = 10
+    eye, t = sp.identity(s, format="csr"), sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(s, s), format="csr")
+    a = (sp.kron(sp.kron(t, eye), eye) + sp.kron(sp.kron(eye, t), eye) + sp.kron(sp.kron(eye, eye), t)).tocsr()
+    sym = Symbolic(a, nb=8)  # narrow panels: long chains
+    fr = sym.fronts
+    inpl = np.nonzero(fr[:, 15] == 1)[0]
+    assert len(inpl) > 10 and sym.info["cArena"] > 0
+    for f in inpl:
+        c = f - 1
+        assert fr[c, 5] == 1 and fr[c, 3] == f and fr[f, 6] == 1          # chain link, only child
+        assert fr[f, 14] == fr[c, 14] == 2 and fr[f, 13] == fr[c, 13]      # same arena, same leading dimension
+        assert fr[f, 9] == fr[c, 9] + fr[f, 1] * (fr[c, 13] + 1)           # trailing block
+        m = fr[f, 2] - fr[f, 1]
+        assert fr[f, 9] + (m - 1) * fr[f, 13] + m <= sym.info["cArena"]
