@@ -243,3 +243,31 @@ def test_block16_eigensolver_uses_the_16_rhs_solve(lap3d):
     y8, y16, yo = pc8.apply(x), pc16.apply(x), rep.pc.apply(x)
     assert np.linalg.norm(y16 - yo) <= 1e-8 * np.linalg.norm(yo)
     assert np.linalg.norm(y16 - y8) <= 1e-8 * np.linalg.norm(y8)
+
+
+def test_cli_reproduces_the_reference_logs(dummy_goldens, dummy_inputs):
+    """The PETSc-free driver (geneo4petsc_b200/geneo4PETSc) run with the command lines of tst/dummy/dummy.sh against the
+    reference's golden logs: local matrices, B, the converged X, and the INFO lines (only the solver names after L1 / L2
+    differ: ldlt / blocklanczos instead of mumps / arpack)."""
+    import os
+    import re
+    import subprocess
+    from tests._cases import driver_command, parse_driver_log
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "geneo4petsc_b200", "geneo4PETSc")
+    names = ["tridiag-pc=geneoASM1-metis=dual", "tridiag-pc=geneoASMH1-metis=dual-opt=overlap1", "tridiag-pc=geneoSORAS2-metis=dual",
+             "tridiag-pc=geneoSORASE2-metis=dual-opt=offload", "identity-pc=geneoASM0-metis=dual", "identity-pc=geneoASME1-metis=dual",
+             "identity-pc=geneoSORASH2-metis=dual-opt=overlap1", "tridiag-pc=geneoSORAS0-metis=dual"]
+
+    def norm(line):
+        line = re.sub(r"L1 \S+", "L1 *", line)
+        return re.sub(r"L2 .*$", "L2 *", line)
+
+    for name in names:
+        g = dummy_goldens["goldens"][name]
+        r = subprocess.run([exe] + driver_command(name, g, dummy_inputs), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (name, r.stdout[-400:], r.stderr[-400:])
+        got = parse_driver_log(r.stdout)
+        assert got["mats"] == g["mats"], name
+        np.testing.assert_allclose(got["b"], g["b"], rtol=1e-6, err_msg=name)
+        np.testing.assert_allclose(got["x"], g["x"], rtol=1e-5, atol=1e-9, err_msg=name)
+        assert [norm(l) for l in got["info"]] == [norm(l) for l in g["info"]], (name, got["info"], g["info"])
