@@ -8,8 +8,10 @@
  * loudly when no CUDA device is present.  Entry points are NOT re-entrant (same as the reference).
  *
  * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
- * The PETSc-facing adapter that re-exports createGenEOPC / PCGenEOSetup / initGenEOPC on top of this ABI is in
- * geneo4petsc_b200/csrc/petsc_adapter/ (compiled only where petsc.h exists) and described in INTEGRATION.md.
+ * The PETSc-facing adapter that re-exports createGenEOPC / PCGenEOSetup / initGenEOPC on top of this ABI cannot be compiled in
+ * this image (no petsc.h, no MPI): INTEGRATION.md section 2 holds the translation unit a maintainer adds on the reference
+ * side; the pre-decomposed input it feeds (geneo_problem_begin_subdomains / _set_subdomain / _end_subdomains) and the PETSc-free
+ * driver with the reference's command line (geneo4petsc_b200/csrc/cli.cpp -> geneo4petsc_b200/geneo4PETSc) are built and tested.
  */
 #ifndef GENEO_B200_H
 #define GENEO_B200_H
