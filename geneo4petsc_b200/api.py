@@ -332,7 +332,7 @@ class Symbolic:
         self.info = {k: int(v) for k, v in zip(keys, i)}
         self.info["flops"] = float(r[0])
         self.perm = np.zeros(self.n, dtype=np.int32)
-        self.fronts = np.zeros((self.info["nfronts"], 16), dtype=np.int64)
+        self.fronts = np.zeros((self.info["nfronts"], 17), dtype=np.int64)
         self.row_idx = np.zeros(self.info["nRowIdx"], dtype=np.int32)
         self.rel = np.zeros(max(1, self.info["nRel"]), dtype=np.int32)
         self.asm_src = np.zeros(self.info["nAsm"], dtype=np.int64)

@@ -580,9 +580,9 @@ int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32
   if (fronts)
     for (size_t f = 0; f < S.fronts.size(); f++) {
       const Front& F = S.fronts[f];
-      const int64_t v[16] = {F.col0, F.k, F.h, F.parent, F.level, F.chain, F.nchild, F.rowOff, F.lOff, F.uOff, F.wOff, F.relOff, F.ld,
-                             F.uLd, F.uArena, F.inplace};
-      std::copy(v, v + 16, fronts + 16 * f);
+      const int64_t v[17] = {F.col0, F.k, F.h, F.parent, F.level, F.chain, F.nchild, F.rowOff, F.lOff, F.uOff, F.wOff, F.relOff, F.ld,
+                             F.uLd, F.uArena, F.inplace, F.pair};
+      std::copy(v, v + 17, fronts + 17 * f);
     }
   if (rowIdx) std::copy(S.rowIdx.begin(), S.rowIdx.end(), rowIdx);
   if (rel) std::copy(S.rel.begin(), S.rel.end(), rel);

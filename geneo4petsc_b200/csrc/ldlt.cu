@@ -49,9 +49,13 @@ __device__ __forceinline__ void cp_async_wait_g() { asm volatile("cp.async.wait_
 // C (+)= A B^T on one 64x64 tile.  All 128 threads of the CTA call this with identical arguments.  The operands travel
 // global -> shared with cp.async through a GEMM_STAGES-deep ring (no register staging: 4-5 CTAs per SM keep the DMMA pipe
 // fed while another CTA is in its prologue or read-modify-writing its C tile); one __syncthreads per K chunk.
+// The K dimension may come in TWO segments (A | A2)(B | B2)^T with their own leading dimensions (K2 = 0: one segment): the
+// rank-256 trailing update of a chain pair multiplies the panels of two consecutive fronts in one pass over the C tile.
 template <int GEMM_STAGES>
 __device__ void gemm_tile_nt(const double* __restrict__ A, int lda, int M, const double* __restrict__ B, int ldb,
-                             int N, int K, double* __restrict__ C, int ldc, int mode, double* smem) {
+                             int N, int K, double* __restrict__ C, int ldc, int mode, double* smem,
+                             const double* __restrict__ A2 = nullptr, int lda2 = 0, const double* __restrict__ B2 = nullptr,
+                             int ldb2 = 0, int K2 = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 1, wn = warp >> 1;
   const int lr = tid & 63;   // row loaded by this thread
@@ -70,19 +74,22 @@ __device__ void gemm_tile_nt(const double* __restrict__ A, int lda, int M, const
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.;
 
-  const int nch = (K + KC - 1) / KC;
+  const int nch1 = (K + KC - 1) / KC;
+  const int nch = nch1 + (K2 + KC - 1) / KC;
   const bool aok = lr < M, bok = lr < N;
-  const double* Ar = A + (aok ? lr : 0);
-  const double* Br = B + (bok ? lr : 0);
   auto issue = [&](int ch) {  // chunk ch -> stage ch % GEMM_STAGES
     double* a = smem + (ch % GEMM_STAGES) * (2 * KC * SLD);
     double* b = a + KC * SLD;
+    const bool seg2 = ch >= nch1;
+    const double* Ar = (seg2 ? A2 : A) + (aok ? lr : 0);
+    const double* Br = (seg2 ? B2 : B) + (bok ? lr : 0);
+    const int la = seg2 ? lda2 : lda, lb = seg2 ? ldb2 : ldb, Ks = seg2 ? K2 : K, k0 = (seg2 ? ch - nch1 : ch) * KC;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const int kl = lk + 2 * i, kk = ch * KC + kl;
-      const bool kok = kk < K;
-      cp_async8(a + kl * SLD + lr, Ar + (size_t)(kok ? kk : 0) * lda, (aok && kok) ? 8 : 0);
-      cp_async8(b + kl * SLD + lr, Br + (size_t)(kok ? kk : 0) * ldb, (bok && kok) ? 8 : 0);
+      const int kl = lk + 2 * i, kk = k0 + kl;
+      const bool kok = kk < Ks;
+      cp_async8(a + kl * SLD + lr, Ar + (size_t)(kok ? kk : 0) * la, (aok && kok) ? 8 : 0);
+      cp_async8(b + kl * SLD + lr, Br + (size_t)(kok ? kk : 0) * lb, (bok && kok) ? 8 : 0);
     }
   };
 #pragma unroll
@@ -311,16 +318,35 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_panel(const WorkItem* __restri
 }
 
 template <int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS) k_schur(const WorkItem* __restrict__ items,
+__global__ void __launch_bounds__(GEMM_THREADS, 5) k_schur(const WorkItem* __restrict__ items,
                                                         const FrontDev* __restrict__ fr, const double* __restrict__ L,
                                                         const double* __restrict__ W, UArenas ua) {
   extern __shared__ __align__(16) double gsm[];
   const WorkItem it = items[blockIdx.x];
   const FrontDev F = fr[it.f];
   const int m = F.h - F.k, k = F.k, h = F.ld;
+  // first panel of a chain pair: EXACTLY the columns the next panel assembles (its k' pivot columns, not rounded up to the
+  // tile: the rank-256 update of the next level covers everything from column k' on)
+  const int ncols = F.pair == 1 ? min(m, fr[it.f + 1].k) : m;
   // U[ti, tj] -= L21[ti rows, :] * W[tj rows, :]^T   (lower triangle of tiles only)
   gemm_tile_nt<STAGES>(L + F.lOff + k + it.a * TS, h, min(TS, m - it.a * TS), W + F.wOff + it.b * TS, m,
-               min(TS, m - it.b * TS), k, ua.a[F.uArena] + F.uOff + it.a * TS + (size_t)it.b * TS * F.uLd, F.uLd, 1, gsm);
+               min(TS, ncols - it.b * TS), k, ua.a[F.uArena] + F.uOff + it.a * TS + (size_t)it.b * TS * F.uLd, F.uLd, 1, gsm);
+}
+
+// Second panel of a chain pair: U -= [L21_prev(rows below this panel's pivots) | L21] [W_prev(same rows) | W]^T, K = k_prev + k.
+// The first panel of the pair only updated the strip of U this panel assembled (its own k pivot columns).
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 5) k_schur2(const WorkItem* __restrict__ items, const FrontDev* __restrict__ fr,
+                                                         const double* __restrict__ L, const double* __restrict__ Wcur,
+                                                         const double* __restrict__ Wprev, UArenas ua) {
+  extern __shared__ __align__(16) double gsm[];
+  const WorkItem it = items[blockIdx.x];
+  const FrontDev F = fr[it.f];
+  const FrontDev Pf = fr[it.f - 1];
+  const int m = F.h - F.k, k = F.k, pm = Pf.h - Pf.k;
+  gemm_tile_nt<STAGES>(L + Pf.lOff + Pf.k + k + it.a * TS, Pf.ld, min(TS, m - it.a * TS), Wprev + Pf.wOff + k + it.b * TS, pm,
+                       min(TS, m - it.b * TS), Pf.k, ua.a[F.uArena] + F.uOff + it.a * TS + (size_t)it.b * TS * F.uLd, F.uLd, 1, gsm,
+                       L + F.lOff + k + it.a * TS, F.ld, Wcur + F.wOff + it.b * TS, m, k);
 }
 
 // =====================================================================================================================
@@ -1006,10 +1032,12 @@ static int gemm_stages() {  // cp.async pipeline depth of the DMMA tile kernels:
       CUDA_CHECK(cudaFuncSetAttribute((const void*)k_dgemm_nt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CUDA_CHECK(cudaFuncSetAttribute((const void*)k_panel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CUDA_CHECK(cudaFuncSetAttribute((const void*)k_schur<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_schur2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     } else {
       CUDA_CHECK(cudaFuncSetAttribute((const void*)k_dgemm_nt<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CUDA_CHECK(cudaFuncSetAttribute((const void*)k_panel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CUDA_CHECK(cudaFuncSetAttribute((const void*)k_schur<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CUDA_CHECK(cudaFuncSetAttribute((const void*)k_schur2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     }
     return st;
   }();
@@ -1046,7 +1074,7 @@ void LdltPlan::build_host() {
   fd.assign(nf, FrontDev());
   for (int f = 0; f < nf; f++) {
     const Front& F = sym.fronts[f];
-    fd[f] = FrontDev{F.lOff, F.uOff, F.wOff, F.rowOff, F.relOff, F.k, F.h, F.ld, F.parent, F.nchild, F.uLd, F.uArena, F.inplace, 0};
+    fd[f] = FrontDev{F.lOff, F.uOff, F.wOff, F.rowOff, F.relOff, F.k, F.h, F.ld, F.parent, F.nchild, F.uLd, F.uArena, F.inplace, F.pair};
   }
   std::vector<WorkItem>& items = hostItems_;
   items.clear();
@@ -1054,6 +1082,7 @@ void LdltPlan::build_host() {
   auto end = [&](Range& r) { r.cnt = (int)((int64_t)items.size() - r.off); };
   const int nl = sym.nlevels;
   eaddItems.resize(nl); diagItems.resize(nl); diagSmallItems.resize(nl); copyItems.resize(nl); panelItems.resize(nl); schurItems.resize(nl);
+  schur2Items.resize(nl);
   levelU.assign(nl, 0);
   levelChainZero.assign(nl, {});
   for (int l = 0; l < nl; l++) {
@@ -1104,10 +1133,21 @@ void LdltPlan::build_host() {
     begin(schurItems[l]);
     for (int t = 0; t < cnt; t++) {
       const Front& F = sym.fronts[lf[t]];
+      if (F.pair == 2) continue;
+      // first of a chain pair: only the column tiles the next panel assembles; the rest waits for the rank-256 update
+      const int ncolTiles = F.pair == 1 ? (std::min(F.m(), sym.fronts[lf[t] + 1].k) + TS - 1) / TS : (F.m() + TS - 1) / TS;
+      for (int ti = 0; ti * TS < F.m(); ti++)
+        for (int tj = 0; tj <= ti && tj < ncolTiles; tj++) items.push_back(WorkItem{lf[t], ti, tj});
+    }
+    end(schurItems[l]);
+    begin(schur2Items[l]);
+    for (int t = 0; t < cnt; t++) {
+      const Front& F = sym.fronts[lf[t]];
+      if (F.pair != 2) continue;
       for (int ti = 0; ti * TS < F.m(); ti++)
         for (int tj = 0; tj <= ti; tj++) items.push_back(WorkItem{lf[t], ti, tj});
     }
-    end(schurItems[l]);
+    end(schur2Items[l]);
   }
 
 }
@@ -1136,7 +1176,7 @@ size_t LdltPlan::plan_bytes() const {
 void LdltWorkspace::ensure(const Symbolic& s) {
   if ((int64_t)u0.n < s.uArena) { u0.alloc((size_t)s.uArena); u1.alloc((size_t)s.uArena); }
   if ((int64_t)uc.n < s.cArena) uc.alloc((size_t)s.cArena);
-  if ((int64_t)w.n < s.wArena) w.alloc((size_t)s.wArena);
+  if ((int64_t)w0.n < s.wArena) { w0.alloc((size_t)s.wArena); w1.alloc((size_t)s.wArena); }
   if (counters.n < 2) counters.alloc(2);
 }
 
@@ -1164,6 +1204,8 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
   const UArenas ua{{ws.u0.p, ws.u1.p, ws.uc.p}};
   for (int l = 0; l < S.nlevels; l++) {
     double* Ucur = (l & 1) ? ws.u1.p : ws.u0.p;
+    double* Wcur = (l & 1) ? ws.w1.p : ws.w0.p;
+    const double* Wprev = (l & 1) ? ws.w0.p : ws.w1.p;
     if (P.levelU[l] > 0) CUDA_CHECK(cudaMemsetAsync(Ucur, 0, (size_t)P.levelU[l] * sizeof(double), st));
     for (auto& z : P.levelChainZero[l]) CUDA_CHECK(cudaMemsetAsync(ws.uc.p + z.first, 0, (size_t)z.second * sizeof(double), st));
     if (P.eaddItems[l].cnt)
@@ -1173,14 +1215,18 @@ FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorksp
     if (P.diagSmallItems[l].cnt)
       k_diag_invert<32, 8><<<GENEO_TICK(P.diagSmallItems[l].cnt), 64, 0, st>>>(items + P.diagSmallItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
     if (P.copyItems[l].cnt)
-      k_copy_panel<<<GENEO_TICK(P.copyItems[l].cnt), 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, L.p, ws.w.p);
+      k_copy_panel<<<GENEO_TICK(P.copyItems[l].cnt), 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, L.p, Wcur);
     if (P.panelItems[l].cnt) {
-      if (gst == 2) k_panel<2><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
-      else k_panel<3><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, ws.w.p);
+      if (gst == 2) k_panel<2><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, Wcur);
+      else k_panel<3><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, Wcur);
     }
     if (P.schurItems[l].cnt) {
-      if (gst == 2) k_schur<2><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, ua);
-      else k_schur<3><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, ws.w.p, ua);
+      if (gst == 2) k_schur<2><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, Wcur, ua);
+      else k_schur<3><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, Wcur, ua);
+    }
+    if (P.schur2Items[l].cnt) {
+      if (gst == 2) k_schur2<2><<<GENEO_TICK(P.schur2Items[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schur2Items[l].off, P.dFronts.p, L.p, Wcur, Wprev, ua);
+      else k_schur2<3><<<GENEO_TICK(P.schur2Items[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schur2Items[l].off, P.dFronts.p, L.p, Wcur, Wprev, ua);
     }
     CUDA_CHECK(cudaGetLastError());
   }

@@ -10,7 +10,7 @@ namespace geneo {
 struct FrontDev {  // device copy of what the kernels need from symbolic.hpp:Front
   int64_t lOff, uOff, wOff, rowOff, relOff;
   int k, h, ld, parent, nchild;
-  int uLd, uArena, inplace, pad;
+  int uLd, uArena, inplace, pair;
 };
 struct UArenas { double* a[3]; };  // ping-pong arenas 0/1 + chain arena 2 (Front::uArena)
 
@@ -34,6 +34,7 @@ class LdltPlan {
   DevBuf<WorkItem> dItems;  // all item lists, concatenated
   struct Range { int64_t off = 0; int cnt = 0; };
   std::vector<Range> eaddItems, diagItems, diagSmallItems, copyItems, panelItems, schurItems;  // per level (factor)
+  std::vector<Range> schur2Items;  // per level: trailing updates of the second panels of chain pairs (K = two panels)
   std::vector<int64_t> levelU;                                                 // doubles of the ping-pong arena used per level
   std::vector<std::vector<std::pair<int64_t, int64_t>>> levelChainZero;        // (offset, doubles) of the chain blocks born at a level
   DevBuf<int> dPerm;                                                           // new -> old
@@ -95,7 +96,8 @@ struct FactorStats { int neg = 0, perturbed = 0; double seconds = 0.; };
 
 // Shared scratch for numeric factorizations (two ping-pong update arenas + the per-level panel scratch).
 struct LdltWorkspace {
-  DevBuf<double> u0, u1, uc, w;  // ping-pong update arenas, chain arena, per-level panel scratch
+  DevBuf<double> u0, u1, uc;     // ping-pong update arenas, chain arena
+  DevBuf<double> w0, w1;         // per-level scratch of the unscaled panels, by level parity (a chain pair reads the previous level's)
   DevBuf<double> spareL;  // storage of the transient factors (inertia / shift-invert), recycled between subdomains
   DevBuf<int> counters;  // [0] negative pivots, [1] perturbed pivots
   void ensure(const Symbolic& s);

@@ -479,6 +479,18 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
     S.wArena = std::max(S.wArena, w);
   }
 
+  if (opt.chainInplace && opt.chainPairs)
+    for (int f = 0; f < nf; f++) {  // chains start at a fresh front followed by in-place panels: pair them up two by two
+      if (!(S.fronts[f].chain && !S.fronts[f].inplace && S.fronts[f].m() > 0)) continue;
+      int last = f;
+      while (S.fronts[last].chain) last++;
+      for (int i = f; i + 1 <= last; i += 2) {
+        if (!S.fronts[i + 1].inplace) break;
+        S.fronts[i].pair = 1;
+        S.fronts[i + 1].pair = 2;
+      }
+    }
+
   lap("fronts+levels");
   // ---- 7. scatter map of the input values (lower triangle of P A P^T) into the panels --------------------------------
   S.perm = perm;

@@ -31,6 +31,10 @@ struct Front {
   int64_t uOff = -1;   // into update arena `uArena`; the update matrix is m x m (lower triangle used) with leading dimension uLd
   int uLd = 0;         // leading dimension of the update matrix storage
   int uArena = 0;      // 0/1: ping-pong arena of parity (level & 1) -- consumed by the next level; 2: chain arena
+  int pair = 0;        // rank-256 trailing updates along a chain: 1 = first of a pair (only the strip of its update matrix
+                       // that the next panel assembles is updated at its own level), 2 = second of a pair (its Schur
+                       // update applies BOTH panels at once: K = k_prev + k, one read-modify-write of the update matrix
+                       // for two panels); 0 = ordinary rank-k update
   int inplace = 0;     // 1: non-first panel of a supernode -- its update matrix IS the trailing block of its (only)
                        // child's update matrix (same storage, uOff = child.uOff + k (uLd + 1)): nothing is copied or
                        // zeroed along a supernode chain, the child only adds its first k columns to this panel
@@ -69,6 +73,7 @@ struct SymbolicOptions {
   int ordering = 1;    // 0 natural, 1 METIS NodeND
   bool amalgamate = true;
   bool chainInplace = true;  // update matrices of supernode chains stay in place (see Front::inplace)
+  bool chainPairs = true;    // rank-256 trailing updates along in-place chains (see Front::pair)
   int subtreeCols = 64; // subtrees of the assembly tree with at most this many columns are merged into one dense front
   int ndDepth = 0;     // top levels of the nested dissection done here (METIS_ComputeVertexSeparator) with the two halves
                        // ordered by concurrent threads: 2^ndDepth threads per matrix; 0 = plain METIS_NodeND

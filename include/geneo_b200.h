@@ -164,7 +164,7 @@ int geneo_symbolic_create(int n, const int64_t* ptr, const int32_t* idx, int nb,
 int geneo_symbolic_destroy(geneo_symbolic_t s);
 /* ints = {n, nfronts, nlevels, lSize, uArena, wArena, nRowIdx, nRel, nAsm, nsuper, cArena} ; reals = {flops} */
 int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[11], double reals[1]);
-/* fronts: 16 int64 per front = {col0,k,h,parent,level,chain,nchild,rowOff,lOff,uOff,wOff,relOff,ld,uLd,uArena,inplace} */
+/* fronts: 17 int64 per front = {col0,k,h,parent,level,chain,nchild,rowOff,lOff,uOff,wOff,relOff,ld,uLd,uArena,inplace,pair} */
 int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32_t* rowIdx, int32_t* rel, int64_t* asmSrc,
                        int64_t* asmDst);
 int geneo_host_sym_eig(int n, double* a /* row-major in, eigenvectors (columns) out */, double* w);

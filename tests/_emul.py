@@ -4,7 +4,7 @@ relative indices, levels and arena offsets on a CPU-only box."""
 import numpy as np
 
 (F_COL0, F_K, F_H, F_PARENT, F_LEVEL, F_CHAIN, F_NCHILD, F_ROWOFF, F_LOFF, F_UOFF, F_WOFF, F_RELOFF, F_LD, F_ULD, F_UARENA,
- F_INPLACE) = range(16)
+ F_INPLACE, F_PAIR) = range(17)
 
 
 def _umat(arenas, fr, f):
@@ -30,6 +30,7 @@ def factorize(sym, vals):
     arenas = [np.full(max(1, sym.info["uArena"]), np.nan), np.full(max(1, sym.info["uArena"]), np.nan),
               np.full(max(1, sym.info["cArena"]), np.nan)]
     neg = 0
+    Wbuf = [np.full(max(1, sym.info["wArena"]), np.nan), np.full(max(1, sym.info["wArena"]), np.nan)]
     order = np.argsort(fr[:, F_LEVEL], kind="stable")
     levels = fr[:, F_LEVEL]
     for lvl in range(sym.info["nlevels"]):
@@ -38,7 +39,9 @@ def factorize(sym, vals):
             if fr[f, F_H] > fr[f, F_K] and fr[f, F_UARENA] == 2 and not fr[f, F_INPLACE]:
                 m = fr[f, F_H] - fr[f, F_K]
                 arenas[2][fr[f, F_UOFF]: fr[f, F_UOFF] + m * m] = 0.0
-        W = np.zeros(max(1, sym.info["wArena"]))
+        W = Wbuf[lvl & 1]  # the unscaled panels of a level live in the scratch of its parity: the second panel of a pair reads
+        Wprev = Wbuf[(lvl & 1) ^ 1]  # the first one's a level later
+        W[:] = np.nan
         if lvl > 0:  # extend-add children (level lvl-1) into their parents
             for c in order[levels[order] == lvl - 1]:
                 k, h, par = fr[c, F_K], fr[c, F_H], fr[c, F_PARENT]
@@ -89,9 +92,24 @@ def factorize(sym, vals):
                 Wf[:, :] = F21
                 P[k:, :] = F21 @ Dinv
                 U = _umat(arenas, fr, f)
-                upd = P[k:, :] @ F21.T
                 il = np.tril_indices(m)
-                U[il] -= upd[il]  # the device writes whole 64x64 tiles; only the lower triangle is ever read
+                if fr[f, F_PAIR] == 1:  # first of a pair: only the strip the next panel assembles (its k' pivot columns)
+                    assert fr[f + 1, F_PAIR] == 2 and fr[f + 1, F_INPLACE] == 1 and fr[f, F_PARENT] == f + 1
+                    kn = fr[f + 1, F_K]
+                    upd = P[k:, :] @ F21[:kn, :].T
+                    strip = il[1] < kn
+                    U[il[0][strip], il[1][strip]] -= upd[il[0][strip], il[1][strip]]
+                elif fr[f, F_PAIR] == 2:  # second of a pair: both panels at once on the trailing block (K = k_prev + k)
+                    pf = f - 1
+                    assert fr[pf, F_PAIR] == 1 and fr[pf, F_LEVEL] == lvl - 1
+                    pk, pm = fr[pf, F_K], fr[pf, F_H] - fr[pf, F_K]
+                    Pp = _panel(L, fr, pf)
+                    Wp = Wprev[fr[pf, F_WOFF]: fr[pf, F_WOFF] + pm * pk].reshape(pm, pk, order="F")
+                    upd = P[k:, :] @ F21.T + Pp[pk + k:, :] @ Wp[k:, :].T
+                    U[il] -= upd[il]
+                else:
+                    upd = P[k:, :] @ F21.T
+                    U[il] -= upd[il]  # the device writes whole 64x64 tiles; only the lower triangle is ever read
     return L, neg
 
 
