@@ -245,3 +245,24 @@ def test_cli_rejects_bad_command_lines():
         assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
     r = subprocess.run([exe, "--help"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "usage: geneo4PETSc" in r.stderr
+
+
+def test_chain_pairs_cover_every_update_exactly_once():
+    """Front::pair (rank-256 trailing updates): pairs are (first, second) = consecutive panels of an in-place chain; the
+    first only updates the strip its successor assembles, the second applies both panels to the trailing block.  The
+    numpy emulation of the device phase (tests/_emul.py) factorizes with exactly these roles and must still solve."""
+    from geneo4petsc_b200.api import Symbolic
+    s = 9
+    eye, t = sp.identity(s, format="csr"), sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(s, s), format="csr")
+    a = (sp.kron(sp.kron(t, eye), eye) + sp.kron(sp.kron(eye, t), eye) + sp.kron(sp.kron(eye, eye), t) + 0.1 * sp.identity(s ** 3)).tocsr()
+    sym = Symbolic(a, nb=6)  # panels of 6 columns (not a multiple of the 64-wide device tile): long chains, ragged strips
+    fr = sym.fronts
+    first, second = np.nonzero(fr[:, 16] == 1)[0], np.nonzero(fr[:, 16] == 2)[0]
+    assert len(first) > 5 and np.array_equal(first + 1, second)
+    for f in first:
+        assert fr[f, 5] == 1 and fr[f, 3] == f + 1 and fr[f + 1, 15] == 1 and fr[f + 1, 4] == fr[f, 4] + 1
+    L, neg = _emul.factorize(sym, a.data)
+    assert neg == 0
+    b = np.random.default_rng(4).standard_normal(a.shape[0])
+    x = _emul.solve(sym, L, b)
+    assert np.linalg.norm(a @ x - b) <= 1e-10 * np.linalg.norm(b)
