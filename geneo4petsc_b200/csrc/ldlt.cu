@@ -1,15 +1,20 @@
 // ldlt.cu -- numeric block LDL^T multifrontal factorization and level-scheduled solves on sm_100a.
 //
-// Kernels (all batched over one schedule level, work lists precomputed on the host, see symbolic.hpp):
+// Factorization kernels (all batched over one schedule level, work lists precomputed on the host, see symbolic.hpp):
 //   k_assemble      scatter the input CSR values (lower triangle, permuted) into the panels
-//   k_extend_add    child update matrix -> parent panel / parent update matrix (relative indices)
+//   k_extend_add    child update matrix -> parent panel / parent update matrix (relative indices); along a supernode chain
+//                   only the parent's panel columns: the update matrix itself stays in place (Front::inplace)
 //   k_diag_invert   one CTA per front: symmetric sweep inversion of the k x k pivot block held in REGISTERS
 //                   (8x8 per thread, 256 threads), pivot signs give the inertia (Sylvester, src/geneo.cpp:452-500)
 //   k_copy_panel    W = F21 (unscaled panel, needed by the Schur product)
-//   k_panel / k_schur  64x64 tiles of  L21 = W * D^-1   and   U -= L21 * W^T   on the FP64 tensor pipe
-//                   (mma.sync.m8n8k4.f64 -- FP64 has no tcgen05 path), smem double-buffered, 4 warps x (32x32)
-//   k_fwd / k_dsolve / k_bwd   warp-per-(front,row block) rectangular GEMV sweeps; the factor is streamed exactly
-//                   once per sweep with fully coalesced 256-byte warp loads (HBM-bound by design)
+//   k_panel / k_schur / k_schur2   64x64 tiles of  L21 = W * D^-1 ,  U -= L21 * W^T  and (second panel of a chain pair)
+//                   U -= [L21_prev | L21] [W_prev | W]^T  on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -- FP64 has no
+//                   tcgen05 path), operands global -> shared with cp.async, double-buffered, 5 CTAs per SM
+// Solve kernels:
+//   k_solve_ring<1 | 8 | 16>   ONE persistent cooperative launch per solve over a forest of factors; the factor tiles stream
+//                   through warp-private cp.async rings that run ahead of the arithmetic across items and level barriers
+//                   (HBM-bound by design); 8 / 16 right-hand sides use DMMA fragments
+//   k_solve_forest<2 | 4>      generic level-scheduled kernels for the other block widths
 #include "ldlt.hpp"
 
 #include <cooperative_groups.h>
