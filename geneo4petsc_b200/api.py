@@ -240,6 +240,12 @@ class GeneoPC:
         keys = ["factor_bytes", "factor_nnz", "factor_flops", "trisolve_bytes", "apply_bytes", "spmv_bytes", "applies", "sum_ni"]
         return dict(zip(keys, s.tolist()))
 
+    def factor_stats(self):
+        """every numeric factorization of the last (re-)setup: device seconds, flops, count; host seconds of the shared ordering."""
+        s = np.zeros(4)
+        _chk(lib.geneo_pc_factor_stats(self.h, _p(s, _f64p)))
+        return dict(seconds=s[0], flops=s[1], count=int(s[2]), ordering_reuse_s=s[3])
+
     def sub_info(self, s):
         i, r = np.zeros(8, dtype=np.int64), np.zeros(2)
         _chk(lib.geneo_pc_sub_info(self.h, C.c_int(s), _p(i, _i64p), _p(r, _f64p)))
@@ -315,17 +321,35 @@ class GeneoPC:
                     history=hist[: int(out[2])].copy())
 
 
+def box_ordering(dims, stencil=((1, 0, 0), (0, 1, 0), (0, 0, 1)), threads=1):
+    """rank[x + d0 (y + d1 z)] of the reference nested dissection of a box (host only)."""
+    d = np.ascontiguousarray(dims, dtype=np.int32)
+    st = np.ascontiguousarray(stencil, dtype=np.int32).reshape(-1, 3)
+    rank = np.zeros(int(d[0]) * int(d[1]) * int(d[2]), dtype=np.int32)
+    _chk(lib.geneo_box_ordering(_p(d, _i32p), C.c_int(len(st)), _p(st, _i32p), C.c_int(threads), _p(rank, _i32p)))
+    return rank
+
+
 class Symbolic:
     """Host-only view of the symbolic analysis (test hook)."""
 
-    def __init__(self, a_csr, nb=128, ordering=1, amalgamate=True):
+    def __init__(self, a_csr, nb=128, ordering=1, amalgamate=True, coords=None, perm=None):
         a = a_csr.tocsr()
         self.n = a.shape[0]
         ptr = np.ascontiguousarray(a.indptr, dtype=np.int64)
         idx = np.ascontiguousarray(a.indices, dtype=np.int32)
         self.h = C.c_void_p()
-        _chk(lib.geneo_symbolic_create(C.c_int(self.n), _p(ptr, _i64p), _p(idx, _i32p), C.c_int(nb), C.c_int(ordering),
-                                       C.c_int(1 if amalgamate else 0), C.byref(self.h)))
+        if perm is not None:    # caller-supplied permutation (new -> old)
+            pp = np.ascontiguousarray(perm, dtype=np.int32)
+            _chk(lib.geneo_symbolic_create_perm(C.c_int(self.n), _p(ptr, _i64p), _p(idx, _i32p), C.c_int(nb),
+                                                C.c_int(1 if amalgamate else 0), _p(pp, _i32p), C.byref(self.h)))
+        elif coords is not None:  # geometric nested dissection on integer vertex coordinates (n x 3)
+            xyz = np.ascontiguousarray(coords, dtype=np.int32).reshape(self.n, 3)
+            _chk(lib.geneo_symbolic_create_geo(C.c_int(self.n), _p(ptr, _i64p), _p(idx, _i32p), C.c_int(nb),
+                                               C.c_int(1 if amalgamate else 0), _p(xyz, _i32p), C.byref(self.h)))
+        else:
+            _chk(lib.geneo_symbolic_create(C.c_int(self.n), _p(ptr, _i64p), _p(idx, _i32p), C.c_int(nb), C.c_int(ordering),
+                                           C.c_int(1 if amalgamate else 0), C.byref(self.h)))
         i, r = np.zeros(11, dtype=np.int64), np.zeros(1)
         _chk(lib.geneo_symbolic_info(self.h, _p(i, _i64p), _p(r, _f64p)))
         keys = ["n", "nfronts", "nlevels", "lSize", "uArena", "wArena", "nRowIdx", "nRel", "nAsm", "nsuper", "cArena"]

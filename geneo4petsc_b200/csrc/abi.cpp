@@ -124,6 +124,11 @@ int geneo_problem_decompose(geneo_problem_t p, int nbPart, int metisDual, int ov
 }
 // ---- pre-decomposed input (the PETSc plug-in's view: initGenEOPC / PCGenEOSetup) -----------------------------------------
 static void csr_from_c(int n, const int64_t* ptr, const int32_t* idx, const double* val, CsrHost& a) {
+  if (ptr[0] != 0) throw Error("geneo_b200: local matrix: row pointer must start at 0");
+  for (int r = 0; r < n; r++)
+    if (ptr[r + 1] < ptr[r]) throw Error("geneo_b200: local matrix: row pointer is not monotone");
+  for (int64_t t = 0; t < ptr[n]; t++)
+    if (idx[t] < 0 || idx[t] >= n) throw Error("geneo_b200: local matrix: column index outside [0, n)");
   a.n = a.ncols = n;
   a.ptr.assign(ptr, ptr + n + 1);
   a.idx.assign(idx, idx + ptr[n]);
@@ -160,6 +165,10 @@ int geneo_problem_set_subdomain(geneo_problem_t p, int s, int64_t n, const int32
   S = Subdomain();
   S.id = s;
   S.nodes.assign(globalIds, globalIds + n);
+  for (int64_t l = 0; l < n; l++) {
+    ABI_REQ(globalIds[l] >= 0 && globalIds[l] < p->dec.nbNode, "subdomain: global id out of range");
+    ABI_REQ(l == 0 || globalIds[l - 1] < globalIds[l], "subdomain: global ids must be sorted ascending (the reference's local numbering)");
+  }
   csr_from_c((int)n, neuPtr, neuIdx, neuVal, S.aNeu);
   if (dirPtr && dirIdx && dirVal) csr_from_c((int)n, dirPtr, dirIdx, dirVal, S.aDir);
   ABI_CATCH
@@ -457,6 +466,12 @@ int geneo_pc_stats(geneo_pc_t pc, double stats[8]) {
   stats[6] = (double)g.applyCount; stats[7] = nall;
   ABI_CATCH
 }
+int geneo_pc_factor_stats(geneo_pc_t pc, double out[4]) {
+  ABI_TRY
+  ABI_REQ(pc && pc->ready && out, "GenEO preconditioner without context");
+  out[0] = pc->pc.allFactorSeconds; out[1] = pc->pc.allFactorFlops; out[2] = (double)pc->pc.allFactorCount; out[3] = pc->pc.orderingReuseTime;
+  ABI_CATCH
+}
 int geneo_pc_sub_info(geneo_pc_t pc, int s, int64_t ints[8], double reals[2]) {
   ABI_TRY
   ABI_REQ(pc && pc->ready && s >= 0 && s < (int)pc->pc.subs.size(), "bad subdomain");
@@ -558,6 +573,39 @@ int geneo_symbolic_create(int n, const int64_t* ptr, const int32_t* idx, int nb,
   o.nb = nb; o.ordering = ordering; o.amalgamate = amalgamate != 0;
   try { symbolic_analyze(n, ptr, idx, o, s->s); } catch (...) { delete s; throw; }
   *out = s;
+  ABI_CATCH
+}
+int geneo_symbolic_create_geo(int n, const int64_t* ptr, const int32_t* idx, int nb, int amalgamate, const int32_t* coords,
+                              geneo_symbolic_t* out) {
+  ABI_TRY
+  ABI_REQ(ptr && idx && out && coords && n > 0, "null argument");
+  geneo_symbolic_s* s = new geneo_symbolic_s();
+  SymbolicOptions o;
+  o.nb = nb; o.ordering = 2; o.amalgamate = amalgamate != 0; o.coords = coords;
+  try { symbolic_analyze(n, ptr, idx, o, s->s); } catch (...) { delete s; throw; }
+  *out = s;
+  ABI_CATCH
+}
+int geneo_symbolic_create_perm(int n, const int64_t* ptr, const int32_t* idx, int nb, int amalgamate, const int32_t* perm,
+                               geneo_symbolic_t* out) {
+  ABI_TRY
+  ABI_REQ(ptr && idx && out && perm && n > 0, "null argument");
+  geneo_symbolic_s* s = new geneo_symbolic_s();
+  SymbolicOptions o;
+  o.nb = nb; o.ordering = 3; o.amalgamate = amalgamate != 0; o.userPerm = perm;
+  try { symbolic_analyze(n, ptr, idx, o, s->s); } catch (...) { delete s; throw; }
+  *out = s;
+  ABI_CATCH
+}
+int geneo_box_ordering(const int32_t dims[3], int nst, const int32_t* stencil, int threads, int32_t* rank) {
+  ABI_TRY
+  ABI_REQ(dims && rank && (nst == 0 || stencil), "null argument");
+  int depth = 0;
+  while ((2 << depth) <= threads && depth < 5) depth++;
+  std::vector<int> r;
+  const int d[3] = {dims[0], dims[1], dims[2]};
+  box_reference_ordering(d, nst, stencil, depth, r);
+  std::copy(r.begin(), r.end(), rank);
   ABI_CATCH
 }
 int geneo_symbolic_destroy(geneo_symbolic_t s) { ABI_TRY delete s; ABI_CATCH }

@@ -77,8 +77,13 @@ inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64
 
 }  // namespace
 
-Comm::~Comm() {
+Comm::~Comm() { reset(); }
+
+void Comm::reset() {
   if (comm_) api().CommDestroy((ncclComm_t)comm_);
+  comm_ = nullptr;
+  rank = 0; world = 1; nOwn = nGhost = 0; bufWidth_ = 0;
+  sendPtr_.clear(); recvPtr_.clear();
 }
 
 void Comm::unique_id(void* out128) {
@@ -88,6 +93,7 @@ void Comm::unique_id(void* out128) {
 }
 
 void Comm::init(int rank_, int world_, const void* uid128, const RankLayout& L, cudaStream_t st) {
+  reset();  // a repeated setup gets a fresh communicator
   rank = rank_; world = world_;
   nOwn = L.nOwn(); nGhost = L.nGhost();
   if (world <= 1) return;

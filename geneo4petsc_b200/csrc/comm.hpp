@@ -18,6 +18,7 @@ class Comm {
   int rank = 0, world = 1;
   bool active() const { return world > 1; }
   ~Comm();
+  void reset();  // destroy the communicator, back to the single-process state
   static void unique_id(void* out128);  // ncclGetUniqueId (rank 0), to be broadcast by the caller
   void init(int rank, int world, const void* uid128, const RankLayout& L, cudaStream_t st);
   void allreduce_sum(double* d, int n, cudaStream_t st);      // in place, device buffer

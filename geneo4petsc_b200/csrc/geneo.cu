@@ -2,7 +2,9 @@
 #include "geneo.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <sstream>
@@ -231,6 +233,7 @@ int GeneoOptions::parse(int argc, const char* const* argv, std::string& err) {
     else if (o == "-els2_eps_ncv") { double c; const char* v = need(a, "-els2_eps_ncv"); if (!v || !num(v, c, "-els2_eps_ncv")) return 1; epsMaxDim = (int)c; a++; }
     else if (o == "-geneo_nb") { double c; const char* v = need(a, "-geneo_nb"); if (!v || !num(v, c, "-geneo_nb")) return 1; nb = (int)c; a++; }
     else if (o == "-geneo_ordering") { double c; const char* v = need(a, "-geneo_ordering"); if (!v || !num(v, c, "-geneo_ordering")) return 1; ordering = (int)c; a++; }
+    else if (o == "-geneo_ordering_reuse") { double c; const char* v = need(a, "-geneo_ordering_reuse"); if (!v || !num(v, c, "-geneo_ordering_reuse")) return 1; orderingReuse = c != 0.; a++; }
     else if (o == "-geneo_timing") timing = true;
     else if (o == "-geneo_kernel_timing") kernelTiming = true;
   }
@@ -281,10 +284,100 @@ struct HostPrep {  // everything the host prepares for one subdomain (worker thr
   CsrHost patP;                 // permuted pattern of A_dir with its values
   std::vector<double> vNeuP, vRobP, dP;
   std::vector<int> gidx;
+  std::vector<int> userPerm;    // ordering inherited from the reference box (see plan_ordering_reuse); empty: METIS on this subdomain
   double anorm = 0.;
   int maxMult = 1;
   std::string err;
 };
+
+// Structured problems (Decomposition::grid known): subdomains that fill their common bounding box share ONE nested
+// dissection -- the reference ordering of that box, restricted to each subdomain (symbolic.hpp box_reference_ordering).
+// Box partitions at 8 subdomains per GPU and 8 ranks per node otherwise spend 20 s of host time in 64 METIS calls.
+// Multi-GPU: rank 0 orders the box with every core of the node and the ranks receive it over NCCL.
+void plan_ordering_reuse(const Decomposition& dec, const std::vector<const Subdomain*>& mine, const GeneoOptions& opt, Comm& comm,
+                         unsigned hwAll, cudaStream_t st, std::vector<HostPrep>& prep) {
+  if (opt.ordering != 1 || !opt.orderingReuse || dec.grid[0] <= 0) return;
+  const int P = (int)mine.size();
+  const int64_t n1 = dec.grid[0], n12 = (int64_t)dec.grid[0] * std::max(1, dec.grid[1]);
+  auto coord = [&](int g, int c[3]) { c[0] = (int)(g % n1); c[1] = (int)((g / n1) % std::max(1, dec.grid[1])); c[2] = (int)(g / n12); };
+  std::vector<std::array<int, 3>> lo(P), ext(P);
+  double ref[4] = {0., 0., 0., 0.};  // max extents, number of candidate subdomains
+  for (int p = 0; p < P; p++) {
+    int l[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, h[3] = {-1, -1, -1}, c[3];
+    for (int g : mine[p]->nodes) { coord(g, c); for (int a = 0; a < 3; a++) { l[a] = std::min(l[a], c[a]); h[a] = std::max(h[a], c[a]); } }
+    for (int a = 0; a < 3; a++) { lo[p][a] = l[a]; ext[p][a] = h[a] - l[a] + 1; }
+    // a candidate is (nearly) a full box: induced separators of a ragged METIS part cost ~1.5x the flops of its own ordering
+    const double box = (double)ext[p][0] * ext[p][1] * ext[p][2];
+    if ((double)mine[p]->nodes.size() >= 0.97 * box && mine[p]->nodes.size() >= 20000) {
+      for (int a = 0; a < 3; a++) ref[a] = std::max(ref[a], (double)ext[p][a]);
+      ref[3] += 1.;
+    }
+  }
+  if (comm.active()) {  // global maximum of the extents through a one-hot sum
+    std::vector<double> all(4 * (size_t)comm.world, 0.);
+    for (int a = 0; a < 4; a++) all[4 * (size_t)comm.rank + a] = ref[a];
+    comm.allreduce_sum_host(all.data(), (int)all.size(), st);
+    for (int a = 0; a < 4; a++) ref[a] = 0.;
+    for (int r = 0; r < comm.world; r++) {
+      for (int a = 0; a < 3; a++) ref[a] = std::max(ref[a], all[4 * (size_t)r + a]);
+      ref[3] += all[4 * (size_t)r + 3];
+    }
+  }
+  if (ref[3] < 2.) return;  // nothing to share
+  const int dims[3] = {(int)ref[0], (int)ref[1], (int)ref[2]};
+  const int64_t nref = (int64_t)dims[0] * dims[1] * dims[2];
+  std::vector<int> rank;
+  if (comm.rank == 0) {
+    // stencil of the operator: coordinate offsets met in the rows of the first local subdomain (capped: a wide stencil
+    // means this is not a nearest-neighbour grid problem and the reference box would not be representative)
+    std::vector<int> sten;
+    const Subdomain& S = *mine[0];
+    bool ok = true;
+    for (int r = 0; r < S.aDir.n && ok; r++) {
+      int cr[3], cc[3];
+      coord(S.nodes[r], cr);
+      for (int64_t t = S.aDir.ptr[r]; t < S.aDir.ptr[r + 1]; t++) {
+        coord(S.nodes[S.aDir.idx[t]], cc);
+        const int d[3] = {cc[0] - cr[0], cc[1] - cr[1], cc[2] - cr[2]};
+        if ((d[0] | d[1] | d[2]) == 0) continue;
+        bool have = false;
+        for (size_t q = 0; q < sten.size() && !have; q += 3) have = sten[q] == d[0] && sten[q + 1] == d[1] && sten[q + 2] == d[2];
+        if (!have) { sten.push_back(d[0]); sten.push_back(d[1]); sten.push_back(d[2]); }
+        if (sten.size() > 3 * 64) { ok = false; break; }
+      }
+    }
+    if (ok && !sten.empty()) {
+      int depth = 0;
+      while ((2u << depth) <= hwAll && depth < 4) depth++;
+      box_reference_ordering(dims, (int)(sten.size() / 3), sten.data(), depth, rank);
+    }
+  }
+  if (comm.active()) {  // broadcast from rank 0 (a sum with zeros elsewhere; ranks < 2^31 are exact in FP64); [0] = valid flag
+    DevBuf<double> d((size_t)nref + 1);
+    std::vector<double> h((size_t)nref + 1, 0.);
+    if (comm.rank == 0 && !rank.empty()) { h[0] = 1.; for (int64_t i = 0; i < nref; i++) h[(size_t)i + 1] = rank[(size_t)i]; }
+    d.upload(h, st);
+    comm.allreduce_sum(d.p, (int)(nref + 1), st);
+    d.download(h.data(), (size_t)nref + 1, st);
+    if (h[0] < 0.5) return;
+    if (comm.rank != 0) { rank.resize((size_t)nref); for (int64_t i = 0; i < nref; i++) rank[(size_t)i] = (int)h[(size_t)i + 1]; }
+  }
+  if (rank.empty()) return;
+  std::vector<int> slot((size_t)nref);
+  for (int p = 0; p < P; p++) {
+    const Subdomain& S = *mine[p];
+    const double box = (double)ext[p][0] * ext[p][1] * ext[p][2];
+    if (!((double)S.nodes.size() >= 0.97 * box && S.nodes.size() >= 20000)) continue;
+    std::fill(slot.begin(), slot.end(), -1);
+    for (int l = 0; l < (int)S.nodes.size(); l++) {
+      int c[3];
+      coord(S.nodes[l], c);
+      slot[(size_t)rank[(size_t)(c[0] - lo[p][0]) + (size_t)dims[0] * ((size_t)(c[1] - lo[p][1]) + (size_t)dims[1] * (size_t)(c[2] - lo[p][2]))]] = l;
+    }
+    prep[p].userPerm.reserve(S.nodes.size());
+    for (int64_t i = 0; i < nref; i++) if (slot[(size_t)i] >= 0) prep[p].userPerm.push_back(slot[(size_t)i]);
+  }
+}
 
 void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth, HostPrep& H) {
   const int n = (int)S.nodes.size();
@@ -292,6 +385,7 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
   so.nb = opt.nb;
   so.ordering = opt.ordering;
   so.ndDepth = ndDepth;
+  if (!H.userPerm.empty()) { so.ordering = 3; so.userPerm = H.userPerm.data(); }
   symbolic_analyze(n, S.aDir.ptr.data(), S.aDir.idx.data(), so, H.sym);
   const std::vector<int>& perm = H.sym.perm;
   const std::vector<int>& iperm = H.sym.iperm;
@@ -381,6 +475,16 @@ void GeneoPC::mult_sub(const double* x, const double* b, double* y) {
 void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const void* ncclUid) {
   require_device();
   const double tSetup0 = now_s();
+  // PCSetUp may be repeated on the same PC with a NEW problem / pattern: nothing of the previous one may survive (the
+  // solve forest holds raw pointers into the old plans, subs[p].L1 is bound to the old plan, comm to the old layout)
+  CUDA_CHECK(::geneo::sync_stream(st));
+  subs.clear();
+  forest = SolveForest();
+  factorWs = LdltWorkspace();
+  eigWs.release();
+  comm.reset();
+  nE = 0; applyCount = 0; ktUsed = 0;
+  nevGlobal.clear(); estimGlobal.clear();
   nbDof = dec.nbNode;
   nLoc = nOwn = nbDof;
   nbPart = dec.nbPart;
@@ -432,6 +536,12 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   const int inFlight = std::max(1, std::min(P, hw >= 8 ? 2 : 1));  // subdomains analysed concurrently
   int ndDepth = 0;
   while ((unsigned)(inFlight << (ndDepth + 1)) <= hw && ndDepth < 4) ndDepth++;
+  {
+    const double tr = now_s();
+    const unsigned hwAll = getenv("GENEO_HOST_THREADS") ? hw : std::max(1u, std::thread::hardware_concurrency());
+    plan_ordering_reuse(dec, mine, opt, comm, hwAll, st, prep);
+    orderingReuseTime = now_s() - tr;
+  }
   std::mutex mtx;
   std::condition_variable cv;
   std::vector<char> ready(P, 0);
@@ -588,6 +698,8 @@ void GeneoPC::numeric_begin() {
   estimDimE = realDimE = nicolaides = 0;
   factorBytes = factorNnz = 0;
   factorFlops = 0.;
+  allFactorSeconds = allFactorFlops = 0.;
+  allFactorCount = 0;
   for (auto& s : subs) {
     s.estim = s.nicolaides = s.eigSteps = s.eigDim = s.negL1 = s.perturbed = 0;
     s.nev = 0;
@@ -730,6 +842,7 @@ void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
     if (!s.L1) s.L1.reset(new LdltFactor(s.plan));  // a re-factorization overwrites the resident factor in place
     HostProfScope hp("lvl1 factorize");
     FactorStats fs = s.L1->factorize(opt.lvl1ORAS ? s.vRob.p : s.pat.val.p, pivTol, ws, st);
+    allFactorSeconds += fs.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
     s.negL1 = fs.neg;
     s.perturbed = fs.perturbed;
     lvl1SetupMinvTime += now_s() - tl1;
@@ -761,6 +874,7 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     vals_axpby(nnz, vA, param, vB, vS.p, st);  // A - param B, src/geneo.cpp:511-515
     HostProfScope hp("syl factorize");
     FactorStats fs = tmp.factorize(vS.p, pivTol, ws, st);
+    allFactorSeconds += fs.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
     est = tauPb ? fs.neg : (n - fs.neg);  // #eigenvalues below tau / above gamma (Sylvester)
     if (est > n) est = n;
     if (opt.cut > 0 && est > opt.cut) est = opt.cut;
@@ -789,11 +903,13 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     eo.ws = &eigWs;
     EigResult er;
     if (tauPb) {  // A x = lambda B x, smallest: T = A^-1 B
-      { HostProfScope hp("eig factorize"); tmp.factorize(vA, pivTol, ws, st); }
+      { HostProfScope hp("eig factorize"); FactorStats f2 = tmp.factorize(vA, pivTol, ws, st);
+        allFactorSeconds += f2.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++; }
       HostProfScope hp("eig block_lanczos");
       block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vB, std::min(nev + guard, n), eo, er, st);
     } else {      // A x = lambda B x, largest: T = B^-1 A, self-adjoint in the A inner product
-      tmp.factorize(vB, pivTol, ws, st);
+      FactorStats f2 = tmp.factorize(vB, pivTol, ws, st);
+      allFactorSeconds += f2.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
       block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vA, std::min(nev + guard, n), eo, er, st);
     }
     if (er.nconv < (int)er.lambda.size())

@@ -28,6 +28,7 @@ struct GeneoOptions {
   // knobs of the sub-solvers (stand for the reference's -dls1_/-syl2_/-els2_/-dcs2_ PETSc option prefixes)
   int nb = 128;          // LDL^T panel width
   int ordering = 1;      // 1 METIS NodeND, 0 natural
+  bool orderingReuse = true;  // structured problems: box subdomains share one nested dissection (-geneo_ordering_reuse 0|1)
   double epsTol = 1e-4;  // -els2_eps_tol (block Lanczos residual tolerance; reference default 1e-3, src/geneo.cpp:658)
   int epsBlock = 0;      // block size of the Lanczos eigen-solver (-els2_eps_block); 0: 8
   bool releaseWorkspace = false;  // free the factorization / eigen-solver workspaces after every setup
@@ -89,10 +90,14 @@ class GeneoPC {
   double lvl2SetupGammaLocTime = 0., lvl2SetupGammaSylTime = 0., lvl2SetupGammaEigTime = 0.;
   double lvl1ApplyTime = 0., lvl1ApplyScatterTime = 0., lvl1ApplyMinvTime = 0., lvl1ApplyGatherTime = 0.;
   double lvl1ApplyPrjFSTime = 0., lvl2ApplyTime = 0., lvl2ApplyZtTime = 0., lvl2ApplyEinvTime = 0., lvl2ApplyZTime = 0.;
-  double symbolicTime = 0., operatorTime = 0., setupTime = 0., uploadTime = 0., numericTime = 0.;
+  double symbolicTime = 0., operatorTime = 0., setupTime = 0., uploadTime = 0., numericTime = 0., orderingReuseTime = 0.;
   int estimDimE = 0, realDimE = 0, nicolaides = 0;
   int64_t factorBytes = 0, factorNnz = 0, applyCount = 0;
   double factorFlops = 0.;
+  // every numeric factorization of the last (re-)setup (A_dir/A_rob, A_neu - tau B, A_neu, ...): device seconds (each call
+  // ends with a stream synchronisation), flops from the symbolic analysis, number of factorizations
+  double allFactorSeconds = 0., allFactorFlops = 0.;
+  int allFactorCount = 0;
   std::string infoL2;
   std::vector<int> nevGlobal, estimGlobal;  // per subdomain (global ids), known on every rank
 

@@ -1293,8 +1293,10 @@ void SolveForest::build(const std::vector<const LdltPlan*>& plans, const std::ve
       const RingLaunch rl = ring_launch(which, ringVar);
       CUDA_CHECK(cudaFuncSetAttribute(rl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.smem));
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rl.fn, rl.warps * 32, rl.smem));
-      if (which < 2) ringGrid[which] = std::max(1, nb) * nsm;  // (NR = 16 walks the NR = 8 lists on the same grid: the warp
-                                                                 //  -> item mapping is computed in the kernel from its own block size)
+      if (which < 2) ringGrid[which] = std::max(1, nb) * nsm;
+      else ringGrid[1] = std::min(ringGrid[1], std::max(1, nb) * nsm);  // NR = 16 walks the NR = 8 lists on the SAME cooperative grid:
+                                                                          // it must fit both kernels (the warp -> item mapping is
+                                                                          // computed in the kernel from its own block size)
     }
   }
 }

@@ -78,6 +78,7 @@ void generate_grid(const GridGenOptions& o, Mesh& m, std::vector<int>* elemPartO
   const int64_t npts = (int64_t)n1 * n2 * n3;
   GENEO_CHECK(npts < (int64_t)2147483647, "grid too large for 32-bit node ids");
   m.nbNode = (int)npts;
+  m.grid[0] = n1; m.grid[1] = n2; m.grid[2] = n3;
   m.elemPtr.clear(); m.elemIdx.clear(); m.matVal.clear();
   const bool sub = o.keepHi[0] >= 0;
   if (!sub) {
@@ -285,6 +286,7 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
   const int ne = m.nbElem(), nn = m.nbNode;
   d = Decomposition();
   d.nbPart = nbPart; d.nbNode = nn; d.nbElem = ne;
+  for (int a = 0; a < 3; a++) d.grid[a] = m.grid[a];
   d.nodeMult.assign(nn, 0);
   d.elemMult.assign(ne, 0);
   d.subs.resize(nbPart);

@@ -18,6 +18,7 @@ struct Mesh {
   std::vector<int> elemIdx;
   std::vector<int64_t> matPtr;   // [nbElem+1]
   std::vector<double> matVal;
+  int grid[3] = {0, 0, 0};       // structured generators: node g sits at (g % grid[0], (g / grid[0]) % grid[1], g / (grid[0] grid[1]))
   int nbElem() const { return (int)elemPtr.size() - 1; }
   void finalize();               // (re)build matPtr from elemPtr
 };
@@ -59,6 +60,7 @@ struct Subdomain {
 
 struct Decomposition {
   int nbPart = 0, nbNode = 0, nbElem = 0;
+  int grid[3] = {0, 0, 0};      // copy of Mesh::grid (0: unstructured) -- lets congruent box subdomains share one nested dissection
   std::vector<int> nodeMult, elemMult;
   std::vector<Subdomain> subs;  // ALL subdomains' index sets; matrices only for the ones in `mine`
   int64_t nnzNeuTotal = 0;      // "nnz coefs" of the INFO line (sum over all local matrices)

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <numeric>
 #include <string>
@@ -127,6 +128,105 @@ void nd_recursive(NdGraph& g, int depth, std::vector<int>& order) {
   for (int v : ids[2]) order.push_back(v);
 }
 
+// Geometric nested dissection: every region is cut at the median coordinate of its longest axis; the separator is the
+// set of vertices of the upper half that touch the lower half (for a 7-point grid: exactly one plane of nodes), ordered
+// last.  Works on any graph whose vertices carry integer coordinates; O(nnz log n), no METIS call.  At 100^3 it costs
+// 0.3 s where METIS_NodeND needs 5-15 s of one core -- the host wall of the cold setup at 8 subdomains per GPU and 8
+// ranks per node -- and, being the textbook ordering of a regular grid, it gives regular separators (planes) and a
+// slightly smaller factor.  order: new -> old.
+void geometric_nd(int n, const int64_t* ptr, const int* idx, const int* coords, int leaf, std::vector<int>& order) {
+  std::vector<int> verts(n), tmp(n);
+  std::iota(verts.begin(), verts.end(), 0);
+  std::vector<int> side(n, -1);     // scratch: region stamp / side of the current cut
+  order.assign(n, -1);
+  struct Region { int b, e, outPos; };  // verts[b, e) -> order[outPos, outPos + (e - b))
+  std::vector<Region> stack;
+  stack.push_back(Region{0, n, 0});
+  std::vector<int> cnt;
+  int metisBelow = 0;
+  if (const char* e = getenv("GENEO_GEO_METIS_T")) metisBelow = atoi(e);
+  while (!stack.empty()) {
+    const Region R = stack.back();
+    stack.pop_back();
+    const int m = R.e - R.b;
+    if (m <= leaf) {
+      for (int t = 0; t < m; t++) order[R.outPos + t] = verts[R.b + t];
+      continue;
+    }
+    if (m <= metisBelow) {  // hybrid: the region's own graph goes to METIS_NodeND
+      NdRngScope rngScope;
+      for (int t = 0; t < m; t++) side[verts[R.b + t]] = t;  // local numbering
+      std::vector<midx_t> xadj(m + 1, 0), adj;
+      for (int t = 0; t < m; t++) {
+        const int v = verts[R.b + t];
+        for (int64_t e = ptr[v]; e < ptr[v + 1]; e++) { const int u = idx[e]; if (u != v && side[u] >= 0) adj.push_back(side[u]); }
+        xadj[t + 1] = (midx_t)adj.size();
+      }
+      for (int t = 0; t < m; t++) side[verts[R.b + t]] = -1;
+      if (adj.empty()) { for (int t = 0; t < m; t++) order[R.outPos + t] = verts[R.b + t]; continue; }
+      midx_t options[40];
+      metis_opts(options);
+      midx_t nv = m;
+      std::vector<midx_t> p(m), ip(m);
+      const int rc = METIS_NodeND(&nv, xadj.data(), adj.data(), NULL, options, p.data(), ip.data());
+      GENEO_CHECK(rc == 1, "METIS_NodeND failed");
+      for (int t = 0; t < m; t++) order[R.outPos + t] = verts[R.b + (int)p[t]];
+      continue;
+    }
+    int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+    for (int t = R.b; t < R.e; t++)
+      for (int a = 0; a < 3; a++) {
+        const int c = coords[3 * (size_t)verts[t] + a];
+        lo[a] = std::min(lo[a], c); hi[a] = std::max(hi[a], c);
+      }
+    int ax = 0;
+    for (int a = 1; a < 3; a++) if (hi[a] - lo[a] > hi[ax] - lo[ax]) ax = a;
+    if (hi[ax] == lo[ax]) {  // all vertices at one point: nothing to cut
+      for (int t = 0; t < m; t++) order[R.outPos + t] = verts[R.b + t];
+      continue;
+    }
+    // cut coordinate: the smallest c with #{coord < c} >= m/2 (histogram over the extent)
+    cnt.assign((size_t)(hi[ax] - lo[ax]) + 2, 0);
+    for (int t = R.b; t < R.e; t++) cnt[coords[3 * (size_t)verts[t] + ax] - lo[ax] + 1]++;
+    int cut = lo[ax] + 1;
+    {
+      int64_t acc = 0;
+      for (int c = lo[ax]; c <= hi[ax]; c++) {
+        acc += cnt[c - lo[ax] + 1];
+        if (2 * acc >= m) { cut = c + 1; break; }
+      }
+      if (cut > hi[ax]) cut = hi[ax];
+    }
+    // side: 0 lower (coord < cut), 1 upper; separator = upper vertices with a lower neighbour INSIDE the region
+    for (int t = R.b; t < R.e; t++) side[verts[t]] = coords[3 * (size_t)verts[t] + ax] < cut ? 0 : 1;
+    int nl = 0, nu = 0, nsep = 0;
+    for (int t = R.b; t < R.e; t++) {
+      const int v = verts[t];
+      if (side[v] == 0) { nl++; continue; }
+      bool sep = false;
+      for (int64_t e = ptr[v]; e < ptr[v + 1] && !sep; e++) {
+        const int u = idx[e];
+        if (u != v && side[u] == 0) sep = true;
+      }
+      if (sep) side[v] = 2;
+    }
+    // stable three-way split of verts[b, e): lower | upper | separator
+    for (int t = R.b; t < R.e; t++) { const int s = side[verts[t]]; if (s == 1) nu++; else if (s == 2) nsep++; }
+    int pl = R.b, pu = R.b + nl, ps = R.b + nl + nu;
+    for (int t = R.b; t < R.e; t++) {
+      const int v = verts[t];
+      const int s = side[v];
+      tmp[s == 0 ? pl++ : (s == 1 ? pu++ : ps++)] = v;
+    }
+    std::copy(tmp.begin() + R.b, tmp.begin() + R.e, verts.begin() + R.b);
+    for (int t = R.b; t < R.e; t++) side[verts[t]] = -1;  // vertices outside the region must never look like "lower"
+    for (int t = 0; t < nsep; t++) order[R.outPos + nl + nu + t] = verts[R.b + nl + nu + t];
+    // (nsep == 0: no edge crosses the cut -- the halves are independent regions all the same)
+    if (nl > 0) stack.push_back(Region{R.b, R.b + nl, R.outPos});
+    if (nu > 0) stack.push_back(Region{R.b + nl, R.b + nl + nu, R.outPos + nl});
+  }
+}
+
 // Elimination tree of P A P^T (Liu, path compression).  Row j of the permuted matrix = row perm[j] of the input.
 void etree(int n, const int64_t* ptr, const int* idx, const std::vector<int>& perm, const std::vector<int>& iperm,
            std::vector<int>& parent) {
@@ -205,6 +305,44 @@ void colcounts(int n, const int64_t* ptr, const int* idx, const std::vector<int>
 
 }  // namespace
 
+void box_reference_ordering(const int dims[3], int nst, const int* stencil, int ndDepth, std::vector<int>& rank) {
+  const int64_t n64 = (int64_t)dims[0] * dims[1] * dims[2];
+  GENEO_CHECK(n64 > 0 && n64 < 2147483647, "reference box: bad dimensions");
+  const int n = (int)n64;
+  // symmetric closure of the stencil, without the origin and without duplicates
+  std::vector<int> off;
+  auto have = [&](int a, int b, int c) {
+    for (size_t t = 0; t < off.size(); t += 3) if (off[t] == a && off[t + 1] == b && off[t + 2] == c) return true;
+    return false;
+  };
+  for (int t = 0; t < nst; t++)
+    for (int sg = -1; sg <= 1; sg += 2) {
+      const int a = sg * stencil[3 * t], b = sg * stencil[3 * t + 1], c = sg * stencil[3 * t + 2];
+      if ((a | b | c) == 0 || have(a, b, c)) continue;
+      off.push_back(a); off.push_back(b); off.push_back(c);
+    }
+  NdGraph g;
+  g.xadj.assign((size_t)n + 1, 0);
+  g.adj.reserve((size_t)n * (off.size() / 3));
+  for (int z = 0; z < dims[2]; z++)
+    for (int y = 0; y < dims[1]; y++)
+      for (int x = 0; x < dims[0]; x++) {
+        const int v = x + dims[0] * (y + dims[1] * z);
+        for (size_t t = 0; t < off.size(); t += 3) {
+          const int a = x + off[t], b = y + off[t + 1], c = z + off[t + 2];
+          if (a < 0 || a >= dims[0] || b < 0 || b >= dims[1] || c < 0 || c >= dims[2]) continue;
+          g.adj.push_back(a + dims[0] * (b + dims[1] * c));
+        }
+        g.xadj[(size_t)v + 1] = (midx_t)g.adj.size();
+      }
+  std::vector<int> order;
+  if (g.adj.empty()) { order.resize(n); std::iota(order.begin(), order.end(), 0); }
+  else nd_recursive(g, ndDepth, order);
+  GENEO_CHECK((int)order.size() == n, "reference box: nested dissection lost vertices");
+  rank.assign(n, 0);
+  for (int i = 0; i < n; i++) rank[order[i]] = i;
+}
+
 void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt, Symbolic& S) {
   const double tStart = now_s();
   (void)tStart;
@@ -216,7 +354,13 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
 
   // ---- 1. fill-reducing ordering ------------------------------------------------------------------------------------
   std::vector<int> perm(n), iperm(n);
-  bool useMetis = (opt.ordering == 1 && n > 32);
+  bool useMetis = ((opt.ordering == 1 || (opt.ordering == 2 && !opt.coords)) && n > 32);
+  bool useGeo = opt.ordering == 2 && opt.coords && n > 32;
+  if (useGeo) {
+    std::vector<int> order;
+    geometric_nd(n, ptr, idx, opt.coords, std::max(1, opt.geoLeaf), order);
+    for (int i = 0; i < n; i++) { GENEO_CHECK(order[i] >= 0, "geometric nested dissection lost vertices"); perm[i] = order[i]; iperm[order[i]] = i; }
+  }
   if (useMetis) {
     std::vector<midx_t> xadj(n + 1, 0), adj;
     adj.reserve(ptr[n]);
@@ -238,7 +382,16 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
       for (int i = 0; i < n; i++) { perm[i] = order[i]; iperm[order[i]] = i; }
     }
   }
-  if (!useMetis) { std::iota(perm.begin(), perm.end(), 0); std::iota(iperm.begin(), iperm.end(), 0); }
+  if (opt.ordering == 3) {
+    GENEO_CHECK(opt.userPerm != nullptr, "ordering 3 needs a permutation");
+    std::fill(iperm.begin(), iperm.end(), -1);
+    for (int i = 0; i < n; i++) {
+      const int o = opt.userPerm[i];
+      GENEO_CHECK(o >= 0 && o < n && iperm[o] < 0, "user permutation is not a permutation");
+      perm[i] = o; iperm[o] = i;
+    }
+  } else
+  if (!useMetis && !useGeo) { std::iota(perm.begin(), perm.end(), 0); std::iota(iperm.begin(), iperm.end(), 0); }
 
   const bool tm = getenv("GENEO_SYM_TIMING") != nullptr;
   double tq = now_s();

@@ -2,7 +2,8 @@
 // (reference call sites: src/geneo.cpp:94-124 directLocalSolve, :452-500 getInertia, :746-780 buildEigenSolver).
 //
 // Design (B200-first, see DESIGN.md "Sparse LDL^T"):
-//   * fill-reducing ordering: METIS NodeND on the host;
+//   * fill-reducing ordering: METIS NodeND on the host, or an O(n log n) geometric nested dissection (coordinate
+//     bisection + vertex separator taken from the cut) when the caller knows vertex coordinates (structured generators);
 //   * elimination tree, postorder, Gilbert-Ng-Peyton column counts, supernodes with relaxed amalgamation;
 //   * every supernode is cut into PANELS ("fronts") of at most NB pivot columns, chained in the assembly tree, so that
 //     each front needs exactly one dense NBxNB pivot-block inversion, one panel product and one Schur GEMM;
@@ -70,7 +71,11 @@ struct Symbolic {
 
 struct SymbolicOptions {
   int nb = 128;        // panel width
-  int ordering = 1;    // 0 natural, 1 METIS NodeND
+  int ordering = 1;    // 0 natural, 1 METIS NodeND, 2 geometric nested dissection (needs coords; falls back to 1 without),
+                       // 3 caller-supplied permutation (userPerm)
+  const int* userPerm = nullptr;  // ordering == 3: new -> old, length n
+  const int* coords = nullptr;  // optional: 3 integer coordinates per vertex (structured generators, SymbolicOptions::ordering == 2)
+  int geoLeaf = 48;    // geometric ND stops at regions of at most this many vertices
   bool amalgamate = true;
   bool chainInplace = true;  // update matrices of supernode chains stay in place (see Front::inplace)
   bool chainPairs = true;    // rank-256 trailing updates along in-place chains (see Front::pair)
@@ -78,6 +83,13 @@ struct SymbolicOptions {
   int ndDepth = 0;     // top levels of the nested dissection done here (METIS_ComputeVertexSeparator) with the two halves
                        // ordered by concurrent threads: 2^ndDepth threads per matrix; 0 = plain METIS_NodeND
 };
+
+// Reference nested dissection of a dims[0] x dims[1] x dims[2] box of grid points coupled through `stencil` (nst integer
+// offsets, 3 ints each; both signs need not be listed).  rank[x + dims[0] (y + dims[1] z)] = position of the point in the
+// elimination order.  ANY subset of the box inherits a valid nested-dissection ordering by sorting its points by rank
+// (induced separators): the subdomains of a structured problem that fit into one bounding box share ONE METIS call instead
+// of one each -- the host wall of the cold setup (MUMPS analysis in the reference, src/geneo.cpp:99-110).
+void box_reference_ordering(const int dims[3], int nst, const int* stencil, int ndDepth, std::vector<int>& rank);
 
 // ptr/idx: CSR pattern of a structurally symmetric n x n matrix (both triangles; column order irrelevant).
 void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt, Symbolic& s);

@@ -104,6 +104,9 @@ int geneo_pc_timers(geneo_pc_t pc, double* t, int cap);
 /* stats = {factor bytes, factor nnz, factor flops, tri-solve algorithmic bytes per apply, apply algorithmic bytes,
  *          SpMV algorithmic bytes, number of applies so far, sum n_i} */
 int geneo_pc_stats(geneo_pc_t pc, double stats[8]);
+/* every numeric factorization of the last (re-)setup: out = {device seconds, flops (symbolic: sum k^3/3 + m k^2 + m^2 k),
+ * number of factorizations, host seconds spent on the shared reference ordering of the cold setup} */
+int geneo_pc_factor_stats(geneo_pc_t pc, double out[4]);
 int geneo_pc_sub_info(geneo_pc_t pc, int s, int64_t ints[8] /* n, nev, estim, nicolaides, eigSteps, eigDim, neg, perturbed */,
                       double reals[2] /* tauLoc, gammaLoc */);
 int geneo_pc_sub_eigenvalues(geneo_pc_t pc, int s, double* vals, int cap, int* count);
@@ -161,6 +164,14 @@ int geneo_allreduce_sum(geneo_pc_t pc, double* h, int n); /* host array, in plac
 typedef struct geneo_symbolic_s* geneo_symbolic_t;
 int geneo_symbolic_create(int n, const int64_t* ptr, const int32_t* idx, int nb, int ordering, int amalgamate,
                           geneo_symbolic_t* out);
+/* same with ordering = geometric nested dissection on integer vertex coordinates (coords[3*n]; structured generators) */
+int geneo_symbolic_create_geo(int n, const int64_t* ptr, const int32_t* idx, int nb, int amalgamate, const int32_t* coords,
+                              geneo_symbolic_t* out);
+/* same with a caller-supplied permutation (new -> old) */
+int geneo_symbolic_create_perm(int n, const int64_t* ptr, const int32_t* idx, int nb, int amalgamate, const int32_t* perm,
+                               geneo_symbolic_t* out);
+/* reference nested dissection of a box of grid points (symbolic.hpp box_reference_ordering): rank[dims[0]*dims[1]*dims[2]] */
+int geneo_box_ordering(const int32_t dims[3], int nst, const int32_t* stencil, int threads, int32_t* rank);
 int geneo_symbolic_destroy(geneo_symbolic_t s);
 /* ints = {n, nfronts, nlevels, lSize, uArena, wArena, nRowIdx, nRel, nAsm, nsuper, cArena} ; reals = {flops} */
 int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[11], double reals[1]);
