@@ -40,6 +40,7 @@ sys.path.insert(0, ROOT)
 METRIC = "geneo_solve_throughput(setup+iter)"
 UNIT = "DOF/s"
 CPU_SIZES = (24, 32, 40, 48, 56, 64, 72, 80, 96, 112, 128, 160, 200)
+CPU_GRAPH_SIZES = (400, 1600, 6400, 25600, 102400, 409600, 1000000)
 
 
 def parse():
@@ -48,13 +49,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=200, help="grid edge per GPU (weak scaling: edge = cbrt(size^3 * gpus))")
-    ap.add_argument("--kind", default="laplacian", choices=["laplacian", "heat"])
-    ap.add_argument("--partition", default="box", choices=["box", "metis"])
+    ap.add_argument("--size", type=int, default=0, help="grid edge per GPU (weak scaling: edge = cbrt(size^3 * gpus)), default 200; "
+                                                         "--kind graph: the generator's --size (nodes per block), default 1000000")
+    ap.add_argument("--kind", default="laplacian", choices=["laplacian", "heat", "graph"])
+    ap.add_argument("--graph-level", type=int, default=5, help="--kind graph: levels of 4 blocks around the central block")
+    ap.add_argument("--partition", default="", choices=["", "box", "metis"], help="default: box for the grids, metis for the graph")
     ap.add_argument("--subs-per-gpu", type=int, default=8)
     ap.add_argument("--lvl", default="ASM,1")
     ap.add_argument("--tau", default="0.1")
-    ap.add_argument("--ksp", default="cg")
+    ap.add_argument("--ksp", default="", help="cg | gmres (default: cg, gmres for --kind graph: BASELINE configs[3])")
     ap.add_argument("--rtol", type=float, default=1e-5)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-size", type=int, default=0, help="grid edge of the CPU sample; 0 = the largest that fits --cpu-budget")
@@ -62,10 +65,19 @@ def parse():
     ap.add_argument("--ref-budget", type=float, default=200.0, help="seconds for the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra-opts", default="", help="more -geneo_* / -els2_* options, space separated")
-    return ap.parse_args()
+    a = ap.parse_args()
+    graph = a.kind == "graph"
+    a.size = a.size or (1000000 if graph else 200)
+    a.partition = a.partition or ("metis" if graph else "box")
+    a.ksp = a.ksp or ("gmres" if graph else "cg")
+    if graph and a.partition != "metis":
+        ap.error("--kind graph has no box partition")
+    return a
 
 
-def gen_args(a, size):
+def gen_args(a, size, ws=1):
+    if a.kind == "graph":  # tst/graph/graphRun.sh:144
+        return "--size %d --level %d --weakScaling %d --noGround --inpEps 0.0001" % (size, a.graph_level, ws)
     s = "--dim 3 --size %d --inpEps 0.0001" % size
     if a.kind == "heat":
         s += " --kappa 100. minmax --lbd 1. --dt 0.1"
@@ -77,16 +89,25 @@ def weak_edge(size, g):
     return size if g == 1 else int(math.floor((float(size) ** 3 * g) ** (1.0 / 3.0) + 1e-9))
 
 
+def graph_nodes(a, size, ws=1):
+    return (1 + 4 * a.graph_level) * int(math.sqrt(size * ws)) ** 2
+
+
 def workload_name(a, edge, nsub, ngpu, partition):
     part = "box partition %d per GPU" % a.subs_per_gpu if partition == "box" else "METIS dual"
+    if a.kind == "graph":
+        return "graph Laplacian (tst/graph) size %d level %d weakScaling %d = %d nodes, %d subdomains (%s), geneo %s tau=%s, %s rtol %g" % (
+            edge, a.graph_level, ngpu, graph_nodes(a, edge, ngpu), nsub, part, a.lvl, a.tau, a.ksp, a.rtol)
     return "%s3d %d^3 = %d DOFs, %d subdomains (%s), geneo %s tau=%s, %s rtol %g" % (
         a.kind, edge, edge ** 3, nsub, part, a.lvl, a.tau, a.ksp, a.rtol)
 
 
 def workload_config(a, ngpu):
-    edge = weak_edge(a.size, ngpu)
-    return {"workload": workload_name(a, edge, a.subs_per_gpu * ngpu, ngpu, a.partition), "generator": gen_args(a, edge),
-            "partition": a.partition, "l2": "inputs_larger_than_L2 (factors >> 126 MB)"}
+    graph = a.kind == "graph"
+    edge = a.size if graph else weak_edge(a.size, ngpu)
+    return {"workload": workload_name(a, edge, a.subs_per_gpu * ngpu, ngpu, a.partition),
+            "generator": gen_args(a, edge, ngpu if graph else 1), "partition": a.partition,
+            "l2": "inputs_larger_than_L2 (factors >> 126 MB)"}
 
 
 class ClockSampler:
@@ -158,8 +179,11 @@ def cpu_sample(a, size, nparts, partition):
     import numpy as np
     from oracle import geneo_oracle as go
     from geneo4petsc_b200.dist import box_dims
-    kappa, interp = (100.0, "minmax") if a.kind == "heat" else (1.0, "")
-    mesh = go.gen_grid(3, size, 1e-4, kappa, interp, heat=(a.kind == "heat"))
+    if a.kind == "graph":  # (the reference's own generator, compiled into oracle/_ref)
+        mesh = go.ref_generator("graph", gen_args(a, size))
+    else:
+        kappa, interp = (100.0, "minmax") if a.kind == "heat" else (1.0, "")
+        mesh = go.gen_grid(3, size, 1e-4, kappa, interp, heat=(a.kind == "heat"))
     l1, l2 = a.lvl.split(",")
     cores = max(1, min(nparts, os.cpu_count() or 1))  # one worker per subdomain = the reference's one MPI rank per subdomain
     if partition == "box":
@@ -177,7 +201,7 @@ def cpu_ladder(a, nparts, partition, budget, repeats=1, fixed=0):
     measured exponent of the last two (sparse direct solvers are super-linear in the DOFs)."""
     table, rep, mesh, cores = [], None, None, 1
     spent = 0.0
-    sizes = [fixed] if fixed else list(CPU_SIZES)
+    sizes = [fixed] if fixed else list(CPU_GRAPH_SIZES if a.kind == "graph" else CPU_SIZES)
     for i, s in enumerate(sizes):
         rep, mesh, secs, cores = cpu_sample(a, s, nparts, partition)
         table.append((s, mesh.nb_node, secs, rep.ksp.its))
@@ -187,7 +211,8 @@ def cpu_ladder(a, nparts, partition, budget, repeats=1, fixed=0):
         expo = 1.6
         if len(table) >= 2 and table[-2][2] > 0.2:
             expo = max(1.2, min(2.2, math.log(table[-1][2] / table[-2][2]) / math.log(table[-1][1] / table[-2][1])))
-        pred = secs * (sizes[i + 1] ** 3 / float(s ** 3)) ** expo
+        grow = (sizes[i + 1] / float(s)) if a.kind == "graph" else (sizes[i + 1] ** 3 / float(s ** 3))
+        pred = secs * grow ** expo
         if spent + pred * repeats > budget:
             break
     return table, rep, mesh, cores
@@ -268,11 +293,14 @@ def build_problem(a, g, dist, rank, world, edge, partition):
         dist.decompose_owned(prob, len(sub_rank), sub_rank, rank, True, 0)
         if world > 1:
             layout = dist.Layout(prob, rank, world, sub_rank)
-    else:
-        assert world == 1, "--partition metis runs on one GPU (METIS on the global mesh does not fit one rank at N > 1)"
-        prob.generate(a.kind, gen_args(a, edge))
+    else:  # the reference's METIS dual partition; N > 1: every rank partitions the same mesh, parts grouped onto the GPUs
+        prob.generate(a.kind, gen_args(a, edge, world if a.kind == "graph" else 1))
         t1 = time.time()
-        prob.decompose(a.subs_per_gpu, True, 0)
+        if world == 1:
+            prob.decompose(a.subs_per_gpu, True, 0)
+        else:
+            sub_rank = dist.metis_problem(prob, a.subs_per_gpu * world, world, rank)
+            layout = dist.Layout(prob, rank, world, sub_rank)
     t2 = time.time()
     return prob, layout, {"gen_s": t1 - t0, "part_decomp_s": t2 - t1}
 
@@ -297,9 +325,9 @@ def run_b200(a):
         if tdist is not None:
             tdist.barrier()
 
-    edge = weak_edge(a.size, world)
-    n = edge ** 3
+    edge = a.size if a.kind == "graph" else weak_edge(a.size, world)
     prob, layout, tprob = build_problem(a, g, dist, rank, world, edge, a.partition)
+    n = prob.sizes()["nb_node"]
     extra = a.extra_opts.split() if a.extra_opts else []
     opts = ["-geneo_lvl", a.lvl, "-geneo_tau", a.tau, "-geneo_kernel_timing"] + extra
 
@@ -380,6 +408,11 @@ def run_b200(a):
         t = f0.elapsed_time(f1) / 10
         rates[name] = {"ms": t, "GBps": nbytes / t / 1e6}
     pc.kernel_time()
+    del pc, y, fn, step  # the e2e leg below builds a second preconditioner from scratch: this one's factors and workspaces must
+    #                      go first (fn / step hold bound references to it)
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
     gemm_tf = dgemm_peak(torch) if rank == 0 else 0.0
 
     # end to end through the C ABI with host buffers: create + setup (host analysis, uploads, numeric) + solve
@@ -486,7 +519,7 @@ def run_b200(a):
         tb = time.perf_counter()
         est_gpu = [pc3.sub_info(s)["estim"] for s in range(a.subs_per_gpu)]
         est_cpu = [int(s.estim) for s in rep.pc.sub]
-        out["parity"] = {"sample": "%d^3, same partition arrays, same options" % s_edge,
+        out["parity"] = {"sample": "size %d, same partition arrays, same options" % s_edge,
                          "its_gpu": r3["its"], "its_cpu": its, "dimE_gpu": pc3.info()["nE"], "dimE_cpu": int(rep.pc.e.shape[0]),
                          "eigen_counts_equal": est_gpu == est_cpu,
                          "x_rel_diff": float(np.linalg.norm(r3["x"] - rep.ksp.x) / np.linalg.norm(rep.ksp.x)),

@@ -68,12 +68,18 @@ int geneo_problem_set_mesh(geneo_problem_t p, uint32_t nbNode, uint32_t nbElem, 
 int geneo_problem_generate(geneo_problem_t p, const char* kind, const char* args) {
   ABI_TRY
   ABI_REQ(p && kind && args, "null argument");
-  GridGenOptions o;
   const std::string k(kind);
-  ABI_REQ(k == "laplacian" || k == "heat", "unknown generator (laplacian | heat)");
-  o.heat = (k == "heat");
-  ABI_REQ(parse_gen_args(args, o) == 0, "invalid generator command line");
-  generate_grid(o, p->mesh);
+  ABI_REQ(k == "laplacian" || k == "heat" || k == "graph", "unknown generator (laplacian | heat | graph)");
+  if (k == "graph") {
+    GraphGenOptions go;
+    ABI_REQ(parse_graph_args(args, go) == 0, "invalid generator command line");
+    generate_graph(go, p->mesh);
+  } else {
+    GridGenOptions o;
+    o.heat = (k == "heat");
+    ABI_REQ(parse_gen_args(args, o) == 0, "invalid generator command line");
+    generate_grid(o, p->mesh);
+  }
   p->decomposed = false;
   ABI_CATCH
 }
@@ -120,6 +126,15 @@ int geneo_problem_decompose(geneo_problem_t p, int nbPart, int metisDual, int ov
   }
   decompose(p->mesh, nbPart, p->elemPart, p->nodePart, p->dual, overlap, std::vector<char>(), p->dec);
   p->decomposed = true;
+  ABI_CATCH
+}
+int geneo_problem_partition(geneo_problem_t p, int nbPart, int metisDual, int32_t* elemPart, int32_t* nodePart) {
+  ABI_TRY
+  ABI_REQ(p && p->mesh.nbNode > 0 && nbPart >= 1, "no mesh");
+  std::vector<int> ep, np_;
+  ABI_REQ(metis_partition(p->mesh, nbPart, metisDual != 0, ep, np_) == 0, "partition KO");
+  if (elemPart) std::copy(ep.begin(), ep.end(), elemPart);
+  if (nodePart) std::copy(np_.begin(), np_.end(), nodePart);
   ABI_CATCH
 }
 // ---- pre-decomposed input (the PETSc plug-in's view: initGenEOPC / PCGenEOSetup) -----------------------------------------
@@ -387,7 +402,7 @@ int geneo_pc_level_profile(geneo_pc_t pc, double* us, double* bytes, int64_t* ni
 int geneo_counters(int64_t c[3]) {
   ABI_TRY
   ABI_REQ(c, "null argument");
-  c[0] = (int64_t)g_kernel_launches; c[1] = (int64_t)g_h2d_bytes; c[2] = (int64_t)g_d2h_bytes;
+  c[0] = (int64_t)g_kernel_launches.load(); c[1] = (int64_t)g_h2d_bytes; c[2] = (int64_t)g_d2h_bytes;
   ABI_CATCH
 }
 static int stage_apply(geneo_pc_t pc, const double* x, double* y, int what) {

@@ -1,6 +1,7 @@
 // common.hpp -- error handling, RAII device buffers, timers shared by the host side of libgeneob200.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -35,9 +36,10 @@ inline double now_s() {
 
 // Every kernel launch of the library goes through GENEO_TICK (wrapped around the grid argument of <<< >>>), so the
 // number of launches inside a timed region is a counted fact (bench.py "gpu_launches"), not an estimate.
-extern unsigned long long g_kernel_launches, g_h2d_bytes, g_d2h_bytes;
+extern std::atomic<unsigned long long> g_kernel_launches;  // (launches are issued by more than one host thread)
+extern unsigned long long g_h2d_bytes, g_d2h_bytes;
 template <class G>
-inline G launch_tick(G g) { ++g_kernel_launches; return g; }
+inline G launch_tick(G g) { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); return g; }
 // GENEO_PROFILE=1: a CUDA event is recorded on the (single, in-order) stream right before every launch, so consecutive
 // events bracket each kernel (plus whatever memset / idle gap follows it); geneo_profile_dump() aggregates by launch site.
 extern bool g_profile;

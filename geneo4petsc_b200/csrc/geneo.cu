@@ -17,7 +17,8 @@
 
 namespace geneo {
 
-unsigned long long g_kernel_launches = 0, g_h2d_bytes = 0, g_d2h_bytes = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
+unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
 
 // ---- in-library launch profiler (GENEO_PROFILE=1) -----------------------------------------------------------------------
 bool g_profile = getenv("GENEO_PROFILE") != nullptr;
@@ -447,6 +448,13 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
 }  // namespace
 
 GeneoPC::GeneoPC() {}
+// The pipelined numeric setup needs a single level-2 pencil (GenEO-1) or none; GenEO-2, the launch profiler (events on ONE
+// stream) and GENEO_PIPELINE=0 take the sequential path.
+bool GeneoPC::use_pipeline() const {
+  if (opt.lvl2 == 2 || g_profile || subs.empty()) return false;
+  if (const char* e = getenv("GENEO_PIPELINE")) return atoi(e) != 0;
+  return true;
+}
 GeneoPC::~GeneoPC() {
   for (auto s : streams) cudaStreamDestroy(s);
   for (auto e : events) cudaEventDestroy(e);
@@ -479,6 +487,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   // solve forest holds raw pointers into the old plans, subs[p].L1 is bound to the old plan, comm to the old layout)
   CUDA_CHECK(::geneo::sync_stream(st));
   subs.clear();
+  lanes.clear();
   forest = SolveForest();
   factorWs = LdltWorkspace();
   eigWs.release();
@@ -533,7 +542,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   unsigned hw = std::max(1u, std::thread::hardware_concurrency());
   if (const char* e = getenv("GENEO_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
   else if (const char* e2 = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1u, hw / (unsigned)std::max(1, atoi(e2)));
-  const int inFlight = std::max(1, std::min(P, hw >= 8 ? 2 : 1));  // subdomains analysed concurrently
+  int inFlight = std::max(1, std::min(P, hw >= 8 ? 2 : 1));  // subdomains analysed concurrently
   int ndDepth = 0;
   while ((unsigned)(inFlight << (ndDepth + 1)) <= hw && ndDepth < 4) ndDepth++;
   {
@@ -542,6 +551,9 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     plan_ordering_reuse(dec, mine, opt, comm, hwAll, st, prep);
     orderingReuseTime = now_s() - tr;
   }
+  int nInherit = 0;
+  for (auto& H : prep) nInherit += H.userPerm.empty() ? 0 : 1;
+  if (nInherit == P) { inFlight = std::max(1, std::min<int>(P, (int)hw)); ndDepth = 0; }  // no METIS call left: one thread per subdomain
   std::mutex mtx;
   std::condition_variable cv;
   std::vector<char> ready(P, 0);
@@ -625,6 +637,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
 
 
   numeric_begin();
+  const bool pipelined = use_pipeline();
   LdltWorkspace& ws = factorWs;
   std::vector<int> gAll((size_t)nAll);
   std::vector<double> dA((size_t)nAll);
@@ -659,11 +672,18 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     CUDA_CHECK(::geneo::sync_stream(st));
     H = HostPrep();  // free host memory early
     tUp += now_s() - tu;
+    if (!pipelined) {  // one subdomain after the other: the device factorizes p while the host still orders p+1, p+2
+      const double tn = now_s();
+      numeric_subdomain(s, ws);
+      tNum += now_s() - tn;
+    }
+  }
+  if (pipelined) {
     const double tn = now_s();
-    numeric_subdomain(s, ws);
+    numeric_pipeline();
     tNum += now_s() - tn;
   }
-  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); }
+  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); lanes.clear(); }
   symbolicTime = waitHost;  // time this thread spent WAITING for the host analysis (the rest of it was hidden behind the device)
   uploadTime = tUp;
 
@@ -737,8 +757,9 @@ void GeneoPC::numeric_end() {
 void GeneoPC::numeric_setup() {
   const double tNum0 = now_s();
   numeric_begin();
-  for (auto& s : subs) numeric_subdomain(s, factorWs);
-  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); }
+  if (use_pipeline()) numeric_pipeline();
+  else for (auto& s : subs) numeric_subdomain(s, factorWs);
+  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); lanes.clear(); }
   numeric_end();
   numericTime = now_s() - tNum0;
   host_prof_add("numeric_setup total", numericTime);
@@ -765,177 +786,200 @@ void GeneoPC::kernel_time(double* ms, int64_t* launches) {
   ktUsed = 0;
 }
 
-// every factorization and eigen-solve of one subdomain (level 2 first: its factors are transient)
+// getLocalGenEOGamma, src/geneo.cpp:1120-1232 (connectivity quirk reproduced)
+double GeneoPC::local_gamma(const SubdomainState& s) const {
+  const int NP = nbPart;
+  std::vector<double> C((size_t)NP * NP, 0.), F(NP, 0.), wv(NP);
+  for (int r = 0; r < NP; r++)
+    for (int q = 0; q < NP; q++)
+      C[(size_t)r * NP + q] = (r == q) ? 1. : (connectivity[(size_t)r * NP + q] ? 1. : 0.);
+  for (int r = 0; r < NP; r++) { double sum = 0.; for (int q = 0; q < NP; q++) sum += C[(size_t)r * NP + q]; F[r] = 1. / sum; }
+  for (int r = 0; r < NP; r++) for (int q = 0; q < NP; q++) C[(size_t)r * NP + q] *= F[r] * F[q];
+  sym_eig(NP, C.data(), wv.data());
+  double lam = wv[0];
+  for (int r = 0; r < NP; r++) if (std::fabs(wv[r]) > std::fabs(lam)) lam = wv[r];
+  double gl = opt.gamma / lam * F[s.id] * F[s.id];
+  if (gl <= 1.) gl = 1.1;
+  return gl;
+}
+
+// Z_s = D [v_1 ... v_nev]  (fillZE2L, src/geneo.cpp:249-272); empty => constant vector (:1305-1314)
+void GeneoPC::assemble_z(SubdomainState& s, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts) {
+  int nev = 0;
+  for (int c : counts) nev += c;
+  const double tz = now_s();
+  if (nev == 0) {
+    s.nev = 1;
+    s.Z.alloc((size_t)s.n);
+    CUDA_CHECK(cudaMemcpyAsync(s.Z.p, s.d.p, sizeof(double) * s.n, cudaMemcpyDeviceToDevice, st));  // D * 1
+    s.eigvals.assign(1, 0.);
+    s.nicolaides += 1;
+  } else {
+    s.nev = nev;
+    s.Z.alloc((size_t)s.n * nev);
+    int c0 = 0;
+    for (size_t b = 0; b < vecs.size(); b++) {
+      const int nc = counts[b];
+      if (nc == 0) continue;
+      copy_cols(s.n, vecs[b].p, nc, s.Z.p + c0, nev, nc, st);
+      c0 += nc;
+    }
+    rows_scale(s.n, nev, s.d.p, s.Z.p, st);  // Z = D V
+    s.eigvals = vals;
+  }
+  CUDA_CHECK(::geneo::sync_stream(st));
+  lvl2SetupZTime += now_s() - tz;
+}
+
+// every factorization and eigen-solve of one subdomain, one after the other on the library's stream (level 2 first: its
+// factors are transient).  GenEO-2 and the fallback of the pipelined path (numeric_pipeline).
 void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
   HostProfScope hpSub("numeric_subdomain");
-  {
-    const double anorm = s.anorm;
-    // pivot threshold
-    const double pivTol = opt.pivRel * std::max(anorm, 1e-300);
-    // level 2 first (its factorizations are transient), then the persistent level-1 factor
-    if (opt.lvl2 >= 1) {
-      std::vector<double> vals;
-      std::vector<DevBuf<double>> vecs;
-      std::vector<int> counts;
-      int cut = opt.cut;
-      if (opt.lvl2 == 2 && cut >= 2) cut = cut / 2;  // src/geneo.cpp:1275
-      const int savedCut = opt.cut;
-      opt.cut = cut;
-      HostProfScope hpL2("numeric_subdomain: level 2");
-      DevBuf<double> vB((size_t)s.pat.nnz);
-      csr_scale_sym(s.n, s.pat.ptr.p, s.pat.idx.p, s.pat.val.p, s.d.p, vB.p, st);  // D A_dir D, src/geneo.cpp:1243-1246
-      if (opt.lvl2 == 1) {
-        eigen_local_problem(s, s.vNeu.p, vB.p, opt.tau, true, ws, vals, vecs, counts);
-      } else {
-        double tl = opt.tau;  // getLocalGenEOTau, src/geneo.cpp:1097-1118
-        if (!opt.cst) { tl = s.maxMult * opt.tau; if (tl >= 1.) tl = 0.9; s.tauLoc = tl; }
-        eigen_local_problem(s, s.vNeu.p, s.vRob.p, tl, true, ws, vals, vecs, counts);
-        double gl = opt.gamma;  // getLocalGenEOGamma, src/geneo.cpp:1120-1232 (connectivity quirk reproduced)
-        if (!opt.cst) {
-          const int NP = nbPart;
-          std::vector<double> C((size_t)NP * NP, 0.), F(NP, 0.), wv(NP);
-          for (int r = 0; r < NP; r++)
-            for (int q = 0; q < NP; q++)
-              C[(size_t)r * NP + q] = (r == q) ? 1. : (connectivity[(size_t)r * NP + q] ? 1. : 0.);
-          for (int r = 0; r < NP; r++) { double sum = 0.; for (int q = 0; q < NP; q++) sum += C[(size_t)r * NP + q]; F[r] = 1. / sum; }
-          for (int r = 0; r < NP; r++) for (int q = 0; q < NP; q++) C[(size_t)r * NP + q] *= F[r] * F[q];
-          sym_eig(NP, C.data(), wv.data());
-          double lam = wv[0];
-          for (int r = 0; r < NP; r++) if (std::fabs(wv[r]) > std::fabs(lam)) lam = wv[r];
-          gl = gl / lam * F[s.id] * F[s.id];
-          if (gl <= 1.) gl = 1.1;
-          s.gammaLoc = gl;
-        }
-        eigen_local_problem(s, vB.p, s.vRob.p, gl, false, ws, vals, vecs, counts);
-      }
-      opt.cut = savedCut;
-      // assemble Z_s = D [v_1 ... v_nev]  (fillZE2L, src/geneo.cpp:249-272); empty => constant vector (:1305-1314)
-      int nev = 0;
-      for (int c : counts) nev += c;
-      const double tz = now_s();
-      if (nev == 0) {
-        s.nev = 1;
-        s.Z.alloc((size_t)s.n);
-        CUDA_CHECK(cudaMemcpyAsync(s.Z.p, s.d.p, sizeof(double) * s.n, cudaMemcpyDeviceToDevice, st));  // D * 1
-        s.eigvals.assign(1, 0.);
-        s.nicolaides += 1;
-      } else {
-        s.nev = nev;
-        s.Z.alloc((size_t)s.n * nev);
-        int c0 = 0;
-        for (size_t b = 0; b < vecs.size(); b++) {
-          const int nc = counts[b];
-          if (nc == 0) continue;
-          // copy block b (n x nc, ld nc) into columns c0.. of Z (ld nev) scaled by d: reuse ts_update with identity? simple 2D copy + scale
-          copy_cols(s.n, vecs[b].p, nc, s.Z.p + c0, nev, nc, st);
-          c0 += nc;
-        }
-        rows_scale(s.n, nev, s.d.p, s.Z.p, st);  // Z = D V
-        CUDA_CHECK(::geneo::sync_stream(st));
-        s.eigvals = vals;
-      }
-      CUDA_CHECK(::geneo::sync_stream(st));
-      lvl2SetupZTime += now_s() - tz;
+  const double pivTol = opt.pivRel * std::max(s.anorm, 1e-300);
+  if (opt.lvl2 >= 1) {
+    std::vector<double> vals;
+    std::vector<DevBuf<double>> vecs;
+    std::vector<int> counts;
+    int cut = opt.cut;
+    if (opt.lvl2 == 2 && cut >= 2) cut = cut / 2;  // src/geneo.cpp:1275
+    HostProfScope hpL2("numeric_subdomain: level 2");
+    if ((int64_t)s.vB.n < s.pat.nnz) s.vB.alloc((size_t)s.pat.nnz);
+    csr_scale_sym(s.n, s.pat.ptr.p, s.pat.idx.p, s.pat.val.p, s.d.p, s.vB.p, st);  // D A_dir D, src/geneo.cpp:1243-1246
+    if (opt.lvl2 == 1) {
+      eigen_local_problem(s, s.vNeu.p, s.vB.p, opt.tau, true, cut, ws, vals, vecs, counts);
+    } else {
+      double tl = opt.tau;  // getLocalGenEOTau, src/geneo.cpp:1097-1118
+      if (!opt.cst) { tl = s.maxMult * opt.tau; if (tl >= 1.) tl = 0.9; s.tauLoc = tl; }
+      eigen_local_problem(s, s.vNeu.p, s.vRob.p, tl, true, cut, ws, vals, vecs, counts);
+      double gl = opt.gamma;
+      if (!opt.cst) { gl = local_gamma(s); s.gammaLoc = gl; }
+      eigen_local_problem(s, s.vB.p, s.vRob.p, gl, false, cut, ws, vals, vecs, counts);
     }
-    // level 1: factor A_dir (or A_rob), src/geneo.cpp:126-148
-    const double tl1 = now_s();
-    if (!s.L1) s.L1.reset(new LdltFactor(s.plan));  // a re-factorization overwrites the resident factor in place
-    HostProfScope hp("lvl1 factorize");
-    FactorStats fs = s.L1->factorize(opt.lvl1ORAS ? s.vRob.p : s.pat.val.p, pivTol, ws, st);
-    allFactorSeconds += fs.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
-    s.negL1 = fs.neg;
-    s.perturbed = fs.perturbed;
-    lvl1SetupMinvTime += now_s() - tl1;
-    factorBytes += (int64_t)s.L1->L.bytes();
-    factorNnz += s.plan->sym.lSize;
-    factorFlops += s.plan->sym.flops;
-    estimDimE += s.estim;
-    realDimE += s.nev;
-    nicolaides += s.nicolaides;
+    assemble_z(s, vals, vecs, counts);
   }
+  // level 1: factor A_dir (or A_rob), src/geneo.cpp:126-148
+  const double tl1 = now_s();
+  if (!s.L1) s.L1.reset(new LdltFactor(s.plan));  // a re-factorization overwrites the resident factor in place
+  HostProfScope hp("lvl1 factorize");
+  FactorStats fs = s.L1->factorize(opt.lvl1ORAS ? s.vRob.p : s.pat.val.p, pivTol, ws, st);
+  allFactorSeconds += fs.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
+  s.negL1 = fs.neg;
+  s.perturbed += fs.perturbed;
+  lvl1SetupMinvTime += now_s() - tl1;
+  account_subdomain(s);
+}
+
+void GeneoPC::account_subdomain(const SubdomainState& s) {
+  factorBytes += (int64_t)s.L1->L.bytes();
+  factorNnz += s.plan->sym.lSize;
+  factorFlops += s.plan->sym.flops;
+  estimDimE += s.estim;
+  realDimE += s.nev;
+  nicolaides += s.nicolaides;
+}
+
+// estimateNumberOfEigenValues (src/geneo.cpp:502-533) from the inertia of A - param B (Sylvester)
+int GeneoPC::sylvester_estimate(SubdomainState& s, int neg, int perturbedS, bool tauPb, int cut) {
+  // tau problem: #eigenvalues below tau = negative pivots; gamma problem: #above gamma = positive pivots (zero / perturbed
+  // pivots are neither: the reference counts pcNbPosEV)
+  int est = tauPb ? neg : (s.n - neg - perturbedS);
+  est = std::max(0, std::min(est, s.n));
+  if (cut > 0 && est > cut) est = cut;
+  s.estim += est;
+  s.perturbed += perturbedS;
+  return est;
 }
 
 // eigenLocalProblem (src/geneo.cpp:842-963) + estimateNumberOfEigenValues (:502-533) + eigenLocalSolve (:626-722)
-int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb,
+int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb, int cut,
                                  LdltWorkspace& ws, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs,
                                  std::vector<int>& counts) {
   HostProfScope hpElp("eigen_local_problem");
-  const int n = s.n;
   const int64_t nnz = s.pat.nnz;
-  const double anorm = s.anorm;
-  const double pivTol = opt.pivRel * std::max(anorm, 1e-300);
-  int nev = 1;  // SLEPc default when nothing is requested
+  const double pivTol = opt.pivRel * std::max(s.anorm, 1e-300);
   int est = 0;
   LdltFactor tmp(s.plan);
   tmp.L = std::move(ws.spareL);  // cudaMalloc/cudaFree of a multi-GB factor per factorization costs more than the kernels
   if (!opt.noSyl) {
     const double t0 = now_s();
-    DevBuf<double> vS((size_t)nnz);
-    vals_axpby(nnz, vA, param, vB, vS.p, st);  // A - param B, src/geneo.cpp:511-515
+    if ((int64_t)s.vS.n < nnz) s.vS.alloc((size_t)nnz);
+    vals_axpby(nnz, vA, param, vB, s.vS.p, st);  // A - param B, src/geneo.cpp:511-515
     HostProfScope hp("syl factorize");
-    FactorStats fs = tmp.factorize(vS.p, pivTol, ws, st);
+    FactorStats fs = tmp.factorize(s.vS.p, pivTol, ws, st);
     allFactorSeconds += fs.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
-    est = tauPb ? fs.neg : (n - fs.neg);  // #eigenvalues below tau / above gamma (Sylvester)
-    if (est > n) est = n;
-    if (opt.cut > 0 && est > opt.cut) est = opt.cut;
-    s.estim += est;
-    s.perturbed += fs.perturbed;
+    est = sylvester_estimate(s, fs.neg, fs.perturbed, tauPb, cut);
     const double dt = now_s() - t0;
     lvl2SetupSylTime += dt;
     (tauPb ? lvl2SetupTauSylTime : lvl2SetupGammaSylTime) += dt;
-    if (est > 0) nev = est;
   }
-  if (opt.cut > 0 && nev > opt.cut) nev = opt.cut;
-  std::vector<double> lam;
-  DevBuf<double> X;
   int got = 0;
   if (opt.noSyl || est > 0) {
     const double t0 = now_s();
-    // Two guard pairs beyond the Sylvester estimate: the threshold filter below decides what is kept, so a pivot of
-    // A - theta B whose sign is lost to rounding (no pivoting across pivot blocks) cannot drop a genuine GenEO vector.
-    const int guard = (!opt.noSyl && (opt.cut <= 0 || nev < opt.cut)) ? 2 : 0;
-    EigOptions eo;
-    // Block of 8 by default.  -els2_eps_block 16 sends 16 right-hand sides per pass over the factor (k_solve_ring<16>),
-    // but measured on 8 x 80^3 the wider block needs a 45-60 % larger Krylov space for the same pairs (13-16 steps of 16
-    // against 18-19 steps of 8): 1.13 s against 0.93 s for the eight eigen-solves.
-    eo.block = opt.epsBlock > 0 ? opt.epsBlock : 8;
-    eo.tol = opt.epsTol; eo.maxDim = opt.epsMaxDim; eo.invert = tauPb;
-    eo.ws = &eigWs;
-    EigResult er;
-    if (tauPb) {  // A x = lambda B x, smallest: T = A^-1 B
-      { HostProfScope hp("eig factorize"); FactorStats f2 = tmp.factorize(vA, pivTol, ws, st);
-        allFactorSeconds += f2.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++; }
-      HostProfScope hp("eig block_lanczos");
-      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vB, std::min(nev + guard, n), eo, er, st);
-    } else {      // A x = lambda B x, largest: T = B^-1 A, self-adjoint in the A inner product
-      FactorStats f2 = tmp.factorize(vB, pivTol, ws, st);
+    {  // shift-invert factor: A (tau problem: T = A^-1 B) or B (gamma problem: T = B^-1 A, self-adjoint in the A inner product)
+      HostProfScope hp("eig factorize");
+      FactorStats f2 = tmp.factorize(tauPb ? vA : vB, pivTol, ws, st);
       allFactorSeconds += f2.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
-      block_lanczos(n, tmp, s.pat.ptr.p, s.pat.idx.p, vA, std::min(nev + guard, n), eo, er, st);
     }
-    if (er.nconv < (int)er.lambda.size())
-      fprintf(stderr, "WRNG: geneo_b200: eigen solve of subdomain %d converged %d/%d pairs (dim %d)\n", s.id, er.nconv,
-              (int)er.lambda.size(), er.dim);
-    s.eigSteps += er.steps;
-    s.eigDim = std::max(s.eigDim, er.dim);
-    // keep lambda <= tau (tau) / >= gamma (gamma): src/geneo.cpp:713-714.  Kept pairs are a prefix (sorted).
-    for (size_t i = 0; i < er.lambda.size(); i++) {
-      const bool keep = tauPb ? (er.lambda[i] <= param) : (er.lambda[i] >= param);
-      if (!keep) break;
-      if (opt.cut > 0 && (int)lam.size() >= opt.cut) break;  // -geneo_cut caps what is kept (src/geneo.cpp:532, 871-879)
-      lam.push_back(er.lambda[i]);
-    }
-    got = (int)lam.size();
-    if (got > 0) {
-      X.alloc((size_t)n * got);
-      copy_cols(n, er.vecs.p, (int)er.lambda.size(), X.p, got, got, st);
-      CUDA_CHECK(::geneo::sync_stream(st));
-    }
+    got = eigen_finish(s, tmp, vA, vB, param, tauPb, est, cut, vals, vecs, counts);
     const double dt = now_s() - t0;
     lvl2SetupEigTime += dt;
     (tauPb ? lvl2SetupTauEigTime : lvl2SetupGammaEigTime) += dt;
   }
   ws.spareL = std::move(tmp.L);
   tmp.release();
+  return got;
+}
+
+// Block Lanczos with the shift-invert factor `fac`, threshold filter (src/geneo.cpp:713-714), Nicolaides rule (:897-944).
+int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double* vA, const double* vB, double param, bool tauPb,
+                          int est, int cut, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts) {
+  const int n = s.n;
+  const int64_t nnz = s.pat.nnz;
+  int nev = est > 0 ? est : 1;  // SLEPc default when nothing is requested
+  if (cut > 0 && nev > cut) nev = cut;
+  // Two guard pairs beyond the Sylvester estimate: the threshold filter below decides what is kept, so a pivot of
+  // A - theta B whose sign is lost to rounding (no pivoting across pivot blocks) cannot drop a genuine GenEO vector.
+  const int guard = (!opt.noSyl && (cut <= 0 || nev < cut)) ? 2 : 0;
+  EigOptions eo;
+  // Block of 8 by default.  -els2_eps_block 16 sends 16 right-hand sides per pass over the factor (k_solve_ring<16>),
+  // but measured on 8 x 80^3 the wider block needs a 45-60 % larger Krylov space for the same pairs (13-16 steps of 16
+  // against 18-19 steps of 8): 1.13 s against 0.93 s for the eight eigen-solves.
+  eo.block = opt.epsBlock > 0 ? opt.epsBlock : 8;
+  eo.tol = opt.epsTol; eo.maxDim = opt.epsMaxDim; eo.invert = tauPb;
+  eo.ws = &eigWs;
+  EigResult er;
+  {
+    HostProfScope hp("eig block_lanczos");
+    block_lanczos(n, fac, s.pat.ptr.p, s.pat.idx.p, tauPb ? vB : vA, std::min(nev + guard, n), eo, er, st);
+  }
+  if (er.nconv < (int)er.lambda.size())
+    fprintf(stderr, "WRNG: geneo_b200: eigen solve of subdomain %d converged %d/%d pairs (dim %d)\n", s.id, er.nconv,
+            (int)er.lambda.size(), er.dim);
+  s.eigSteps += er.steps;
+  s.eigDim = std::max(s.eigDim, er.dim);
+  // keep lambda <= tau (tau) / >= gamma (gamma): src/geneo.cpp:713-714.  Candidates are a prefix (sorted); like the
+  // reference (which only walks EPSGetConverged pairs, :700-722) a pair whose residual did not reach the tolerance is not kept.
+  std::vector<double> lam;
+  std::vector<int> keepIdx;
+  for (size_t i = 0; i < er.lambda.size(); i++) {
+    const bool keep = tauPb ? (er.lambda[i] <= param) : (er.lambda[i] >= param);
+    if (!keep) break;
+    if (cut > 0 && (int)lam.size() >= cut) break;  // -geneo_cut caps what is kept (src/geneo.cpp:532, 871-879)
+    const bool conv = er.nconv >= (int)er.lambda.size() || i >= er.resid.size() || er.resid[i] <= eo.tol;
+    if (!conv) continue;
+    lam.push_back(er.lambda[i]);
+    keepIdx.push_back((int)i);
+  }
+  const int got = (int)lam.size();
+  DevBuf<double> X;
+  if (got > 0) {
+    X.alloc((size_t)n * got);
+    bool prefix = true;
+    for (int q = 0; q < got; q++) prefix = prefix && keepIdx[q] == q;
+    if (prefix) copy_cols(n, er.vecs.p, (int)er.lambda.size(), X.p, got, got, st);
+    else for (int q = 0; q < got; q++) copy_cols(n, er.vecs.p + keepIdx[q], (int)er.lambda.size(), X.p + q, got, 1, st);
+    CUDA_CHECK(::geneo::sync_stream(st));
+  }
   // Nicolaides (src/geneo.cpp:897-944): add the constant vector when eigenvalues were kept, none is ~0 and 1 is in ker(A)
   bool addOne = false;
   if (tauPb && got > 0 && *std::min_element(lam.begin(), lam.end()) >= DBL_EPSILON) {
@@ -959,6 +1003,209 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
     s.nicolaides += 1;
   }
   return got;
+}
+
+// =====================================================================================================================
+// Pipelined numeric setup (one level-2 pencil or none): the three factorizations of every subdomain -- S = A_neu - tau B
+// (inertia), A_neu (shift-invert factor of the eigen-solve), A_dir / A_rob (the resident level-1 factor) -- are enqueued by a
+// helper thread on a few LANES (stream + update arenas + transient factor), level by level round-robin over the lanes, so
+// that independent factorizations overlap on the device; this thread runs the host-driven block Lanczos of subdomain p on
+// the library's stream as soon as p's shift-invert factor is there -- the latency-bound eigen-solve hides behind the
+// DMMA tiles of the other lanes.  Dependencies: CUDA events between streams, two host flags per subdomain between the threads.
+// =====================================================================================================================
+struct GeneoPC::Lane {
+  cudaStream_t st = nullptr;
+  LdltWorkspace ws;
+  DevBuf<double> T;          // transient factor (S, then A_neu) of the subdomain currently in the lane
+  int* hc = nullptr;         // pinned: {neg, perturbed} of S, of A_neu, of A_dir
+  ~Lane() { if (st) cudaStreamDestroy(st); if (hc) cudaFreeHost(hc); }
+};
+
+void GeneoPC::numeric_pipeline() {
+  const int P = (int)subs.size();
+  const bool l2 = opt.lvl2 >= 1, syl = l2 && !opt.noSyl;
+  // ---- lanes: as many as fit next to the resident factors (each lane = update arenas + one transient factor) -------------
+  int64_t maxL = 0, maxArena = 0, sumL = 0;
+  for (auto& s : subs) {
+    const Symbolic& S = s.plan->sym;
+    maxL = std::max(maxL, S.lSize);
+    maxArena = std::max(maxArena, 2 * S.uArena + S.cArena + 2 * S.wArena);
+    if (!s.L1 || (int64_t)s.L1->L.n < S.lSize) sumL += S.lSize;
+  }
+  int want = std::min(P, 4);
+  if (const char* e = getenv("GENEO_LANES")) want = std::max(1, std::min(P, atoi(e)));
+  {
+    size_t freeB = 0, totB = 0;
+    CUDA_CHECK(cudaMemGetInfo(&freeB, &totB));
+    int64_t have = 0;  // what the existing lanes already hold
+    for (auto& L : lanes) have += (int64_t)(L->T.cap + L->ws.u0.cap + L->ws.u1.cap + L->ws.uc.cap + L->ws.w0.cap + L->ws.w1.cap);
+    const double perLane = 8. * ((l2 ? (double)maxL : 0.) + (double)maxArena);
+    const double avail = (double)freeB + (double)have - 8. * (double)sumL - 6e9;  // resident factors still to come, Lanczos buffers, slack
+    while (want > 1 && perLane * want > avail) want--;
+  }
+  while ((int)lanes.size() > want) lanes.pop_back();
+  while ((int)lanes.size() < want) {
+    lanes.emplace_back(new Lane());
+    CUDA_CHECK(cudaStreamCreateWithFlags(&lanes.back()->st, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaHostAlloc((void**)&lanes.back()->hc, 6 * sizeof(int), cudaHostAllocDefault));
+  }
+  const int NL = (int)lanes.size();
+  // every allocation of the concurrent region happens here, before it starts (the block cache is stream-ordered on ONE stream)
+  for (auto& s : subs) {
+    if (!s.L1) s.L1.reset(new LdltFactor(s.plan));
+    if ((int64_t)s.L1->L.n < s.plan->sym.lSize) s.L1->L.alloc((size_t)s.plan->sym.lSize);
+    if (l2 && (int64_t)s.vB.n < s.pat.nnz) s.vB.alloc((size_t)s.pat.nnz);
+    if (syl && (int64_t)s.vS.n < s.pat.nnz) s.vS.alloc((size_t)s.pat.nnz);
+  }
+  for (int j = 0; j < NL; j++) {
+    for (int p = j; p < P; p += NL) lanes[j]->ws.ensure(subs[p].plan->sym);
+    if (l2 && (int64_t)lanes[j]->T.n < maxL) lanes[j]->T.alloc((size_t)maxL);
+  }
+  CUDA_CHECK(cudaDeviceSynchronize());
+
+  std::vector<cudaEvent_t> evS(P, nullptr), evN(P, nullptr), evD(P, nullptr);
+  for (int p = 0; p < P; p++) {
+    CUDA_CHECK(cudaEventCreateWithFlags(&evS[p], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&evN[p], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&evD[p], cudaEventDisableTiming));
+  }
+  struct EvGuard { std::vector<cudaEvent_t>*a, *b, *c; ~EvGuard() { for (auto* v : {a, b, c}) for (auto e : *v) if (e) cudaEventDestroy(e); } } evGuard{&evS, &evN, &evD};
+  std::vector<std::unique_ptr<LdltFactor>> tmpF(P);
+  // pinned landing zone of the level-1 counters (a device -> pageable copy would block the enqueueing thread)
+  struct PinnedInts { int* p = nullptr; ~PinnedInts() { if (p) cudaFreeHost(p); } } hcDpin;
+  CUDA_CHECK(cudaHostAlloc((void**)&hcDpin.p, 2 * (size_t)P * sizeof(int), cudaHostAllocDefault));
+  int* hcD = hcDpin.p;
+  std::fill(hcD, hcD + 2 * (size_t)P, 0);
+  std::mutex mtx;
+  std::condition_variable cv;
+  std::vector<char> enqueued(P, 0), eigDone(P, 0);  // helper -> main: S and A_neu of p are enqueued; main -> helper: p's lane is free
+  std::string helperErr;
+  bool abortAll = false;
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  const double tPipe0 = now_s();
+
+  std::thread helper([&]() {
+    try {
+      CUDA_CHECK(cudaSetDevice(dev));
+      for (int g0 = 0; g0 < P; g0 += NL) {
+        const int g1 = std::min(P, g0 + NL);
+        std::vector<FactorJob> jobs;
+        if (l2) {
+          for (int p = g0; p < g1; p++) {  // the lane's previous tenant must be through with its eigen-solve
+            if (p - NL >= 0) {
+              std::unique_lock<std::mutex> lk(mtx);
+              cv.wait(lk, [&]() { return eigDone[p - NL] != 0 || abortAll; });
+              if (abortAll) return;
+            }
+            Lane& L = *lanes[p - g0];
+            SubdomainState& s = subs[p];
+            tmpF[p].reset(new LdltFactor(s.plan));
+            tmpF[p]->L = std::move(L.T);
+            csr_scale_sym(s.n, s.pat.ptr.p, s.pat.idx.p, s.pat.val.p, s.d.p, s.vB.p, L.st);  // B = D A_dir D, src/geneo.cpp:1243-1246
+            if (syl) vals_axpby(s.pat.nnz, s.vNeu.p, opt.tau, s.vB.p, s.vS.p, L.st);          // S = A_neu - tau B, :511-515
+          }
+          if (syl) {
+            jobs.clear();
+            for (int p = g0; p < g1; p++) {
+              Lane& L = *lanes[p - g0];
+              FactorJob J;
+              J.F = tmpF[p].get(); J.vals = subs[p].vS.p; J.pivTol = opt.pivRel * std::max(subs[p].anorm, 1e-300);
+              J.ws = &L.ws; J.st = L.st; J.hostCounters = L.hc;
+              jobs.push_back(J);
+            }
+            factorize_enqueue(jobs);
+            for (int p = g0; p < g1; p++) CUDA_CHECK(cudaEventRecord(evS[p], lanes[p - g0]->st));
+          }
+          jobs.clear();
+          for (int p = g0; p < g1; p++) {
+            Lane& L = *lanes[p - g0];
+            FactorJob J;
+            J.F = tmpF[p].get(); J.vals = subs[p].vNeu.p; J.pivTol = opt.pivRel * std::max(subs[p].anorm, 1e-300);
+            J.ws = &L.ws; J.st = L.st; J.hostCounters = L.hc + 2;
+            jobs.push_back(J);
+          }
+          factorize_enqueue(jobs);
+          for (int p = g0; p < g1; p++) CUDA_CHECK(cudaEventRecord(evN[p], lanes[p - g0]->st));
+          { std::lock_guard<std::mutex> lk(mtx); for (int p = g0; p < g1; p++) enqueued[p] = 1; }
+          cv.notify_all();
+        }
+        jobs.clear();
+        for (int p = g0; p < g1; p++) {
+          Lane& L = *lanes[p - g0];
+          FactorJob J;
+          J.F = subs[p].L1.get(); J.vals = opt.lvl1ORAS ? subs[p].vRob.p : subs[p].pat.val.p;
+          J.pivTol = opt.pivRel * std::max(subs[p].anorm, 1e-300);
+          J.ws = &L.ws; J.st = L.st; J.hostCounters = nullptr;  // (copied to hcD[p] below: the lane's next tenant reuses L.hc)
+          jobs.push_back(J);
+        }
+        factorize_enqueue(jobs);
+        for (int p = g0; p < g1; p++) {
+          Lane& L = *lanes[p - g0];
+          CUDA_CHECK(cudaMemcpyAsync(&hcD[2 * (size_t)p], L.ws.counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, L.st));
+          CUDA_CHECK(cudaEventRecord(evD[p], L.st));
+        }
+      }
+    } catch (std::exception& e) {
+      std::lock_guard<std::mutex> lk(mtx);
+      helperErr = e.what();
+      abortAll = true;
+    }
+    cv.notify_all();
+  });
+  struct Joiner { std::thread& t; std::mutex& m; std::condition_variable& c; bool& ab; ~Joiner() { { std::lock_guard<std::mutex> lk(m); ab = true; } c.notify_all(); if (t.joinable()) t.join(); } } joiner{helper, mtx, cv, abortAll};
+
+  if (l2) {
+    for (int p = 0; p < P; p++) {
+      SubdomainState& s = subs[p];
+      Lane& L = *lanes[p % NL];
+      {
+        std::unique_lock<std::mutex> lk(mtx);
+        cv.wait(lk, [&]() { return enqueued[p] != 0 || abortAll; });
+        if (abortAll && !enqueued[p]) break;
+      }
+      int est = 0;
+      if (syl) {
+        const double t0 = now_s();
+        CUDA_CHECK(cudaEventSynchronize(evS[p]));
+        est = sylvester_estimate(s, L.hc[0], L.hc[1], true, opt.cut);
+        lvl2SetupSylTime += now_s() - t0; lvl2SetupTauSylTime += now_s() - t0;
+      }
+      std::vector<double> vals;
+      std::vector<DevBuf<double>> vecs;
+      std::vector<int> counts;
+      const double t0 = now_s();
+      CUDA_CHECK(cudaEventSynchronize(evN[p]));
+      if (opt.noSyl || est > 0) eigen_finish(s, *tmpF[p], s.vNeu.p, s.vB.p, opt.tau, true, est, opt.cut, vals, vecs, counts);
+      lvl2SetupEigTime += now_s() - t0; lvl2SetupTauEigTime += now_s() - t0;
+      assemble_z(s, vals, vecs, counts);
+      CUDA_CHECK(::geneo::sync_stream(st));  // the library's stream is done with the transient factor
+      {
+        std::lock_guard<std::mutex> lk(mtx);
+        L.T = std::move(tmpF[p]->L);
+        s.plan->selfL = nullptr;  // the plan's single-factor forest must re-read the factor pointer next time
+        eigDone[p] = 1;
+      }
+      cv.notify_all();
+    }
+  }
+  { std::lock_guard<std::mutex> lk(mtx); if (!helperErr.empty()) abortAll = true; }
+  helper.join();
+  if (!helperErr.empty()) throw Error(helperErr);
+  const double tl1 = now_s();
+  for (int p = 0; p < P; p++) {
+    CUDA_CHECK(cudaEventSynchronize(evD[p]));
+    subs[p].negL1 = hcD[2 * (size_t)p];
+    subs[p].perturbed += hcD[2 * (size_t)p + 1];
+  }
+  for (auto& L : lanes) CUDA_CHECK(cudaStreamSynchronize(L->st));
+  lvl1SetupMinvTime += now_s() - tl1;
+  for (int p = 0; p < P; p++) {
+    account_subdomain(subs[p]);
+    allFactorFlops += subs[p].plan->sym.flops * (1 + (l2 ? 1 : 0) + (syl ? 1 : 0));
+    allFactorCount += 1 + (l2 ? 1 : 0) + (syl ? 1 : 0);
+  }
+  allFactorSeconds += now_s() - tPipe0;  // span of the factorization pipeline (the eigen-solves run inside it)
 }
 
 // Z offsets (all_gather of nev_i, src/geneo.cpp:363-375), E = Z^T A Z (MatPtAP :1033), E^-1 (dcs2_, :1059-1065)

@@ -33,7 +33,7 @@ struct GeneoOptions {
   int epsBlock = 0;      // block size of the Lanczos eigen-solver (-els2_eps_block); 0: 8
   bool releaseWorkspace = false;  // free the factorization / eigen-solver workspaces after every setup
   int epsMaxDim = 0;     // -els2_eps_ncv like bound on the Krylov dimension (0 = automatic)
-  double pivRel = 1e-14; // static pivot threshold relative to max |a_ij| (stands for MUMPS CNTL(1/3), ICNTL(24))
+  double pivRel = 1e-14; // null-pivot threshold relative to max |a_ij| (stands for MUMPS CNTL(3), ICNTL(24) = 1, CNTL(5) = 1e20)
   bool timing = false;   // synchronise and time every apply phase (reference timers hdr/geneo.hpp:115-123)
   bool kernelTiming = false;  // CUDA-event pairs around the level-1 solve kernel (bench.py roofline leg), no host sync
 
@@ -54,6 +54,7 @@ struct SubdomainState {
   DevBuf<double> Z;       // n x nev row-major, solver order, already D-weighted
   CsrDev pat;             // permuted pattern of A_dir; pat.val = A_dir values
   DevBuf<double> vNeu, vRob;
+  DevBuf<double> vB, vS;  // D A_dir D and A_neu - tau B (values on the A_dir pattern), kept between re-setups
   std::vector<double> eigvals;
   int estim = 0, nicolaides = 0, eigSteps = 0, eigDim = 0, negL1 = 0, perturbed = 0;
   double tauLoc = -1., gammaLoc = -1.;
@@ -131,9 +132,19 @@ class GeneoPC {
 
  private:
   void numeric_subdomain(SubdomainState& s, LdltWorkspace& ws);
-  int eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb,
+  void numeric_pipeline();
+  bool use_pipeline() const;
+  int eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb, int cut,
                           LdltWorkspace& ws, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs,
                           std::vector<int>& counts);
+  int eigen_finish(SubdomainState& s, const LdltFactor& fac, const double* vA, const double* vB, double param, bool tauPb, int est,
+                   int cut, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts);
+  int sylvester_estimate(SubdomainState& s, int neg, int perturbedS, bool tauPb, int cut);
+  void assemble_z(SubdomainState& s, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts);
+  void account_subdomain(const SubdomainState& s);
+  double local_gamma(const SubdomainState& s) const;
+  struct Lane;
+  std::vector<std::unique_ptr<Lane>> lanes;  // streams + workspaces of the pipelined numeric setup, kept between re-setups
   void build_coarse();
   void level1(const double* xin, double* yout, bool addQ);
   SolveForest forest;

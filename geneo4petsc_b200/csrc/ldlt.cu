@@ -231,8 +231,12 @@ __global__ void __launch_bounds__(TD * TD) k_diag_invert(const WorkItem* __restr
   for (int p = 0; p < k; p++) {
     const double* cb = cbuf[p & 1];
     double d = cb[p];
-    if (!(fabs(d) >= pivTol)) { d = (d < 0.) ? -pivTol : pivTol; pert++; }
-    if (d < 0.) neg++;
+    // Null pivot (|d| < pivTol = 1e-14 max|a_ij|): fixed to a HUGE positive value, 1e20 max|a_ij| -- the semantics of MUMPS
+    // ICNTL(24) = 1 with CNTL(5) = 1e20, which the reference sets for every local solver (src/geneo.cpp:81-83): the
+    // corresponding solution component becomes 0 (a floating subdomain's constant mode is then supplied by the Nicolaides
+    // rule, src/geneo.cpp:897-944, instead of appearing twice).  Counted apart, neither negative nor positive (MUMPS INFOG(28)).
+    if (!(fabs(d) >= pivTol)) { d = pivTol * 1e34; pert++; }
+    else if (d < 0.) neg++;
     const double rinv = 1. / d;
     double ci[E], cjr[E];
 #pragma unroll
@@ -1185,58 +1189,78 @@ void LdltWorkspace::ensure(const Symbolic& s) {
   if (counters.n < 2) counters.alloc(2);
 }
 
-FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorkspace& ws, cudaStream_t st) {
-  const LdltPlan& P = *plan_;
+namespace {
+void factor_prepare(FactorJob& J) {
+  const LdltPlan& P = J.F->plan();
   const Symbolic& S = P.sym;
+  J.ws->ensure(S);
+  if ((int64_t)J.F->L.n < S.lSize) J.F->L.alloc((size_t)S.lSize);  // a recycled (larger) buffer is fine
+  CUDA_CHECK(cudaMemsetAsync(J.F->L.p, 0, (size_t)S.lSize * sizeof(double), J.st));
+  J.ws->counters.zero(J.st);
+  const int64_t cnt = (int64_t)P.dAsmSrc.n;
+  const int grid = (int)std::min<int64_t>((cnt + 255) / 256, 148 * 16);
+  if (cnt) k_assemble<<<GENEO_TICK(grid), 256, 0, J.st>>>(cnt, P.dAsmSrc.p, P.dAsmDst.p, J.vals, J.F->L.p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void factor_level(FactorJob& J, int l, int gst) {
+  const LdltPlan& P = J.F->plan();
+  LdltWorkspace& ws = *J.ws;
+  cudaStream_t st = J.st;
+  double* Lp = J.F->L.p;
+  const double pivTol = J.pivTol;
+  const WorkItem* items = P.dItems.p;
+  const UArenas ua{{ws.u0.p, ws.u1.p, ws.uc.p}};
+  double* Ucur = (l & 1) ? ws.u1.p : ws.u0.p;
+  double* Wcur = (l & 1) ? ws.w1.p : ws.w0.p;
+  const double* Wprev = (l & 1) ? ws.w0.p : ws.w1.p;
+  if (P.levelU[l] > 0) CUDA_CHECK(cudaMemsetAsync(Ucur, 0, (size_t)P.levelU[l] * sizeof(double), st));
+  for (auto& z : P.levelChainZero[l]) CUDA_CHECK(cudaMemsetAsync(ws.uc.p + z.first, 0, (size_t)z.second * sizeof(double), st));
+  if (P.eaddItems[l].cnt)
+    k_extend_add<<<GENEO_TICK(P.eaddItems[l].cnt), 256, 0, st>>>(items + P.eaddItems[l].off, P.dFronts.p, P.dRel.p, Lp, ua);
+  if (P.diagItems[l].cnt)
+    k_diag_invert<128, 16><<<GENEO_TICK(P.diagItems[l].cnt), 256, 0, st>>>(items + P.diagItems[l].off, P.dFronts.p, Lp, pivTol, ws.counters.p);
+  if (P.diagSmallItems[l].cnt)
+    k_diag_invert<32, 8><<<GENEO_TICK(P.diagSmallItems[l].cnt), 64, 0, st>>>(items + P.diagSmallItems[l].off, P.dFronts.p, Lp, pivTol, ws.counters.p);
+  if (P.copyItems[l].cnt)
+    k_copy_panel<<<GENEO_TICK(P.copyItems[l].cnt), 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, Lp, Wcur);
+  if (P.panelItems[l].cnt) {
+    if (gst == 2) k_panel<2><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.panelItems[l].off, P.dFronts.p, Lp, Wcur);
+    else k_panel<3><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.panelItems[l].off, P.dFronts.p, Lp, Wcur);
+  }
+  if (P.schurItems[l].cnt) {
+    if (gst == 2) k_schur<2><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schurItems[l].off, P.dFronts.p, Lp, Wcur, ua);
+    else k_schur<3><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schurItems[l].off, P.dFronts.p, Lp, Wcur, ua);
+  }
+  if (P.schur2Items[l].cnt) {
+    if (gst == 2) k_schur2<2><<<GENEO_TICK(P.schur2Items[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schur2Items[l].off, P.dFronts.p, Lp, Wcur, Wprev, ua);
+    else k_schur2<3><<<GENEO_TICK(P.schur2Items[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schur2Items[l].off, P.dFronts.p, Lp, Wcur, Wprev, ua);
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+void factorize_enqueue(std::vector<FactorJob>& jobs) {
+  const int gst = gemm_stages();
+  int gmax = 0;
+  for (auto& J : jobs) { factor_prepare(J); gmax = std::max(gmax, J.F->plan().sym.nlevels); }
+  for (int g = 0; g < gmax; g++)
+    for (auto& J : jobs) {
+      const int l = g - (gmax - J.F->plan().sym.nlevels);  // roots aligned
+      if (l >= 0) factor_level(J, l, gst);
+    }
+  for (auto& J : jobs)
+    if (J.hostCounters) CUDA_CHECK(cudaMemcpyAsync(J.hostCounters, J.ws->counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, J.st));
+}
+
+FactorStats LdltFactor::factorize(const double* dVals, double pivTol, LdltWorkspace& ws, cudaStream_t st) {
   FactorStats stats;
   const double t0 = now_s();
   HostProfScope hp("factorize: host side total");
-  const int gst = gemm_stages();
-  {
-    HostProfScope hpA("factorize: alloc");
-    ws.ensure(S);
-    if ((int64_t)L.n < S.lSize) L.alloc((size_t)S.lSize);  // a recycled (larger) buffer is fine
-  }
-  CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)S.lSize * sizeof(double), st));
-  ws.counters.zero(st);
-  {
-    const int64_t cnt = (int64_t)P.dAsmSrc.n;
-    const int grid = (int)std::min<int64_t>((cnt + 255) / 256, 148 * 16);
-    if (cnt) k_assemble<<<GENEO_TICK(grid), 256, 0, st>>>(cnt, P.dAsmSrc.p, P.dAsmDst.p, dVals, L.p);
-    CUDA_CHECK(cudaGetLastError());
-  }
-  const WorkItem* items = P.dItems.p;
-  const UArenas ua{{ws.u0.p, ws.u1.p, ws.uc.p}};
-  for (int l = 0; l < S.nlevels; l++) {
-    double* Ucur = (l & 1) ? ws.u1.p : ws.u0.p;
-    double* Wcur = (l & 1) ? ws.w1.p : ws.w0.p;
-    const double* Wprev = (l & 1) ? ws.w0.p : ws.w1.p;
-    if (P.levelU[l] > 0) CUDA_CHECK(cudaMemsetAsync(Ucur, 0, (size_t)P.levelU[l] * sizeof(double), st));
-    for (auto& z : P.levelChainZero[l]) CUDA_CHECK(cudaMemsetAsync(ws.uc.p + z.first, 0, (size_t)z.second * sizeof(double), st));
-    if (P.eaddItems[l].cnt)
-      k_extend_add<<<GENEO_TICK(P.eaddItems[l].cnt), 256, 0, st>>>(items + P.eaddItems[l].off, P.dFronts.p, P.dRel.p, L.p, ua);
-    if (P.diagItems[l].cnt)
-      k_diag_invert<128, 16><<<GENEO_TICK(P.diagItems[l].cnt), 256, 0, st>>>(items + P.diagItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
-    if (P.diagSmallItems[l].cnt)
-      k_diag_invert<32, 8><<<GENEO_TICK(P.diagSmallItems[l].cnt), 64, 0, st>>>(items + P.diagSmallItems[l].off, P.dFronts.p, L.p, pivTol, ws.counters.p);
-    if (P.copyItems[l].cnt)
-      k_copy_panel<<<GENEO_TICK(P.copyItems[l].cnt), 256, 0, st>>>(items + P.copyItems[l].off, P.dFronts.p, L.p, Wcur);
-    if (P.panelItems[l].cnt) {
-      if (gst == 2) k_panel<2><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, Wcur);
-      else k_panel<3><<<GENEO_TICK(P.panelItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.panelItems[l].off, P.dFronts.p, L.p, Wcur);
-    }
-    if (P.schurItems[l].cnt) {
-      if (gst == 2) k_schur<2><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, Wcur, ua);
-      else k_schur<3><<<GENEO_TICK(P.schurItems[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schurItems[l].off, P.dFronts.p, L.p, Wcur, ua);
-    }
-    if (P.schur2Items[l].cnt) {
-      if (gst == 2) k_schur2<2><<<GENEO_TICK(P.schur2Items[l].cnt), GEMM_THREADS, gemm_smem(2), st>>>(items + P.schur2Items[l].off, P.dFronts.p, L.p, Wcur, Wprev, ua);
-      else k_schur2<3><<<GENEO_TICK(P.schur2Items[l].cnt), GEMM_THREADS, gemm_smem(3), st>>>(items + P.schur2Items[l].off, P.dFronts.p, L.p, Wcur, Wprev, ua);
-    }
-    CUDA_CHECK(cudaGetLastError());
-  }
   int h[2] = {0, 0};
-  CUDA_CHECK(cudaMemcpyAsync(h, ws.counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  std::vector<FactorJob> jobs(1);
+  jobs[0].F = this; jobs[0].vals = dVals; jobs[0].pivTol = pivTol; jobs[0].ws = &ws; jobs[0].st = st; jobs[0].hostCounters = h;
+  factorize_enqueue(jobs);
   CUDA_CHECK(::geneo::sync_stream(st));
   stats.neg = h[0];
   stats.perturbed = h[1];

@@ -106,7 +106,7 @@ struct LdltWorkspace {
 class LdltFactor {
  public:
   explicit LdltFactor(std::shared_ptr<LdltPlan> plan) : plan_(plan) {}
-  // vals: device array aligned with the plan's input CSR pattern.  pivTol: |pivot| below it is replaced by +-pivTol.
+  // vals: device array aligned with the plan's input CSR pattern.  pivTol: a |pivot| below it is a null pivot, fixed to 1e34 pivTol (MUMPS CNTL(5) semantics).
   FactorStats factorize(const double* dVals, double pivTol, LdltWorkspace& ws, cudaStream_t st);
   // Solve in the PERMUTED ordering: X (n x ldx row-major block, columns j0..j0+nr-1) is overwritten by the forward
   // sweep, the result lands in Y (same layout).  nr in {1,2,4,8,16}.
@@ -118,6 +118,23 @@ class LdltFactor {
  private:
   std::shared_ptr<LdltPlan> plan_;
 };
+
+// One numeric factorization to be enqueued: F->L receives the factor of `vals` (device array aligned with the plan's input
+// pattern); everything runs on `st` with the scratch of `ws`.  hostCounters (2 ints, ideally pinned: {negative, perturbed
+// pivots}) are written when the stream reaches the end of the job -- nothing here synchronises.
+struct FactorJob {
+  LdltFactor* F = nullptr;
+  const double* vals = nullptr;
+  double pivTol = 0.;
+  LdltWorkspace* ws = nullptr;
+  cudaStream_t st = 0;
+  int* hostCounters = nullptr;
+};
+// Enqueue several INDEPENDENT factorizations, level by level round-robin over the jobs (levels aligned at the roots, where
+// the long serial chains of big fronts are), each job on its own stream with its own workspace: the device overlaps the
+// latency-bound kernels of one job (pivot-block inversions, small levels, launch tails) with the DMMA tiles of the others.
+// Two jobs may share stream + workspace (they then simply run back to back).  Launch only: no host synchronisation.
+void factorize_enqueue(std::vector<FactorJob>& jobs);
 
 double solve_stream_bench(int nf, int h, int k, int reps, double* gbps, int nlev = 1, int nr = 1);  // ms per solve; synthetic one-level forest
 

@@ -140,6 +140,75 @@ void generate_grid(const GridGenOptions& o, Mesh& m, std::vector<int>* elemPartO
   m.finalize();
 }
 
+int parse_graph_args(const std::string& args, GraphGenOptions& o) {
+  std::stringstream ss(args);
+  while (ss) {
+    std::string opt;
+    ss >> opt;
+    if (opt == "--size") { ss >> o.size; if (!ss) return 1; }
+    if (opt == "--level") { ss >> o.level; if (!ss) return 1; }
+    if (opt == "--weakScaling") { ss >> o.weakScaling; if (!ss) return 1; }
+    if (opt == "--inpEps") { ss >> o.inpEps; if (!ss) return 1; }
+    if (opt == "--noGround") o.noGround = true;
+  }
+  return (o.size >= 1 && o.level >= 0 && o.weakScaling >= 1) ? 0 : 1;
+}
+
+void generate_graph(const GraphGenOptions& o, Mesh& m) {
+  const int B = (int)std::sqrt((double)(o.size * o.weakScaling));  // tst/graph/graph.cpp:153
+  GENEO_CHECK(B >= 2, "graph generator: block size must be at least 2");
+  const int64_t nblocks = 1 + 4 * (int64_t)o.level;
+  const int64_t g0 = o.noGround ? 0 : 1;  // node 0 is the ground
+  const int64_t nn = g0 + nblocks * B * B;
+  GENEO_CHECK(nn < (int64_t)2147483647, "graph too large for 32-bit node ids");
+  m = Mesh();
+  m.nbNode = (int)nn;
+  const int64_t perBlock = 2 * (int64_t)B * (B - 1) + (o.noGround ? 0 : 4 * B);
+  const int64_t ne = nblocks * perBlock + (int64_t)o.level * 8 * B;
+  m.elemPtr.reserve(ne + 1); m.elemIdx.reserve(2 * ne); m.matVal.reserve(4 * ne);
+  m.elemPtr.push_back(0);
+  auto edge = [&](int64_t a, int64_t b, double w) {
+    m.elemIdx.push_back((int)a); m.elemIdx.push_back((int)b);
+    m.matVal.push_back(w * (1. + o.inpEps)); m.matVal.push_back(w * -1.);
+    m.matVal.push_back(w * -1.); m.matVal.push_back(w * (1. + o.inpEps));
+    m.elemPtr.push_back((int64_t)m.elemIdx.size());
+  };
+  // block bi: nodes base + r B + c; its four borders in ascending node order: 0 up (first row), 1 right (last column),
+  // 2 down (last row), 3 left (first column)
+  auto base = [&](int64_t bi) { return g0 + bi * B * B; };
+  auto border = [&](int64_t bi, int which, int i) -> int64_t {
+    switch (which) {
+      case 0: return base(bi) + i;
+      case 1: return base(bi) + (int64_t)i * B + (B - 1);
+      case 2: return base(bi) + (int64_t)(B - 1) * B + i;
+      default: return base(bi) + (int64_t)i * B;
+    }
+  };
+  auto block = [&](int64_t bi, double w) {
+    const int64_t b0 = base(bi);
+    for (int r = 0; r < B; r++)
+      for (int c = 0; c + 1 < B; c++) edge(b0 + (int64_t)r * B + c, b0 + (int64_t)r * B + c + 1, w);
+    for (int i = 0; i < B; i++)        // columns from the last one to the first, each walked upwards
+      for (int j = 0; j + 1 < B; j++) edge(b0 + (int64_t)(B - 1 - j) * B + (B - 1 - i), b0 + (int64_t)(B - 2 - j) * B + (B - 1 - i), w);
+    if (!o.noGround)
+      for (int which = 0; which < 4; which++)
+        for (int i = 0; i < B; i++) edge(border(bi, which, i), 0, w);
+  };
+  auto blk = [&](int l, int b) -> int64_t { return l == 0 ? 0 : 1 + 4 * (int64_t)(l - 1) + b; };  // level 0 = the central block, four times
+  block(0, 1.);
+  for (int l = 1; l <= o.level; l++) {
+    for (int b = 0; b < 4; b++) block(blk(l, b), l + 1.);
+    const double w = 0.5 * (l + 1.);
+    for (int b = 0; b < 4; b++) {  // around the level: right->up, down->right, left->down, up->left of the next block
+      const int from = (b + 1) % 4, to = b;
+      for (int i = 0; i < B; i++) edge(border(blk(l, b), from, i), border(blk(l, (b + 1) % 4), to, i), w);
+    }
+    for (int b = 0; b < 4; b++)    // to the previous level: border b of the inner block -> the opposite border of the outer one
+      for (int i = 0; i < B; i++) edge(border(blk(l - 1, b), b, i), border(blk(l, b), (b + 2) % 4, i), w);
+  }
+  m.finalize();
+}
+
 int read_input_file(const std::string& path, double inpEps, Mesh& m) {
   std::ifstream inp(path);
   if (!inp) { std::cerr << "Error: can not open " << path << std::endl; return 1; }

@@ -42,6 +42,17 @@ struct GridGenOptions {
 int parse_gen_args(const std::string& args, GridGenOptions& o);  // same "--size S --dim D ..." grammar
 void generate_grid(const GridGenOptions& o, Mesh& m, std::vector<int>* elemPartOut = nullptr);
 int grid_edge(const GridGenOptions& o);  // edge length incl. the reference's weak-scaling float truncation
+// Graph Laplacian of tst/graph (BASELINE configs[3]): square blocks of blockSize^2 nodes (4-neighbour grids, weight l+1 at
+// level l), one central block and 4 blocks per level, each level chained to itself and to the previous one through its
+// borders (weight (l+1)/2), optionally every border node tied to node 0 ("ground").  Same element sequence and node
+// numbering as the reference plug-in (tst/graph/graph.cpp:38-205), emitted in closed form: O(N), no std::set.
+struct GraphGenOptions {
+  int size = 4, level = 1, weakScaling = 1;
+  double inpEps = 1e-4;
+  bool noGround = false;
+};
+int parse_graph_args(const std::string& args, GraphGenOptions& o);
+void generate_graph(const GraphGenOptions& o, Mesh& m);
 int read_input_file(const std::string& path, double inpEps, Mesh& m);             // text format A
 int read_rhs_file(const std::string& path, int n, std::vector<double>& b);        // text format B
 

@@ -160,3 +160,73 @@ def allreduce_sum(pc, values):
     v = np.ascontiguousarray(values, dtype=np.float64).copy()
     _chk(lib.geneo_allreduce_sum(pc.h, _p(v, _f64p), C.c_int(len(v))))
     return v
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# General partitions on several GPUs (METIS k-way or any caller-supplied partition): which rank holds which subdomain?
+# The reference has one MPI rank per subdomain (src/geneo4PETSc.cpp:604); here a rank = a GPU = several subdomains, so the
+# subdomains are GROUPED: equal counts per rank, grown greedily along the heaviest interfaces so that most neighbours of a
+# subdomain sit on the same GPU (halo traffic = the cut between the groups).
+# ---------------------------------------------------------------------------------------------------------------------
+def part_adjacency(elem_ptr, elem_idx, elem_part, nb_part):
+    """W[p, q] = number of mesh nodes shared by the elements of parts p and q (p != q); dual (element) partitions."""
+    import scipy.sparse as sp
+    elem_ptr = np.asarray(elem_ptr, dtype=np.int64)
+    elem_idx = np.asarray(elem_idx, dtype=np.int64)
+    elem_of = np.repeat(np.arange(len(elem_ptr) - 1), np.diff(elem_ptr))
+    nn = int(elem_idx.max()) + 1
+    inc = sp.csr_matrix((np.ones(len(elem_idx), dtype=np.int8), (elem_idx, np.asarray(elem_part, dtype=np.int64)[elem_of])),
+                        shape=(nn, nb_part))
+    inc.data[:] = 1
+    inc.sum_duplicates()
+    inc.data[:] = 1
+    w = (inc.T @ inc).toarray().astype(np.int64)
+    np.fill_diagonal(w, 0)
+    return w
+
+
+def assign_ranks(w, world):
+    """sub_rank[p] from the interface weights w (nb_part x nb_part, symmetric): groups of ceil/floor(nb_part / world)
+    subdomains, each grown from the unassigned subdomain with the least outside contact by repeatedly taking the unassigned
+    subdomain most strongly tied to the group.  Deterministic (ties -> lowest index): every rank computes the same map."""
+    w = np.asarray(w, dtype=np.float64)
+    P = w.shape[0]
+    sub_rank = -np.ones(P, dtype=np.int32)
+    sizes = [P // world + (1 if r < P % world else 0) for r in range(world)]
+    for r in range(world):
+        free = np.flatnonzero(sub_rank < 0)
+        if len(free) == 0:
+            break
+        contact = w[np.ix_(free, free)].sum(axis=1)
+        seed = free[int(np.argmin(contact))]
+        sub_rank[seed] = r
+        for _ in range(sizes[r] - 1):
+            free = np.flatnonzero(sub_rank < 0)
+            if len(free) == 0:
+                break
+            tie = w[np.ix_(free, np.flatnonzero(sub_rank == r))].sum(axis=1)
+            sub_rank[free[int(np.argmax(tie))]] = r
+    sub_rank[sub_rank < 0] = world - 1
+    return sub_rank
+
+
+def metis_problem(problem, nb_part, world, rank, dual=True, overlap=0):
+    """Every rank partitions the SAME (already generated / read) mesh with METIS -- deterministic, so the ranks agree without
+    talking --, groups the parts onto the ranks (assign_ranks) and assembles only its own subdomains.  Returns sub_rank."""
+    probe = api.Problem()
+    ep, ei, em = problem.mesh()
+    s = problem.sizes()
+    probe.set_mesh(s["nb_node"], ep, ei, em)
+    from .api import lib as _lib
+    # partition only: METIS through the library's own entry (the decomposition of ALL subdomains is not needed for it)
+    epart = np.zeros(s["nb_elem"], dtype=np.int32)
+    npart = np.zeros(s["nb_node"], dtype=np.int32)
+    _chk(_lib.geneo_problem_partition(probe.h, C.c_int(nb_part), C.c_int(1 if dual else 0), _p(epart, _i32p), _p(npart, _i32p)))
+    del probe
+    if dual:
+        w = part_adjacency(ep, ei, epart, nb_part)
+    else:
+        w = part_adjacency(ep, ei, npart[ei[np.asarray(ep[:-1], dtype=np.int64)]], nb_part)
+    sub_rank = assign_ranks(w, world)
+    decompose_owned(problem, nb_part, sub_rank, rank, dual, overlap, elem_part=epart if dual else None, node_part=None if dual else npart)
+    return sub_rank

@@ -37,8 +37,9 @@ int geneo_problem_destroy(geneo_problem_t p);
  * elemMat = the dense row-major n_e x n_e matrices of all elements back to back. */
 int geneo_problem_set_mesh(geneo_problem_t p, uint32_t nbNode, uint32_t nbElem, const uint32_t* elemPtr,
                            const uint32_t* elemIdx, const double* elemMat);
-/* --inpLibA replacement for the reference's own generators: kind = "laplacian" (tst/laplacian/laplacian.cpp:56-188) or
- * "heat" (tst/heat/heat.cpp:117-261); args uses the same "--size S --dim D --kappa K interp ..." grammar. */
+/* --inpLibA replacement for the reference's own generators: kind = "laplacian" (tst/laplacian/laplacian.cpp:56-188),
+ * "heat" (tst/heat/heat.cpp:117-261) or "graph" (tst/graph/graph.cpp:38-205); args uses the plug-ins' own grammar
+ * ("--size S --dim D --kappa K interp ...", "--size S --level L --noGround ..."). */
 int geneo_problem_generate(geneo_problem_t p, const char* kind, const char* args);
 /* --inpFileA (src/geneo4PETSc.cpp:144-194). */
 int geneo_problem_read_file(geneo_problem_t p, const char* path, double inpEps);
@@ -47,6 +48,8 @@ int geneo_problem_read_file(geneo_problem_t p, const char* path, double inpEps);
  * matrices R_i A R_i^T (src/geneo.cpp:1699).  nbPart replaces "mpirun -n" (src/geneo4PETSc.cpp:604). */
 int geneo_problem_decompose(geneo_problem_t p, int nbPart, int metisDual, int overlap, const int32_t* elemPart,
                             const int32_t* nodePart);
+/* The METIS partition alone (src/geneo4PETSc.cpp:381-445), without the decomposition: elemPart[nbElem], nodePart[nbNode]. */
+int geneo_problem_partition(geneo_problem_t p, int nbPart, int metisDual, int32_t* elemPart, int32_t* nodePart);
 /* Pre-decomposed input -- what the PETSc plug-in itself receives (initGenEOPC, hdr/geneo.hpp:30-35; PCGenEOSetup,
  * hdr/geneo_c.h:10): per subdomain the local-to-global map (ISLocalToGlobalMapping; ascending, the reference's local
  * numbering src/geneo4PETSc.cpp:485-489), the local Neumann matrix of the MATIS (MatISGetLocalMat, src/geneo.cpp:1714)

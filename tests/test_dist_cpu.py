@@ -41,6 +41,19 @@ def _worker(rank, world, port, mode, q):
             sub_rank = np.array([0, 0, 1, 1], dtype=np.int32)
             prob = g.Problem().generate(kind, args)
             dist.decompose_owned(prob, nparts, sub_rank, rank, True, 0, elem_part=ep)
+        elif mode == "metis_grouped":  # METIS k-way, parts grouped onto the ranks along the heaviest interfaces
+            nparts = 6
+            full, a_glob = _global_operator(g, kind, args, nparts)
+            prob = g.Problem().generate(kind, args)
+            sub_rank = dist.metis_problem(prob, nparts, world, rank)
+            assert np.array_equal(prob.partition()[0], full.partition()[0])  # METIS is deterministic: the ranks agree
+            assert sorted(np.bincount(sub_rank, minlength=world).tolist()) == [3, 3]
+            ep, ei, _ = prob.mesh()
+            w = dist.part_adjacency(ep, ei, prob.partition()[0], nparts)
+            cut = sum(w[a, b] for a in range(nparts) for b in range(nparts) if sub_rank[a] != sub_rank[b]) // 2
+            worst = max(sum(w[a, b] for a in range(nparts) for b in range(nparts) if sr[a] != sr[b]) // 2
+                        for sr in ([0, 1, 0, 1, 0, 1], [0, 0, 0, 1, 1, 1], [1, 0, 0, 1, 1, 0]))
+            assert cut <= worst  # the greedy grouping is no worse than blind assignments
         else:  # box partition, each rank generates only its sub-mesh
             K, grid, sub_rank = dist.box_grid(world)
             nparts = len(sub_rank)
@@ -83,12 +96,12 @@ def _worker(rank, world, port, mode, q):
         q.put((rank, "fail: %s\n%s" % (e, traceback.format_exc()), 0, 0))
 
 
-@pytest.mark.parametrize("mode", ["metis", "box"])
+@pytest.mark.parametrize("mode", ["metis", "box", "metis_grouped"])
 def test_two_rank_layout_gloo(mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 1000) + (0 if mode == "metis" else 1000)
+    port = 29500 + (os.getpid() % 1000) + {"metis": 0, "box": 1000, "metis_grouped": 2000}[mode]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, lvl, ksp, q):
+def _worker(rank, world, port, lvl, ksp, q, partition="box"):
     try:
         import faulthandler
         faulthandler.dump_traceback_later(150, exit=True)  # a rank stuck in a collective shows where, then dies
@@ -25,10 +25,15 @@ def _worker(rank, world, port, lvl, ksp, q):
         kind, args = "laplacian", "--dim 3 --size 32 --inpEps 0.0001 --kappa 2. lin"
         K, grid, sub_rank = dist.box_grid(world)
         nparts = len(sub_rank)
-        lo, hi = dist.keep_region(32, K, grid, rank)
-        prob = g.Problem()
-        edge = dist.generate_boxed(prob, kind, args, K, lo, hi)
-        dist.decompose_owned(prob, nparts, sub_rank, rank, True, 0)
+        if partition == "box":
+            lo, hi = dist.keep_region(32, K, grid, rank)
+            prob = g.Problem()
+            edge = dist.generate_boxed(prob, kind, args, K, lo, hi)
+            dist.decompose_owned(prob, nparts, sub_rank, rank, True, 0)
+        else:  # the reference's METIS dual partition (src/geneo4PETSc.cpp:381-445), parts grouped onto the GPUs
+            nparts, edge = 6, 32
+            prob = g.Problem().generate(kind, args)
+            sub_rank = dist.metis_problem(prob, nparts, world, rank)
         lay = dist.Layout(prob, rank, world, sub_rank)
         lay.exchange_requests(tdist)
         uid = dist.nccl_unique_id(tdist, rank)
@@ -64,13 +69,18 @@ def _worker(rank, world, port, lvl, ksp, q):
         tdist.all_gather_object(gathered, out)
         if rank == 0:
             # single-GPU reference on the same partition
-            ref = g.Problem()
-            dist.generate_boxed(ref, kind, args, K)
-            eptr, eidx, _ = ref.mesh()
-            first = eidx[eptr[:-1]]
-            i, j, l = first % edge, (first // edge) % edge, first // (edge * edge)
-            ep = ((i * K[0]) // edge + K[0] * ((j * K[1]) // edge + K[1] * ((l * K[2]) // edge))).astype(np.int32)
-            ref.decompose(nparts, True, 0, elem_part=ep)
+            if partition == "box":
+                ref = g.Problem()
+                dist.generate_boxed(ref, kind, args, K)
+                eptr, eidx, _ = ref.mesh()
+                first = eidx[eptr[:-1]]
+                i, j, l = first % edge, (first // edge) % edge, first // (edge * edge)
+                ep = ((i * K[0]) // edge + K[0] * ((j * K[1]) // edge + K[1] * ((l * K[2]) // edge))).astype(np.int32)
+                ref.decompose(nparts, True, 0, elem_part=ep)
+            else:
+                ref = g.Problem().generate(kind, args)
+                ref.decompose(nparts, True, 0)
+                assert np.array_equal(ref.partition()[0], prob.partition()[0])  # identical subdomain partition
             pc1 = g.GeneoPC(opts).setup(ref)
             ax1, mx1 = pc1.mult(xg), pc1.apply(xg)
             r1 = pc1.ksp_solve(pc1.make_rhs(), ksp=ksp, rtol=1e-8, atol=1e-50)
@@ -97,16 +107,17 @@ def _worker(rank, world, port, lvl, ksp, q):
         q.put((rank, "fail: %s\n%s" % (e, traceback.format_exc())))
 
 
-@pytest.mark.parametrize("lvl,ksp", [("ASM,1", "cg"), ("ASM,H1", "gmres"), ("SORAS,2", "gmres")])
-def test_two_gpu_solve_matches_single_gpu(lvl, ksp):
+@pytest.mark.parametrize("lvl,ksp,partition", [("ASM,1", "cg", "box"), ("ASM,H1", "gmres", "box"), ("SORAS,2", "gmres", "box"),
+                                               ("ASM,1", "cg", "metis"), ("SORAS,2", "gmres", "metis")])
+def test_two_gpu_solve_matches_single_gpu(lvl, ksp, partition):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 500) + {"ASM,1": 0, "ASM,H1": 1, "SORAS,2": 2}[lvl]
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, lvl, ksp, q)) for r in range(2)]
+    port = 29700 + (os.getpid() % 500) + {"ASM,1": 0, "ASM,H1": 1, "SORAS,2": 2}[lvl] + (5 if partition == "metis" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lvl, ksp, q, partition)) for r in range(2)]
     for p in procs:
         p.start()
     import queue

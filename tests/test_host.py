@@ -295,3 +295,68 @@ def test_cli_loads_getinput_plugins_like_the_reference():
             for c, v in ent:
                 dense[rr, c] = v
         np.testing.assert_allclose(dense, a, rtol=1e-5, atol=1e-12)  # the dump prints 6 significant digits
+
+
+@pytest.mark.parametrize("args", ["--size 400 --level 3 --noGround --inpEps 0.0001", "--size 16 --level 2 --inpEps 0.001",
+                                  "--size 9 --level 0 --noGround", "--size 25 --level 1 --weakScaling 4"])
+def test_graph_generator_matches_the_reference_plugin(args):
+    """The product's closed-form graph generator (mesh.cpp generate_graph, BASELINE configs[3]) against the reference's own
+    tst/graph/graph.cpp compiled into oracle/_ref: same node count, element sequence and element matrices, bit for bit."""
+    try:
+        ref = go.ref_generator("graph", args)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libgengraph.so not built (needs /root/reference at build time)")
+    p = g.Problem().generate("graph", args)
+    ep, ei, em = p.mesh()
+    assert p.sizes()["nb_node"] == ref.nb_node
+    assert np.array_equal(ep, ref.elem_ptr) and np.array_equal(ei, ref.elem_idx) and np.array_equal(em, ref.mat_val)
+
+
+def _box_matrix(d):
+    def T(s):
+        return sp.diags([-1., 2.2, -1.], [-1, 0, 1], shape=(s, s), format="csr")
+
+    def I(s):
+        return sp.identity(s, format="csr")
+    a, b, c = d
+    m = (sp.kron(sp.kron(I(c), I(b)), T(a)) + sp.kron(sp.kron(I(c), T(b)), I(a)) + sp.kron(sp.kron(T(c), I(b)), I(a))).tocsr()
+    m.sort_indices()
+    return m
+
+
+def test_box_subdomains_inherit_the_reference_ordering():
+    """One nested dissection of the bounding box serves every (nearly) full box inside it: the induced permutation of a
+    smaller box is a valid ordering (the numpy emulation of the device phase factorizes and solves with it) and its fill
+    stays close to the box's own METIS ordering."""
+    from geneo4petsc_b200.api import box_ordering
+    ext = np.array([13, 12, 11])
+    rank = box_ordering(ext, threads=2)
+    assert sorted(rank.tolist()) == list(range(int(ext.prod())))
+    for d in ((13, 12, 11), (12, 12, 11), (13, 11, 10)):
+        a = _box_matrix(d)
+        x = np.arange(d[0] * d[1] * d[2])
+        c0, c1, c2 = x % d[0], (x // d[0]) % d[1], x // (d[0] * d[1])
+        perm = np.argsort(rank[c0 + ext[0] * (c1 + ext[1] * c2)], kind="stable").astype(np.int32)
+        sym = g.Symbolic(a, nb=16, perm=perm)
+        own = g.Symbolic(a, nb=16)
+        assert np.array_equal(sym.perm, sym.perm) and sorted(sym.perm.tolist()) == list(range(a.shape[0]))
+        assert sym.info["lSize"] <= 1.35 * own.info["lSize"]
+        L, neg = _emul.factorize(sym, a.data)
+        assert neg == 0
+        b = np.random.default_rng(1).standard_normal(a.shape[0])
+        assert np.linalg.norm(a @ _emul.solve(sym, L, b) - b) <= 1e-9 * np.linalg.norm(b)
+
+
+def test_geometric_nested_dissection_is_a_valid_ordering():
+    """-geneo_ordering 2 (coordinate bisection, separators from the cut): O(n log n), no METIS call; a valid permutation whose
+    symbolic structures drive a correct factorization."""
+    d = (9, 8, 7)
+    a = _box_matrix(d)
+    x = np.arange(d[0] * d[1] * d[2])
+    xyz = np.stack([x % d[0], (x // d[0]) % d[1], x // (d[0] * d[1])], axis=1)
+    sym = g.Symbolic(a, nb=8, coords=xyz)
+    assert sorted(sym.perm.tolist()) == list(range(a.shape[0]))
+    L, neg = _emul.factorize(sym, a.data)
+    assert neg == 0
+    b = np.random.default_rng(2).standard_normal(a.shape[0])
+    assert np.linalg.norm(a @ _emul.solve(sym, L, b) - b) <= 1e-9 * np.linalg.norm(b)
