@@ -49,7 +49,11 @@ inline void sym_eig(int n, double* a, double* w) {
   if (n == 0) return;
   std::vector<double> e(n, 0.);
   double* d = w;
-  auto V = [&](int i, int j) -> double& { return a[(size_t)i * n + j]; };
+  // The input is symmetric, so the tridiagonalisation and the accumulation of the Householder transformations may run on
+  // the TRANSPOSED layout: V(k, j) with k running is then contiguous -- every O(n^3) inner loop below streams memory
+  // (the projected matrices of the block Lanczos solver reach n ~ 1000-1600 when a subdomain needs hundreds of pairs:
+  // 5x faster than the strided walk at n = 800).
+  auto V = [&](int i, int j) -> double& { return a[(size_t)j * n + i]; };
   for (int j = 0; j < n; j++) d[j] = V(n - 1, j);
   for (int i = n - 1; i > 0; i--) {
     double scale = 0., h = 0.;
@@ -105,9 +109,7 @@ inline void sym_eig(int n, double* a, double* w) {
   // implicit QL.  The rotations combine two COLUMNS of V: they run on the transpose (two contiguous rows, vectorisable),
   // which is what makes the O(n^3) accumulation of the eigenvectors cheap for the projected matrices of the block
   // Lanczos solver (n up to a few hundred, once per step).
-  std::vector<double> vt((size_t)n * n);
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j < n; j++) vt[(size_t)j * n + i] = V(i, j);
+  std::vector<double> vt(a, a + (size_t)n * n);  // vt[j * n + i] = V(i, j): the storage of `a` already is that transpose
   for (int i = 1; i < n; i++) e[i - 1] = e[i];
   e[n - 1] = 0.;
   double f = 0., tst1 = 0.;
@@ -174,7 +176,7 @@ inline void sym_eig(int n, double* a, double* w) {
     }
   }
   for (int i = 0; i < n; i++)
-    for (int j = 0; j < n; j++) V(i, j) = vt[(size_t)j * n + i];
+    for (int j = 0; j < n; j++) a[(size_t)i * n + j] = vt[(size_t)j * n + i];  // row-major out: column j = eigenvector j
 }
 
 }  // namespace geneo
