@@ -653,6 +653,13 @@ int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32
   if (asmDst) std::copy(S.asmDst.begin(), S.asmDst.end(), asmDst);
   ABI_CATCH
 }
+int geneo_host_sym_eig_rows(int n, double* a, const int32_t* rows, int nrows, double* w, double* yrows) {
+  ABI_TRY
+  ABI_REQ(a && w && yrows && rows && n >= 0 && nrows >= 0, "null argument");
+  for (int t = 0; t < nrows; t++) ABI_REQ(rows[t] >= 0 && rows[t] < n, "row index out of range");
+  sym_eig_rows(n, a, rows, nrows, w, yrows);
+  ABI_CATCH
+}
 int geneo_host_sym_eig(int n, double* a, double* w) { ABI_TRY ABI_REQ(a && w && n >= 0, "null argument"); sym_eig(n, a, w); ABI_CATCH }
 
 int geneo_microbench(int kind, int n, int reps, double result[2]) {

@@ -179,4 +179,130 @@ inline void sym_eig(int n, double* a, double* w) {
     for (int j = 0; j < n; j++) a[(size_t)i * n + j] = vt[(size_t)j * n + i];  // row-major out: column j = eigenvector j
 }
 
+// Eigenvalues of a symmetric matrix plus SELECTED ROWS of its eigenvector matrix: the Rayleigh-Ritz step of the block
+// Lanczos solver only needs the last b components of every Ritz vector (residual estimate ||R y_bottom||), the whole
+// vectors only at a restart and at the end.  Householder tridiagonalisation (4/3 n^3, the only cubic part), the needed rows
+// of Q by applying the reflectors to unit vectors (O(n^2) per row), implicit QL with the rotations applied to those rows
+// only (O(n^2) per row) -- against ~7 n^3 for the full decomposition.
+//   a      row-major n x n symmetric (destroyed)
+//   rows   indices of the wanted rows (nrows of them)
+//   w      n eigenvalues, ascending
+//   yrows  nrows x n row-major: yrows[t * n + j] = component rows[t] of the eigenvector of w[j]
+inline void sym_eig_rows(int n, double* a, const int* rows, int nrows, double* w, double* yrows) {
+  if (n == 0) return;
+  std::vector<double> d(n), e(n, 0.), tau(n, 0.), p(n), v(n);
+  auto A = [&](int i, int j) -> double& { return a[(size_t)i * n + j]; };  // lower triangle is referenced
+  for (int i = 0; i + 1 < n; i++) {
+    // reflector annihilating A[i+2.., i]
+    const int m = n - i - 1;  // length of x = A[i+1.., i]
+    double alpha = A(i + 1, i), xn = 0.;
+    for (int r = i + 2; r < n; r++) xn += A(r, i) * A(r, i);
+    if (xn == 0.) { tau[i] = 0.; e[i] = alpha; d[i] = A(i, i); continue; }
+    const double beta = -std::copysign(std::sqrt(alpha * alpha + xn), alpha);
+    tau[i] = (beta - alpha) / beta;
+    const double sc = 1. / (alpha - beta);
+    for (int r = i + 2; r < n; r++) A(r, i) *= sc;  // v[1..] stored below the sub-diagonal, v[0] = 1 implicit
+    e[i] = beta;
+    d[i] = A(i, i);
+    v[0] = 1.;
+    for (int r = 1; r < m; r++) v[r] = A(i + 1 + r, i);
+    // p = tau * A22 v (symmetric, lower triangle, row-wise sweeps)
+    std::fill(p.begin(), p.begin() + m, 0.);
+    for (int r = 0; r < m; r++) {
+      const double* row = &A(i + 1 + r, i + 1);
+      double s1 = 0.;
+      const double vr = v[r];
+      for (int c = 0; c < r; c++) { s1 += row[c] * v[c]; p[c] += row[c] * vr; }
+      p[r] += s1 + row[r] * vr;
+    }
+    double pv = 0.;
+    for (int r = 0; r < m; r++) { p[r] *= tau[i]; pv += p[r] * v[r]; }
+    const double hh = 0.5 * tau[i] * pv;
+    for (int r = 0; r < m; r++) p[r] -= hh * v[r];  // w
+    for (int r = 0; r < m; r++) {                    // A22 -= v w^T + w v^T (lower triangle)
+      double* row = &A(i + 1 + r, i + 1);
+      const double vr = v[r], wr = p[r];
+      for (int c = 0; c <= r; c++) row[c] -= vr * p[c] + wr * v[c];
+    }
+  }
+  d[n - 1] = A(n - 1, n - 1);
+  // wanted rows of Q = H_0 H_1 ... H_{n-3}: row r = e_r^T H_0 H_1 ...  (H_i = I - tau_i v_i v_i^T acts on indices i+1..n-1)
+  std::vector<double> zt((size_t)n * nrows);  // transposed: zt[j * nrows + t] = Q[rows[t], j]
+  {
+    std::vector<double> x(n);
+    for (int t = 0; t < nrows; t++) {
+      std::fill(x.begin(), x.end(), 0.);
+      x[rows[t]] = 1.;
+      for (int i = 0; i + 1 < n; i++) {
+        if (tau[i] == 0.) continue;
+        double s1 = x[i + 1];
+        for (int r = i + 2; r < n; r++) s1 += x[r] * A(r, i);
+        s1 *= tau[i];
+        if (s1 == 0.) continue;
+        x[i + 1] -= s1;
+        for (int r = i + 2; r < n; r++) x[r] -= s1 * A(r, i);
+      }
+      for (int j = 0; j < n; j++) zt[(size_t)j * nrows + t] = x[j];
+    }
+  }
+  // implicit QL on (d, e); rotation (i, i+1) combines columns i, i+1 of the row block = rows i, i+1 of zt
+  e[n - 1] = 0.;
+  double f = 0., tst1 = 0.;
+  const double eps = std::pow(2., -52.);
+  for (int l = 0; l < n; l++) {
+    tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n) { if (std::fabs(e[m]) <= eps * tst1) break; m++; }
+    if (m > l) {
+      int iter = 0;
+      do {
+        iter++;
+        double g = d[l];
+        double pp = (d[l + 1] - g) / (2. * e[l]);
+        double r = std::hypot(pp, 1.);
+        if (pp < 0) r = -r;
+        d[l] = e[l] / (pp + r);
+        d[l + 1] = e[l] * (pp + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < n; i++) d[i] -= h;
+        f += h;
+        pp = d[m];
+        double c = 1., c2 = c, c3 = c, s = 0., s2 = 0.;
+        const double el1 = e[l + 1];
+        for (int i = m - 1; i >= l; i--) {
+          c3 = c2; c2 = c; s2 = s;
+          g = c * e[i];
+          h = c * pp;
+          r = std::hypot(pp, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = pp / r;
+          pp = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          double* __restrict__ vi = &zt[(size_t)i * nrows];
+          double* __restrict__ vi1 = &zt[(size_t)(i + 1) * nrows];
+          for (int k = 0; k < nrows; k++) {
+            const double t1 = vi1[k];
+            vi1[k] = s * vi[k] + c * t1;
+            vi[k] = c * vi[k] - s * t1;
+          }
+        }
+        pp = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * pp;
+        d[l] = c * pp;
+      } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] = d[l] + f;
+    e[l] = 0.;
+  }
+  std::vector<int> ord(n);
+  for (int i = 0; i < n; i++) ord[i] = i;
+  std::sort(ord.begin(), ord.end(), [&](int x, int y) { return d[x] < d[y]; });
+  for (int j = 0; j < n; j++) {
+    w[j] = d[ord[j]];
+    for (int t = 0; t < nrows; t++) yrows[(size_t)t * n + j] = zt[(size_t)ord[j] * nrows + t];
+  }
+}
+
 }  // namespace geneo

@@ -223,12 +223,12 @@ int GeneoOptions::parse(int argc, const char* const* argv, std::string& err) {
       const std::string f = s.substr(0, c);
       if (f != "log" && f != "bin" && f != "mat") { err = "invalid option -geneo_dbg, unknown " + f; return 1; }
       double d; if (!num(s.substr(c + 1).c_str(), d, "-geneo_dbg")) return 1;
-      debug = (int)d; a++;
+      debug = (int)d; debugFmt = f; a++;
     } else if (o == "-geneo_chk") {
       const char* v = need(a, "-geneo_chk"); if (!v) return 1;
       std::string f(v);
       if (f != "log" && f != "bin" && f != "mat") { err = "invalid option -geneo_chk, unknown " + f; return 1; }
-      check = true; a++;
+      check = true; checkFmt = f; a++;
     } else if (o == "-els2_eps_tol") { const char* v = need(a, "-els2_eps_tol"); if (!v || !num(v, epsTol, "-els2_eps_tol")) return 1; a++; }
     else if (o == "-els2_eps_block") { double c; const char* v = need(a, "-els2_eps_block"); if (!v || !num(v, c, "-els2_eps_block")) return 1; epsBlock = (int)c; a++; }
     else if (o == "-els2_eps_ncv") { double c; const char* v = need(a, "-els2_eps_ncv"); if (!v || !num(v, c, "-els2_eps_ncv")) return 1; epsMaxDim = (int)c; a++; }
@@ -456,6 +456,7 @@ bool GeneoPC::use_pipeline() const {
   return true;
 }
 GeneoPC::~GeneoPC() {
+  try { write_timing_log(); } catch (...) {}
   for (auto s : streams) cudaStreamDestroy(s);
   for (auto e : events) cudaEventDestroy(e);
   for (auto e : ktEvents) cudaEventDestroy(e);
@@ -752,6 +753,104 @@ void GeneoPC::numeric_end() {
     infoL2 = "blocklanczos ldlt";
   }
   CUDA_CHECK(::geneo::sync_stream(st));
+  if (opt.check || opt.debug >= 2) run_checks_and_dumps();
+}
+
+// ---- -geneo_chk / -geneo_dbg (diagnostics; file names follow the reference: one prefix per subdomain = per MPI rank there) -----
+namespace {
+std::string diag_prefix(const char* what, int id, int nbPart) {
+  const int w = (int)std::to_string(nbPart).size();
+  std::string r = std::to_string(id);
+  while ((int)r.size() < w) r = "0" + r;
+  return std::string(what) + r;
+}
+}  // namespace
+
+void GeneoPC::run_checks_and_dumps() {
+  for (auto& s : subs) {
+    if (opt.debug >= 2) {
+      const std::string pre = diag_prefix("debug", s.id, nbPart);
+      if (opt.lvl2 >= 1) {
+        FILE* f = fopen((pre + ".setup.Z.ev.log").c_str(), "w");  // src/geneo.cpp:344-349
+        if (f) {
+          fprintf(f, "\nZ - nb of eigen values: %d\n", (int)s.eigvals.size());
+          for (size_t e = 0; e < s.eigvals.size(); e++) fprintf(f, "Z - eigen value %d: %.17g\n", (int)e, s.eigvals[e]);
+          fclose(f);
+        }
+        const char* pb[2] = {"tau", "gamma"};
+        for (int q = 0; q < (opt.lvl2 == 2 ? 2 : 1); q++) {
+          if (opt.noSyl) continue;
+          f = fopen((pre + ".setup." + pb[q] + ".sylvester.inertia.log").c_str(), "w");  // :547-551
+          if (!f) continue;
+          fprintf(f, "\nnbNegEV %d, nbNullEV %d, nbPosEV %d => estim %d\n", s.sylNeg[q], s.sylNull[q], s.n - s.sylNeg[q] - s.sylNull[q], s.sylEstim[q]);
+          fclose(f);
+        }
+      }
+    }
+    if (opt.check) {
+      const std::string pre = diag_prefix("check", s.id, nbPart);
+      // partition of unity (src/geneo.cpp:988-997): min D > 0
+      std::vector<double> d = s.d.to_host(st);
+      double dmin = d.empty() ? 1. : *std::min_element(d.begin(), d.end());
+      if (std::fabs(dmin) <= DBL_EPSILON) throw Error("geneo_b200: GenEO - check D: bad partition of unity, min " + std::to_string(dmin));
+      // SPD of the level-1 matrix through the inertia of its factorization (checkSPD, :782-840: the inertia half)
+      {
+        const char* info = opt.lvl1ORAS ? "ARob" : "ADir";
+        FILE* f = fopen((pre + ".SPD." + info + ".log").c_str(), "w");
+        if (f) {
+          fprintf(f, "\n%s - inertia: nbNegEV %d, nbNullEV %d, nbPosEV %d\n", info, s.negL1, 0, s.n - s.negL1);
+          fclose(f);
+        }
+        if (s.negL1 > 0) throw Error("geneo_b200: GenEO - check SPD: not SPD (inertia - negative or null eigen value found)");
+      }
+      // rank of Z_i (checkRank, :173-247): Z = Q R by modified Gram-Schmidt with refinement on the host, diag(R) != 0
+      if (opt.lvl2 >= 1 && s.nev > 0) {
+        std::vector<double> z = s.Z.to_host(st);  // n x nev row-major
+        const int n = s.n, k = s.nev;
+        std::vector<double> R((size_t)k * k, 0.), col(n);
+        for (int j = 0; j < k; j++) {
+          for (int pass = 0; pass < 2; pass++)
+            for (int i = 0; i < j; i++) {
+              double dot = 0.;
+              for (int r = 0; r < n; r++) dot += z[(size_t)r * k + i] * z[(size_t)r * k + j];
+              R[(size_t)i * k + j] += dot;
+              for (int r = 0; r < n; r++) z[(size_t)r * k + j] -= dot * z[(size_t)r * k + i];
+            }
+          double nrm = 0.;
+          for (int r = 0; r < n; r++) nrm += z[(size_t)r * k + j] * z[(size_t)r * k + j];
+          nrm = std::sqrt(nrm);
+          R[(size_t)j * k + j] = nrm;
+          if (nrm > 0.) for (int r = 0; r < n; r++) z[(size_t)r * k + j] /= nrm;
+        }
+        FILE* f = fopen((pre + ".setup.Z.R").c_str(), "w");
+        if (f) {
+          for (int i = 0; i < k; i++) { for (int j = 0; j < k; j++) fprintf(f, "%.10e ", R[(size_t)i * k + j]); fprintf(f, "\n"); }
+          fclose(f);
+        }
+        for (int j = 0; j < k; j++)
+          if (std::fabs(R[(size_t)j * k + j]) <= DBL_EPSILON)
+            throw Error("geneo_b200: GenEO - check rank: Z = Q*R with R(" + std::to_string(j) + ", " + std::to_string(j) + ") = " + std::to_string(R[(size_t)j * k + j]));
+      }
+    }
+  }
+}
+
+void GeneoPC::write_timing_log() const {
+  if (opt.debug < 1) return;
+  for (auto& s : subs) {
+    FILE* f = fopen((diag_prefix("debug", s.id, nbPart) + ".timing.log").c_str(), "w");
+    if (!f) continue;
+    const struct { const char* n; double v; } T[] = {
+        {"lvl1SetupMinvTimeLoc", lvl1SetupMinvTime}, {"lvl1ApplyTimeLoc", lvl1ApplyTime}, {"lvl1ApplyScatterTimeLoc", lvl1ApplyScatterTime},
+        {"lvl1ApplyMinvTimeLoc", lvl1ApplyMinvTime}, {"lvl1ApplyGatherTimeLoc", lvl1ApplyGatherTime}, {"lvl1ApplyPrjFSTimeLoc", lvl1ApplyPrjFSTime},
+        {"lvl2SetupTauLocTimeLoc", lvl2SetupTauLocTime}, {"lvl2SetupTauSylTimeLoc", lvl2SetupTauSylTime}, {"lvl2SetupTauEigTimeLoc", lvl2SetupTauEigTime},
+        {"lvl2SetupGammaLocTimeLoc", lvl2SetupGammaLocTime}, {"lvl2SetupGammaSylTimeLoc", lvl2SetupGammaSylTime},
+        {"lvl2SetupGammaEigTimeLoc", lvl2SetupGammaEigTime}, {"lvl2SetupSylTimeLoc", lvl2SetupSylTime}, {"lvl2SetupEigTimeLoc", lvl2SetupEigTime},
+        {"lvl2SetupZTimeLoc", lvl2SetupZTime}, {"lvl2SetupETimeLoc", lvl2SetupETime}, {"lvl2ApplyTimeLoc", lvl2ApplyTime},
+        {"lvl2ApplyZtTimeLoc", lvl2ApplyZtTime}, {"lvl2ApplyEinvTimeLoc", lvl2ApplyEinvTime}, {"lvl2ApplyZTimeLoc", lvl2ApplyZTime}};
+    for (auto& t : T) fprintf(f, "%-26s%g ms\n", t.n, 1e3 * t.v);  // (this GPU holds every local subdomain: the timers are per process)
+    fclose(f);
+  }
 }
 
 void GeneoPC::numeric_setup() {
@@ -887,6 +986,8 @@ int GeneoPC::sylvester_estimate(SubdomainState& s, int neg, int perturbedS, bool
   if (cut > 0 && est > cut) est = cut;
   s.estim += est;
   s.perturbed += perturbedS;
+  const int q = tauPb ? 0 : 1;
+  s.sylNeg[q] = neg; s.sylNull[q] = perturbedS; s.sylEstim[q] = est;
   return est;
 }
 
@@ -944,7 +1045,9 @@ int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double
   // Block of 8 by default.  -els2_eps_block 16 sends 16 right-hand sides per pass over the factor (k_solve_ring<16>),
   // but measured on 8 x 80^3 the wider block needs a 45-60 % larger Krylov space for the same pairs (13-16 steps of 16
   // against 18-19 steps of 8): 1.13 s against 0.93 s for the eight eigen-solves.
-  eo.block = opt.epsBlock > 0 ? opt.epsBlock : 8;
+  // A pencil that wants many pairs (high-contrast heat: 100-250 per subdomain) is bound by the passes over the basis, one per
+  // step whatever the block: there the block of 16 (fewer, fatter steps) wins.
+  eo.block = opt.epsBlock > 0 ? opt.epsBlock : (nev + guard >= 64 ? 16 : 8);
   eo.tol = opt.epsTol; eo.maxDim = opt.epsMaxDim; eo.invert = tauPb;
   eo.ws = &eigWs;
   EigResult er;
@@ -992,6 +1095,7 @@ int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double
     CUDA_CHECK(::geneo::sync_stream(st));
     if (std::fabs(num / den) <= (double)FLT_EPSILON) addOne = true;
   }
+  s.nKept[tauPb ? 0 : 1] = got;
   if (got > 0) { vals.insert(vals.end(), lam.begin(), lam.end()); vecs.push_back(std::move(X)); counts.push_back(got); }
   if (addOne) {
     DevBuf<double> one((size_t)n);

@@ -23,8 +23,9 @@ struct GeneoOptions {
   bool cst = false;
   int cut = -1;
   bool noSyl = false, offload = false;
-  int debug = 0;
-  bool check = false;
+  int debug = 0;                // -geneo_dbg F,D : D = 1 timing log, D = 2 + per-subdomain eigenvalue / inertia logs (src/geneo.cpp:2189, 726, 547)
+  bool check = false;           // -geneo_chk F   : partition of unity, SPD (inertia), rank of Z (src/geneo.cpp:988, 782-840, 173-247)
+  std::string debugFmt = "log", checkFmt = "log";  // log | bin | mat (only the text logs are written; matrices: CLI --verbose 2)
   // knobs of the sub-solvers (stand for the reference's -dls1_/-syl2_/-els2_/-dcs2_ PETSc option prefixes)
   int nb = 128;          // LDL^T panel width
   int ordering = 1;      // 1 METIS NodeND, 0 natural
@@ -57,6 +58,7 @@ struct SubdomainState {
   DevBuf<double> vB, vS;  // D A_dir D and A_neu - tau B (values on the A_dir pattern), kept between re-setups
   std::vector<double> eigvals;
   int estim = 0, nicolaides = 0, eigSteps = 0, eigDim = 0, negL1 = 0, perturbed = 0;
+  int sylNeg[2] = {0, 0}, sylNull[2] = {0, 0}, sylEstim[2] = {0, 0}, nKept[2] = {0, 0};  // per pencil (tau, gamma): inertia of A - theta B, kept pairs
   double tauLoc = -1., gammaLoc = -1.;
   int maxMult = 1;
   double anorm = 0.;  // max |a_ij| of A_dir (scale of the static pivot threshold)
@@ -129,6 +131,8 @@ class GeneoPC {
   double apply_algo_bytes() const;
   double trisolve_algo_bytes() const;
   void copy_einv(double* out) const;  // nE x nE row-major E^-1 to the host
+  void write_timing_log() const;      // -geneo_dbg F,1: <debugNN>.timing.log, the reference's timer list (src/geneo.cpp:2189-2216)
+  void run_checks_and_dumps();        // -geneo_chk / -geneo_dbg F,2 after a (re-)setup
 
  private:
   void numeric_subdomain(SubdomainState& s, LdltWorkspace& ws);

@@ -182,6 +182,9 @@ int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[11], double reals[1]);
 int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32_t* rowIdx, int32_t* rel, int64_t* asmSrc,
                        int64_t* asmDst);
 int geneo_host_sym_eig(int n, double* a /* row-major in, eigenvectors (columns) out */, double* w);
+/* eigenvalues + selected rows of the eigenvector matrix (the Rayleigh-Ritz shortcut of the block Lanczos solver):
+ * yrows[t * n + j] = component rows[t] of the eigenvector of w[j]; a is destroyed */
+int geneo_host_sym_eig_rows(int n, double* a, const int32_t* rows, int nrows, double* w, double* yrows);
 /* microbenchmarks on the device (first-run calibration): kind 0 = DMMA 64x64-tile GEMM C=AB^T (M=N=K=n) TFLOP/s,
  * kind 1 = device copy GB/s over n doubles, kind 2 = solve-kernel streaming over ~2 GB of synthetic n x 128 panels at a
  * single level (result[0] = algorithmic GB/s, result[1] = ms per solve).  result[0] = rate, result[1] = max abs error vs a

@@ -195,3 +195,35 @@ def test_80_cubed_against_the_oracle():
     r = pc.ksp_solve(pc.make_rhs(), ksp="cg", rtol=1e-5, atol=1e-50)
     assert r["reason"] > 0 and abs(r["its"] - rep.ksp.its) <= 1, (r["its"], rep.ksp.its)
     assert np.linalg.norm(r["x"] - rep.ksp.x) <= 1e-4 * np.linalg.norm(rep.ksp.x)
+
+
+def test_check_and_debug_files(tmp_path, monkeypatch):
+    """-geneo_chk log / -geneo_dbg log,2 (src/geneo.cpp:2438-2480): the per-subdomain diagnostics the reference writes next to
+    the run -- SPD check through the inertia (:782-840), rank of Z through the diagonal of R (:173-247), partition of unity
+    (:988-997), eigenvalue / Sylvester-inertia logs (:344-349, :547-551), the timing log at destroy (:2189-2216)."""
+    monkeypatch.chdir(tmp_path)
+    mesh, nparts = go.gen_grid(3, 12, 1e-4, 2.0, "lin"), 4
+    p = _problem(mesh, nparts)
+    pc = g.GeneoPC(["-geneo_lvl", "ASM,1", "-geneo_tau", "0.3", "-geneo_chk", "log", "-geneo_dbg", "log,2"]).setup(p)
+    rep = _oracle(mesh, p, nparts, go.GenEOOptions(lvl1="ASM", lvl2="1", tau=0.3), ksp="cg", rtol=1e-6)
+    for s in range(nparts):
+        spd = (tmp_path / ("check%d.SPD.ADir.log" % s)).read_text()
+        assert "ADir - inertia: nbNegEV 0, nbNullEV 0, nbPosEV %d" % pc.sub_info(s)["n"] in spd
+        r = np.loadtxt(tmp_path / ("check%d.setup.Z.R" % s), ndmin=2)
+        assert r.shape == (pc.sub_info(s)["nev"],) * 2 and np.all(np.abs(np.diag(r)) > 1e-12)
+        ev = (tmp_path / ("debug%d.setup.Z.ev.log" % s)).read_text()
+        assert "Z - nb of eigen values: %d" % pc.sub_info(s)["nev"] in ev
+        syl = (tmp_path / ("debug%d.setup.tau.sylvester.inertia.log" % s)).read_text()
+        assert "=> estim %d" % rep.pc.sub[s].estim in syl and "nbNegEV %d," % rep.pc.sub[s].estim in syl
+    pc.ksp_solve(pc.make_rhs(), ksp="cg", rtol=1e-6)
+    del pc
+    import gc
+    gc.collect()
+    t = (tmp_path / "debug0.timing.log").read_text()
+    assert "lvl1SetupMinvTimeLoc" in t and "lvl2SetupEigTimeLoc" in t and " ms" in t
+    # a matrix that is not SPD is caught by the check (the reference aborts, src/geneo.cpp:829-832)
+    ids = [p.sub_nodes(s)[0] for s in range(nparts)]
+    bad = [(ids[s], p.sub_matrix(s, 0) * (-1.0 if s == 1 else 1.0), p.sub_matrix(s, 1) * (-1.0 if s == 1 else 1.0)) for s in range(nparts)]
+    q = g.Problem().set_subdomains(mesh.nb_node, bad)
+    with pytest.raises(g.GeneoError, match="not SPD"):
+        g.GeneoPC(["-geneo_lvl", "ASM,0", "-geneo_chk", "log"]).setup(q)
