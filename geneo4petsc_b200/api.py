@@ -246,6 +246,12 @@ class GeneoPC:
         _chk(lib.geneo_pc_factor_stats(self.h, _p(s, _f64p)))
         return dict(seconds=s[0], flops=s[1], count=int(s[2]), ordering_reuse_s=s[3])
 
+    def factor_bench(self):
+        """(seconds, flops) of the level-1 factorizations run once more, alone on the device (CUDA events)."""
+        s = np.zeros(2)
+        _chk(lib.geneo_pc_factor_bench(self.h, _p(s, _f64p)))
+        return float(s[0]), float(s[1])
+
     def sub_info(self, s):
         i, r = np.zeros(8, dtype=np.int64), np.zeros(2)
         _chk(lib.geneo_pc_sub_info(self.h, C.c_int(s), _p(i, _i64p), _p(r, _f64p)))

@@ -487,6 +487,12 @@ int geneo_pc_factor_stats(geneo_pc_t pc, double out[4]) {
   out[0] = pc->pc.allFactorSeconds; out[1] = pc->pc.allFactorFlops; out[2] = (double)pc->pc.allFactorCount; out[3] = pc->pc.orderingReuseTime;
   ABI_CATCH
 }
+int geneo_pc_factor_bench(geneo_pc_t pc, double out[2]) {
+  ABI_TRY
+  ABI_REQ(pc && pc->ready && out, "GenEO preconditioner without context");
+  pc->pc.factor_bench(&out[0], &out[1]);
+  ABI_CATCH
+}
 int geneo_pc_sub_info(geneo_pc_t pc, int s, int64_t ints[8], double reals[2]) {
   ABI_TRY
   ABI_REQ(pc && pc->ready && s >= 0 && s < (int)pc->pc.subs.size(), "bad subdomain");

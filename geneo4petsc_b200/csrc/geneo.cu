@@ -455,6 +455,15 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
 
 }  // namespace
 
+// one lane of the pipelined numeric setup (numeric_pipeline): a stream, its update arenas and a transient factor
+struct GeneoPC::Lane {
+  cudaStream_t st = nullptr;
+  LdltWorkspace ws;
+  DevBuf<double> T;          // transient factor (S, then A_neu) of the subdomain currently in the lane
+  int* hc = nullptr;         // pinned: {neg, perturbed} of S, of A_neu, of A_dir
+  ~Lane() { if (st) cudaStreamDestroy(st); if (hc) cudaFreeHost(hc); }
+};
+
 GeneoPC::GeneoPC() {}
 // The pipelined numeric setup needs a single level-2 pencil (GenEO-1) or none; GenEO-2, the launch profiler (events on ONE
 // stream) and GENEO_PIPELINE=0 take the sequential path.
@@ -554,31 +563,44 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   int inFlight = std::max(1, std::min(P, hw >= 8 ? 2 : 1));  // subdomains analysed concurrently
   int ndDepth = 0;
   while ((unsigned)(inFlight << (ndDepth + 1)) <= hw && ndDepth < 4) ndDepth++;
-  {
-    const double tr = now_s();
-    const unsigned hwAll = getenv("GENEO_HOST_THREADS") ? hw : std::max(1u, std::thread::hardware_concurrency());
-    plan_ordering_reuse(dec, mine, opt, comm, hwAll, st, prep);
-    orderingReuseTime = now_s() - tr;
-  }
-  int nInherit = 0;
-  for (auto& H : prep) nInherit += H.userPerm.empty() ? 0 : 1;
-  if (nInherit == P) { inFlight = std::max(1, std::min<int>(P, (int)hw)); ndDepth = 0; }  // no METIS call left: one thread per subdomain
   std::mutex mtx;
   std::condition_variable cv;
   std::vector<char> ready(P, 0);
   std::atomic<int> ticket(0);
   std::vector<std::thread> pool;
-  for (int w = 0; w < inFlight; w++)
-    pool.emplace_back([&]() {
-      for (;;) {
-        const int p = ticket.fetch_add(1);
-        if (p >= P) break;
-        try { prepare_subdomain(*mine[p], opt, ndDepth, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
-        { std::lock_guard<std::mutex> lk(mtx); ready[p] = 1; }
-        cv.notify_all();
-      }
-    });
-  struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); } } joiner{pool};
+  std::string orchErr;
+  // The shared reference ordering (one METIS call for all box subdomains) and then the analysis workers are started from
+  // an orchestrating thread: this thread assembles and uploads the operator meanwhile.  Single process only -- with
+  // several ranks the ordering is a collective on the library's stream and stays on this thread.
+  auto orchestrate = [&]() {
+    try {
+      const double tr = now_s();
+      const unsigned hwAll = getenv("GENEO_HOST_THREADS") ? hw : std::max(1u, std::thread::hardware_concurrency());
+      plan_ordering_reuse(dec, mine, opt, comm, hwAll, st, prep);
+      orderingReuseTime = now_s() - tr;
+      int nInherit = 0;
+      for (auto& H : prep) nInherit += H.userPerm.empty() ? 0 : 1;
+      if (nInherit == P) { inFlight = std::max(1, std::min<int>(P, (int)hw)); ndDepth = 0; }  // no METIS call left: one thread per subdomain
+    } catch (std::exception& e) { orchErr = e.what(); }
+    for (int w = 0; w < inFlight; w++)
+      pool.emplace_back([&]() {
+        for (;;) {
+          const int p = ticket.fetch_add(1);
+          if (p >= P) break;
+          if (!orchErr.empty()) prep[p].err = orchErr;
+          else try { prepare_subdomain(*mine[p], opt, ndDepth, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
+          { std::lock_guard<std::mutex> lk(mtx); ready[p] = 1; }
+          cv.notify_all();
+        }
+      });
+  };
+  std::thread orch;
+  struct Joiner {
+    std::thread& o; std::vector<std::thread>& t;
+    ~Joiner() { if (o.joinable()) o.join(); for (auto& x : t) if (x.joinable()) x.join(); }
+  } joiner{orch, pool};
+  if (layout && comm.active()) orchestrate();
+  else orch = std::thread(orchestrate);
 
   // (assembled by this thread while the workers are already busy with the first subdomains)
   // ---- operator A = sum_i R_i^T A_neu,i R_i  (MatConvert MATIS->AIJ, src/geneo.cpp:1692), SELL-32 on the device ------
@@ -985,6 +1007,58 @@ void GeneoPC::account_subdomain(const SubdomainState& s) {
   nicolaides += s.nicolaides;
 }
 
+// Measurement hook (bench.py roofline_factorization): every level-1 matrix factorized once more -- same values, same result,
+// written over the resident factors -- through the lanes of the pipelined setup, and NOTHING else on the device: the
+// factorization kernels timed alone with CUDA events (start on lane 0 with every lane waiting for it, stop after every lane).
+void GeneoPC::factor_bench(double* seconds, double* flops) {
+  GENEO_CHECK(!subs.empty() && subs[0].L1, "factor_bench before setup");
+  const int P = (int)subs.size();
+  CUDA_CHECK(cudaDeviceSynchronize());
+  double fl = 0.;
+  for (auto& s : subs) fl += s.plan->sym.flops;
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  float ms = 0.f;
+  if (lanes.empty()) {  // sequential path
+    CUDA_CHECK(cudaEventRecord(e0, st));
+    for (auto& s : subs) s.L1->factorize(opt.lvl1ORAS ? s.vRob.p : s.pat.val.p, opt.pivRel * std::max(s.anorm, 1e-300), factorWs, st);
+    CUDA_CHECK(cudaEventRecord(e1, st));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+  } else {
+    const int NL = (int)lanes.size();
+    for (int j = 0; j < NL; j++)
+      for (int p = j; p < P; p += NL) lanes[j]->ws.ensure(subs[p].plan->sym);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaEventRecord(e0, lanes[0]->st));
+    for (int j = 1; j < NL; j++) CUDA_CHECK(cudaStreamWaitEvent(lanes[j]->st, e0, 0));
+    for (int g0 = 0; g0 < P; g0 += NL) {
+      std::vector<FactorJob> jobs;
+      for (int p = g0; p < std::min(P, g0 + NL); p++) {
+        FactorJob J;
+        J.F = subs[p].L1.get(); J.vals = opt.lvl1ORAS ? subs[p].vRob.p : subs[p].pat.val.p;
+        J.pivTol = opt.pivRel * std::max(subs[p].anorm, 1e-300);
+        J.ws = &lanes[p - g0]->ws; J.st = lanes[p - g0]->st;
+        jobs.push_back(J);
+      }
+      factorize_enqueue(jobs);
+    }
+    std::vector<cudaEvent_t> done(NL, nullptr);
+    for (int j = 1; j < NL; j++) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&done[j], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventRecord(done[j], lanes[j]->st));
+      CUDA_CHECK(cudaStreamWaitEvent(lanes[0]->st, done[j], 0));
+    }
+    CUDA_CHECK(cudaEventRecord(e1, lanes[0]->st));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    for (int j = 1; j < NL; j++) cudaEventDestroy(done[j]);
+  }
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (seconds) *seconds = 1e-3 * ms;
+  if (flops) *flops = fl;
+}
+
 // estimateNumberOfEigenValues (src/geneo.cpp:502-533) from the inertia of A - param B (Sylvester)
 int GeneoPC::sylvester_estimate(SubdomainState& s, int neg, int perturbedS, bool tauPb, int cut) {
   // tau problem: #eigenvalues below tau = negative pivots; gamma problem: #above gamma = positive pivots (zero / perturbed
@@ -1125,14 +1199,6 @@ int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double
 // the library's stream as soon as p's shift-invert factor is there -- the latency-bound eigen-solve hides behind the
 // DMMA tiles of the other lanes.  Dependencies: CUDA events between streams, two host flags per subdomain between the threads.
 // =====================================================================================================================
-struct GeneoPC::Lane {
-  cudaStream_t st = nullptr;
-  LdltWorkspace ws;
-  DevBuf<double> T;          // transient factor (S, then A_neu) of the subdomain currently in the lane
-  int* hc = nullptr;         // pinned: {neg, perturbed} of S, of A_neu, of A_dir
-  ~Lane() { if (st) cudaStreamDestroy(st); if (hc) cudaFreeHost(hc); }
-};
-
 void GeneoPC::numeric_pipeline() {
   const int P = (int)subs.size();
   const bool l2 = opt.lvl2 >= 1, syl = l2 && !opt.noSyl;

@@ -131,6 +131,7 @@ class GeneoPC {
   double apply_algo_bytes() const;
   double trisolve_algo_bytes() const;
   void copy_einv(double* out) const;  // nE x nE row-major E^-1 to the host
+  void factor_bench(double* seconds, double* flops);  // the level-1 factorizations once more, alone on the device (CUDA events)
   void write_timing_log() const;      // -geneo_dbg F,1: <debugNN>.timing.log, the reference's timer list (src/geneo.cpp:2189-2216)
   void run_checks_and_dumps();        // -geneo_chk / -geneo_dbg F,2 after a (re-)setup
 

@@ -225,41 +225,53 @@ constexpr int TG_PCOLS = 64;   // columns of X per CTA (8 fragments)
 __device__ __forceinline__ void dmma_f64(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// QT = 8-column tiles of Y per CTA (1 or 2): a block of 16 shares every X fragment between two B fragments, so X -- the
+// n x dim basis, the only big operand -- is read once per Gram product whatever the Lanczos block.
+template <int QT>
 __global__ void __launch_bounds__(256) k_ts_gram(int n, const double* __restrict__ X, int ldx, int p,
                                                  const double* __restrict__ Y, int ldy, int q, double* G, int ldg,
                                                  int rowsPerCta) {
   __shared__ double red[8][8][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int p0 = blockIdx.x * TG_PCOLS, q0 = blockIdx.y * 8;
+  const int p0 = blockIdx.x * TG_PCOLS, q0 = blockIdx.y * 8 * QT;
   const int64_t r0 = (int64_t)blockIdx.z * rowsPerCta;
   const int64_t r1 = min((int64_t)n, r0 + rowsPerCta);
-  double acc[8][2];
+  double acc[QT][8][2];
 #pragma unroll
-  for (int pb = 0; pb < 8; pb++) acc[pb][0] = acc[pb][1] = 0.;
-  const bool qok = q0 + g < q;
+  for (int qt = 0; qt < QT; qt++)
+#pragma unroll
+    for (int pb = 0; pb < 8; pb++) acc[qt][pb][0] = acc[qt][pb][1] = 0.;
   for (int64_t r = r0 + 4 * warp; r < r1; r += 32) {
     const int64_t row = r + t;
     const bool rok = row < r1;
     const double* xr = X + (size_t)(rok ? row : r0) * ldx + p0 + g;
-    const double yb = (rok && qok) ? __ldg(Y + (size_t)row * ldy + q0 + g) : 0.;
+    double yb[QT];
+#pragma unroll
+    for (int qt = 0; qt < QT; qt++) yb[qt] = (rok && q0 + qt * 8 + g < q) ? __ldg(Y + (size_t)row * ldy + q0 + qt * 8 + g) : 0.;
     double a[8];
 #pragma unroll
     for (int pb = 0; pb < 8; pb++) a[pb] = (rok && p0 + pb * 8 + g < p) ? __ldg(xr + pb * 8) : 0.;
 #pragma unroll
-    for (int pb = 0; pb < 8; pb++) dmma_f64(acc[pb][0], acc[pb][1], a[pb], yb);
+    for (int qt = 0; qt < QT; qt++)
+#pragma unroll
+      for (int pb = 0; pb < 8; pb++) dmma_f64(acc[qt][pb][0], acc[qt][pb][1], a[pb], yb[qt]);
   }
 #pragma unroll
-  for (int pb = 0; pb < 8; pb++) { red[warp][pb][2 * lane] = acc[pb][0]; red[warp][pb][2 * lane + 1] = acc[pb][1]; }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 8 * 64; e += 256) {
-    const int pb = e >> 6, f = e & 63;  // fragment entry f of lane f/2: C[m = (f/2) >> 2][n = 2 ((f/2) & 3) + (f & 1)]
-    double sum = 0.;
+  for (int qt = 0; qt < QT; qt++) {
+    if (qt > 0) __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; w++) sum += red[w][pb][f];
-    const int ln = f >> 1;
-    const int pc = p0 + pb * 8 + (ln >> 2), qc = q0 + 2 * (ln & 3) + (f & 1);
-    if (pc < p && qc < q && sum != 0.) atomicAdd(&G[(size_t)pc * ldg + qc], sum);
+    for (int pb = 0; pb < 8; pb++) { red[warp][pb][2 * lane] = acc[qt][pb][0]; red[warp][pb][2 * lane + 1] = acc[qt][pb][1]; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 8 * 64; e += 256) {
+      const int pb = e >> 6, f = e & 63;  // fragment entry f of lane f/2: C[m = (f/2) >> 2][n = 2 ((f/2) & 3) + (f & 1)]
+      double sum = 0.;
+#pragma unroll
+      for (int w = 0; w < 8; w++) sum += red[w][pb][f];
+      const int ln = f >> 1;
+      const int pc = p0 + pb * 8 + (ln >> 2), qc = q0 + qt * 8 + 2 * (ln & 3) + (f & 1);
+      if (pc < p && qc < q && sum != 0.) atomicAdd(&G[(size_t)pc * ldg + qc], sum);
+    }
   }
 }
 
@@ -267,21 +279,22 @@ __global__ void __launch_bounds__(256) k_ts_gram(int n, const double* __restrict
 // 128 rows x 32 columns go through shared memory so that the global reads are coalesced 256-byte row segments and the
 // per-row reads are conflict-free (leading dimension 33); C (p x 8) sits in shared memory and is read as a broadcast.
 constexpr int TSU_ROWS = 128, TSU_COLS = 32;
+template <int QW>  // columns of W per pass (8 or 16): Q is read once per pass
 __global__ void __launch_bounds__(TSU_ROWS) k_ts_update(int n, const double* __restrict__ Q, int ldq, int p,
                                                         const double* __restrict__ C, int ldc, int q, double* __restrict__ W,
                                                         int ldw, double alpha, double beta) {
   extern __shared__ double sm[];
-  double* sC = sm;                    // [p][8]
-  double* tile = sm + (size_t)p * 8;  // [TSU_ROWS][TSU_COLS + 1]
+  double* sC = sm;                     // [p][QW]
+  double* tile = sm + (size_t)p * QW;  // [TSU_ROWS][TSU_COLS + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int e = tid; e < p * 8; e += TSU_ROWS) {
-    const int pp = e >> 3, jj = e & 7;
+  for (int e = tid; e < p * QW; e += TSU_ROWS) {
+    const int pp = e / QW, jj = e % QW;
     sC[e] = jj < q ? C[(size_t)pp * ldc + jj] : 0.;
   }
   const int64_t r0 = (int64_t)blockIdx.x * TSU_ROWS;
-  double acc[8];
+  double acc[QW];
 #pragma unroll
-  for (int j = 0; j < 8; j++) acc[j] = 0.;
+  for (int j = 0; j < QW; j++) acc[j] = 0.;
   for (int pb = 0; pb < p; pb += TSU_COLS) {
     __syncthreads();
     // warp w loads rows w*32 .. w*32+31 of the tile, lane = column
@@ -295,16 +308,16 @@ __global__ void __launch_bounds__(TSU_ROWS) k_ts_update(int n, const double* __r
     const double* trow = tile + tid * (TSU_COLS + 1);
     for (int pp = 0; pp < pc; pp++) {
       const double a = trow[pp];
-      const double* c = sC + (size_t)(pb + pp) * 8;
+      const double* c = sC + (size_t)(pb + pp) * QW;
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[j] += a * c[j];
+      for (int j = 0; j < QW; j++) acc[j] += a * c[j];
     }
   }
   const int64_t r = r0 + tid;
   if (r < n) {
     double* w = W + (size_t)r * ldw;
 #pragma unroll
-    for (int j = 0; j < 8; j++)
+    for (int j = 0; j < QW; j++)
       if (j < q) w[j] = (beta == 0. ? 0. : beta * w[j]) + alpha * acc[j];
   }
 }
@@ -496,27 +509,34 @@ void pull_sum(int n, const int64_t* ptr, const int64_t* pos, const double* t, do
 }
 void ts_gram(int n, const double* X, int ldx, int p, const double* Y, int ldy, int q, double* G, int ldg, cudaStream_t st) {
   if (n <= 0 || p <= 0 || q <= 0) return;
-  const int tp = (p + TG_PCOLS - 1) / TG_PCOLS, tq = (q + 7) / 8;
+  const bool wide = q > 8;  // two 8-column tiles of Y per CTA: X is read once for a block of 16
+  const int tp = (p + TG_PCOLS - 1) / TG_PCOLS, tq = wide ? (q + 15) / 16 : 1;
   int nz = std::max(1, std::min((n + 255) / 256, std::max(1, NSM * 8 / (tp * tq))));
   int rowsPerCta = ((n + nz - 1) / nz + 31) / 32 * 32;
   nz = (n + rowsPerCta - 1) / rowsPerCta;
   dim3 grid(tp, tq, nz);
-  k_ts_gram<<<GENEO_TICK(grid), 256, 0, st>>>(n, X, ldx, p, Y, ldy, q, G, ldg, rowsPerCta);
+  if (wide) k_ts_gram<2><<<GENEO_TICK(grid), 256, 0, st>>>(n, X, ldx, p, Y, ldy, q, G, ldg, rowsPerCta);
+  else k_ts_gram<1><<<GENEO_TICK(grid), 256, 0, st>>>(n, X, ldx, p, Y, ldy, q, G, ldg, rowsPerCta);
   CUDA_CHECK(cudaGetLastError());
 }
 void ts_update(int n, const double* Q, int ldq, int p, const double* C, int ldc, int q, double* W, int ldw, double alpha,
                double beta, cudaStream_t st) {
-  constexpr int PCHUNK = 192;  // C chunk (192 x 8 doubles) + the Q tile stay below 48 KB of shared memory
+  // C chunk (192 x 8 or 96 x 16 doubles) + the Q tile stay below 48 KB of shared memory
   const int grid = (n + TSU_ROWS - 1) / TSU_ROWS;
   if (n <= 0) return;
-  for (int j0 = 0; j0 < q; j0 += 8) {
-    const int qc = std::min(8, q - j0);
+  for (int j0 = 0; j0 < q;) {
+    const bool wide = q - j0 > 8;  // 16 columns per pass: Q is read once for a block of 16
+    const int QW = wide ? 16 : 8, PCHUNK = wide ? 96 : 192;
+    const int qc = std::min(QW, q - j0);
     for (int p0 = 0; p0 < std::max(p, 1); p0 += PCHUNK) {
       const int pc = std::max(0, std::min(PCHUNK, p - p0));
-      const size_t smem = ((size_t)pc * 8 + (size_t)TSU_ROWS * (TSU_COLS + 1)) * sizeof(double);
-      k_ts_update<<<GENEO_TICK(grid), TSU_ROWS, smem, st>>>(n, Q + p0, ldq, pc, C + (size_t)p0 * ldc + j0, ldc, qc, W + j0, ldw, alpha,
-                                                             p0 == 0 ? beta : 1.);
+      const size_t smem = ((size_t)pc * QW + (size_t)TSU_ROWS * (TSU_COLS + 1)) * sizeof(double);
+      if (wide) k_ts_update<16><<<GENEO_TICK(grid), TSU_ROWS, smem, st>>>(n, Q + p0, ldq, pc, C + (size_t)p0 * ldc + j0, ldc, qc, W + j0, ldw,
+                                                                          alpha, p0 == 0 ? beta : 1.);
+      else k_ts_update<8><<<GENEO_TICK(grid), TSU_ROWS, smem, st>>>(n, Q + p0, ldq, pc, C + (size_t)p0 * ldc + j0, ldc, qc, W + j0, ldw, alpha,
+                                                                    p0 == 0 ? beta : 1.);
     }
+    j0 += QW;
   }
   CUDA_CHECK(cudaGetLastError());
 }

@@ -110,6 +110,9 @@ int geneo_pc_stats(geneo_pc_t pc, double stats[8]);
 /* every numeric factorization of the last (re-)setup: out = {device seconds, flops (symbolic: sum k^3/3 + m k^2 + m^2 k),
  * number of factorizations, host seconds spent on the shared reference ordering of the cold setup} */
 int geneo_pc_factor_stats(geneo_pc_t pc, double out[4]);
+/* Measurement: the level-1 factorizations of every local subdomain once more (same values, same factors), alone on the
+ * device, timed with CUDA events: out = {seconds, flops}. */
+int geneo_pc_factor_bench(geneo_pc_t pc, double out[2]);
 int geneo_pc_sub_info(geneo_pc_t pc, int s, int64_t ints[8] /* n, nev, estim, nicolaides, eigSteps, eigDim, neg, perturbed */,
                       double reals[2] /* tauLoc, gammaLoc */);
 int geneo_pc_sub_eigenvalues(geneo_pc_t pc, int s, double* vals, int cap, int* count);
