@@ -1,5 +1,7 @@
 """CPU-side tests of the product's HOST logic (no device needed): C-ABI exports, generators, decomposition parity with
 the oracle, symbolic analysis (validated by a numpy emulation of the device numeric phase), small dense eigen-solver."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -360,3 +362,41 @@ def test_geometric_nested_dissection_is_a_valid_ordering():
     assert neg == 0
     b = np.random.default_rng(2).standard_normal(a.shape[0])
     assert np.linalg.norm(a @ _emul.solve(sym, L, b) - b) <= 1e-9 * np.linalg.norm(b)
+
+
+def test_reference_plot_script_parses_the_cli_log():
+    """tst/plot.py (the reference's post-processing, :56-116) must read the logs of the PETSc-free driver: its own `job` parser
+    is imported from /root/reference (matplotlib stubbed out) and fed a log of geneo4petsc_b200/geneo4PETSc captured on the B200
+    box (tests/golden/cli_tridiag_geneo1ASM.log, --timing --cmdLine)."""
+    import importlib.util
+    import sys
+    import types
+    ref = "/root/reference/tst/plot.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present")
+    saved = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d")}
+    try:
+        for name in saved:
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        spec = importlib.util.spec_from_file_location("geneo_ref_plot", ref)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    log = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cli_tridiag_geneo1ASM.log")
+    lines = open(log).readlines()
+    first = next(i for i, ln in enumerate(lines) if ln.startswith("INFO:"))
+    lines = [ln for ln in lines[first:] if ln[0:3] != "WRNG" and len(ln.split()) > 0]  # plot.py:215-216
+    j = mod.job()
+    j.buildJob("tridiag-ws=1-np=2-tol=1e-12-metis=dual-ksp=gmres-pc=geneoASM1.log", lines)
+    assert (j.nbDOF, j.nbCoef, j.metis, j.overlap, j.ksp, j.pc) == (8, 23, "dual", "0", "gmres", "geneo1ASM")
+    assert j.L1 == "ldlt" and j.tau == "0.10" and j.L2 == "blocklanczos+ldlt" and j.gamma is None and not j.offload
+    assert (j.estimDimE, j.estimDimEMin, j.estimDimEMax, j.realDimE, j.realDimEMin, j.realDimEMax, j.nicolaides) == (0, 0, 0, 2, 1, 1, 2)
+    assert j.nbIt == 6 and j.setUpSolve > 0 and j.itSolve > 0 and abs(j.solve - (j.setUpSolve + j.itSolve)) < 1e-4
+    assert j.getSurfName() == "metis=dual-overlap=0-ksp=gmres-pc=geneo1ASM-L1=ldlt-tau=0.10-L2=blocklanczos+ldlt-distribE"
