@@ -122,12 +122,20 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
   bool prefetched = false;  // the solve of this step was already queued behind the previous step's device work
   int nextRR = 0, prevRRstep = -1;
   double prevWorst = 0.;
+  double* xs = (opt.solve && opt.xsExt && opt.wExt) ? opt.xsExt : Xs.p;
+  bool grouped = xs != Xs.p;  // this pencil's solves ride on the group's forest solve (until a pencil of the group is done)
+  struct Leaver { const EigOptions& o; bool on; ~Leaver() { if (on && o.leave) o.leave(); } } leaver{opt, grouped};
   auto launch_solve = [&](int col0) {  // W = F^-1 (B Q[:, col0 : col0+b])
     HostProfScope hp("lanczos: launch_solve");
-    k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)col0, maxDim, Xs.p, bp, b, bp);
+    k_copy_block<<<GENEO_TICK(gridn((int64_t)n * bp)), 256, 0, st>>>(n, BQ.p + (size_t)col0, maxDim, xs, bp, b, bp);
     for (int j0 = 0; j0 < bp;) {  // 16 right-hand sides per pass over the factor where the block allows it
       const int nr = (bp - j0 >= 16) ? 16 : 8;
-      F.solve_permuted(Xs.p, w, bp, j0, nr, st);
+      if (grouped && opt.solve(j0, nr, st))
+        k_copy_block<<<GENEO_TICK(gridn((int64_t)n * nr)), 256, 0, st>>>(n, opt.wExt + j0, bp, w + j0, bp, nr, nr);
+      else {
+        grouped = false;  // the group dissolved: from here on this pencil solves alone
+        F.solve_permuted(xs, w, bp, j0, nr, st);
+      }
       j0 += nr;
     }
   };

@@ -8,6 +8,7 @@
 // A whole block of right-hand sides goes through the factor per step, so the factor is streamed once per block
 // (ARPACK streams it once per vector).
 #pragma once
+#include <functional>
 #include <vector>
 #include "kernels.hpp"
 #include "ldlt.hpp"
@@ -27,6 +28,15 @@ struct EigOptions {
   int maxDim = 0;         // 0: automatic
   bool invert = true;     // report lambda = 1/theta
   EigWorkspace* ws = nullptr;  // optional persistent buffers
+  // Lock-step eigen-solves of several pencils (one host thread each) share ONE forest solve per step -- a single factor is
+  // latency-bound in the level barriers of the solve kernel, four of them stream.  xsExt / wExt: this pencil's slices (n x bp,
+  // ld = bp) of the group's right-hand-side / solution buffers; solve(j0, nr, st): true when the group solve wrote
+  // wExt[:, j0:j0+nr] = F^-1 xsExt[:, j0:j0+nr] (ordered after `st`, `st` ordered after it), false = do it yourself;
+  // leave(): called once when this pencil stops asking for solves.
+  double* xsExt = nullptr;
+  double* wExt = nullptr;
+  std::function<bool(int j0, int nr, cudaStream_t st)> solve;
+  std::function<void()> leave;
 };
 
 struct EigResult {

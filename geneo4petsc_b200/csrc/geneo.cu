@@ -461,7 +461,62 @@ struct GeneoPC::Lane {
   LdltWorkspace ws;
   DevBuf<double> T;          // transient factor (S, then A_neu) of the subdomain currently in the lane
   int* hc = nullptr;         // pinned: {neg, perturbed} of S, of A_neu, of A_dir
-  ~Lane() { if (st) cudaStreamDestroy(st); if (hc) cudaFreeHost(hc); }
+  cudaStream_t est = nullptr;  // the eigen-solve of the lane's subdomain: stream, Lanczos buffers, scalar scratch
+  EigWorkspace eig;
+  DevBuf<double> scal;
+  ~Lane() { if (st) cudaStreamDestroy(st); if (est) cudaStreamDestroy(est); if (hc) cudaFreeHost(hc); }
+};
+
+// Lock-step block solves of the pencils of one lane group (EigOptions::solve): every member (one host thread each) hands in
+// its right-hand side block; the last one to arrive launches ONE forest solve over the group's shift-invert factors.  A
+// single 100^3 factor keeps the solve kernel in its level barriers (1.5 TB/s); four of them stream.  The group dissolves
+// when its first member is done: the others finish their last steps alone.
+struct GroupSolver {
+  SolveForest forest;
+  std::vector<const LdltPlan*> plans;
+  std::vector<int64_t> off;      // first row of every member in the concatenated buffers
+  DevBuf<double> xs, w;          // (sum n_i) x ld, row-major
+  int ld = 0;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> evIn;
+  cudaEvent_t evOut[2] = {nullptr, nullptr};
+  std::mutex m;
+  std::condition_variable cv;
+  int members = 0, arrived = 0;
+  long gen = 0;
+  bool on = false;
+  ~GroupSolver() {
+    for (auto e : evIn) if (e) cudaEventDestroy(e);
+    for (auto e : evOut) if (e) cudaEventDestroy(e);
+    if (st) cudaStreamDestroy(st);
+  }
+  bool solve(int i, int j0, int nr, cudaStream_t ist) {
+    CUDA_CHECK(cudaEventRecord(evIn[i], ist));
+    std::unique_lock<std::mutex> lk(m);
+    if (!on) return false;
+    const long my = gen;
+    if (++arrived == members) {
+      try {
+        for (int q = 0; q < members; q++) CUDA_CHECK(cudaStreamWaitEvent(st, evIn[q], 0));
+        forest.solve(xs.p, w.p, ld, j0, nr, st);
+        CUDA_CHECK(cudaEventRecord(evOut[my & 1], st));
+      } catch (...) { on = false; arrived = 0; cv.notify_all(); throw; }
+      arrived = 0;
+      gen++;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&]() { return gen != my || !on; });
+      if (gen == my) { arrived--; return false; }  // dissolved while waiting: solve alone
+    }
+    lk.unlock();
+    CUDA_CHECK(cudaStreamWaitEvent(ist, evOut[my & 1], 0));
+    return true;
+  }
+  void leave() {
+    std::lock_guard<std::mutex> lk(m);
+    on = false;
+    cv.notify_all();
+  }
 };
 
 GeneoPC::GeneoPC() {}
@@ -505,6 +560,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   // solve forest holds raw pointers into the old plans, subs[p].L1 is bound to the old plan, comm to the old layout)
   CUDA_CHECK(::geneo::sync_stream(st));
   subs.clear();
+  groupSolvers.clear();
   lanes.clear();
   forest = SolveForest();
   factorWs = LdltWorkspace();
@@ -714,7 +770,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
     numeric_pipeline();
     tNum += now_s() - tn;
   }
-  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); lanes.clear(); }
+  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); groupSolvers.clear(); lanes.clear(); }
   symbolicTime = waitHost;  // time this thread spent WAITING for the host analysis (the rest of it was hidden behind the device)
   uploadTime = tUp;
 
@@ -888,7 +944,7 @@ void GeneoPC::numeric_setup() {
   numeric_begin();
   if (use_pipeline()) numeric_pipeline();
   else for (auto& s : subs) numeric_subdomain(s, factorWs);
-  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); lanes.clear(); }
+  if (opt.releaseWorkspace) { factorWs = LdltWorkspace(); eigWs.release(); groupSolvers.clear(); lanes.clear(); }
   numeric_end();
   numericTime = now_s() - tNum0;
   host_prof_add("numeric_setup total", numericTime);
@@ -933,14 +989,15 @@ double GeneoPC::local_gamma(const SubdomainState& s) const {
 }
 
 // Z_s = D [v_1 ... v_nev]  (fillZE2L, src/geneo.cpp:249-272); empty => constant vector (:1305-1314)
-void GeneoPC::assemble_z(SubdomainState& s, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts) {
+void GeneoPC::assemble_z(SubdomainState& s, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts,
+                         cudaStream_t zs) {
   int nev = 0;
   for (int c : counts) nev += c;
   const double tz = now_s();
   if (nev == 0) {
     s.nev = 1;
     s.Z.alloc((size_t)s.n);
-    CUDA_CHECK(cudaMemcpyAsync(s.Z.p, s.d.p, sizeof(double) * s.n, cudaMemcpyDeviceToDevice, st));  // D * 1
+    CUDA_CHECK(cudaMemcpyAsync(s.Z.p, s.d.p, sizeof(double) * s.n, cudaMemcpyDeviceToDevice, zs));  // D * 1
     s.eigvals.assign(1, 0.);
     s.nicolaides += 1;
   } else {
@@ -950,13 +1007,13 @@ void GeneoPC::assemble_z(SubdomainState& s, std::vector<double>& vals, std::vect
     for (size_t b = 0; b < vecs.size(); b++) {
       const int nc = counts[b];
       if (nc == 0) continue;
-      copy_cols(s.n, vecs[b].p, nc, s.Z.p + c0, nev, nc, st);
+      copy_cols(s.n, vecs[b].p, nc, s.Z.p + c0, nev, nc, zs);
       c0 += nc;
     }
-    rows_scale(s.n, nev, s.d.p, s.Z.p, st);  // Z = D V
+    rows_scale(s.n, nev, s.d.p, s.Z.p, zs);  // Z = D V
     s.eigvals = vals;
   }
-  CUDA_CHECK(::geneo::sync_stream(st));
+  CUDA_CHECK(::geneo::sync_stream(zs));
   lvl2SetupZTime += now_s() - tz;
 }
 
@@ -984,7 +1041,7 @@ void GeneoPC::numeric_subdomain(SubdomainState& s, LdltWorkspace& ws) {
       if (!opt.cst) { gl = local_gamma(s); s.gammaLoc = gl; }
       eigen_local_problem(s, s.vB.p, s.vRob.p, gl, false, cut, ws, vals, vecs, counts);
     }
-    assemble_z(s, vals, vecs, counts);
+    assemble_z(s, vals, vecs, counts, st);
   }
   // level 1: factor A_dir (or A_rob), src/geneo.cpp:126-148
   const double tl1 = now_s();
@@ -1103,7 +1160,9 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
       FactorStats f2 = tmp.factorize(tauPb ? vA : vB, pivTol, ws, st);
       allFactorSeconds += f2.seconds; allFactorFlops += s.plan->sym.flops; allFactorCount++;
     }
-    got = eigen_finish(s, tmp, vA, vB, param, tauPb, est, cut, vals, vecs, counts);
+    EigCtx cx;
+    cx.st = st; cx.ws = &eigWs; cx.scal = scal.p;
+    got = eigen_finish(s, tmp, vA, vB, param, tauPb, est, cut, vals, vecs, counts, cx);
     const double dt = now_s() - t0;
     lvl2SetupEigTime += dt;
     (tauPb ? lvl2SetupTauEigTime : lvl2SetupGammaEigTime) += dt;
@@ -1114,8 +1173,22 @@ int GeneoPC::eigen_local_problem(SubdomainState& s, const double* vA, const doub
 }
 
 // Block Lanczos with the shift-invert factor `fac`, threshold filter (src/geneo.cpp:713-714), Nicolaides rule (:897-944).
+int GeneoPC::eig_block(int est, int cut) const {
+  int nev = est > 0 ? est : 1;
+  if (cut > 0 && nev > cut) nev = cut;
+  const int guard = (!opt.noSyl && (cut <= 0 || nev < cut)) ? 2 : 0;
+  // Block of 8 by default.  -els2_eps_block 16 sends 16 right-hand sides per pass over the factor (k_solve_ring<16>),
+  // but measured on 8 x 80^3 the wider block needs a 45-60 % larger Krylov space for the same pairs (13-16 steps of 16
+  // against 18-19 steps of 8): 1.13 s against 0.93 s for the eight eigen-solves.
+  // A pencil that wants many pairs (high-contrast heat: 100-250 per subdomain) is bound by the passes over the basis, one per
+  // step whatever the block: there the block of 16 (fewer, fatter steps) wins.
+  return opt.epsBlock > 0 ? opt.epsBlock : (nev + guard >= 64 ? 16 : 8);
+}
+
 int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double* vA, const double* vB, double param, bool tauPb,
-                          int est, int cut, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts) {
+                          int est, int cut, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts,
+                          const EigCtx& cx) {
+  cudaStream_t st = cx.st;  // (shadows the library's stream: everything below runs where the caller says)
   const int n = s.n;
   const int64_t nnz = s.pat.nnz;
   int nev = est > 0 ? est : 1;  // SLEPc default when nothing is requested
@@ -1124,14 +1197,17 @@ int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double
   // A - theta B whose sign is lost to rounding (no pivoting across pivot blocks) cannot drop a genuine GenEO vector.
   const int guard = (!opt.noSyl && (cut <= 0 || nev < cut)) ? 2 : 0;
   EigOptions eo;
-  // Block of 8 by default.  -els2_eps_block 16 sends 16 right-hand sides per pass over the factor (k_solve_ring<16>),
-  // but measured on 8 x 80^3 the wider block needs a 45-60 % larger Krylov space for the same pairs (13-16 steps of 16
-  // against 18-19 steps of 8): 1.13 s against 0.93 s for the eight eigen-solves.
-  // A pencil that wants many pairs (high-contrast heat: 100-250 per subdomain) is bound by the passes over the basis, one per
-  // step whatever the block: there the block of 16 (fewer, fatter steps) wins.
-  eo.block = opt.epsBlock > 0 ? opt.epsBlock : (nev + guard >= 64 ? 16 : 8);
+  eo.block = eig_block(est, cut);
   eo.tol = opt.epsTol; eo.maxDim = opt.epsMaxDim; eo.invert = tauPb;
-  eo.ws = &eigWs;
+  eo.ws = cx.ws;
+  if (cx.grp && cx.member >= 0) {  // this pencil's block solves ride on the group's forest solve
+    GroupSolver* G = cx.grp;
+    const int mi = cx.member;
+    eo.xsExt = G->xs.p + (size_t)G->off[mi] * G->ld;
+    eo.wExt = G->w.p + (size_t)G->off[mi] * G->ld;
+    eo.solve = [G, mi](int j0, int nr, cudaStream_t ist) { return G->solve(mi, j0, nr, ist); };
+    eo.leave = [G]() { G->leave(); };
+  }
   EigResult er;
   {
     HostProfScope hp("eig block_lanczos");
@@ -1169,11 +1245,11 @@ int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double
   bool addOne = false;
   if (tauPb && got > 0 && *std::min_element(lam.begin(), lam.end()) >= DBL_EPSILON) {
     double num = 0., den = 0.;
-    csr_sum_all(nnz, vA, scal.p, st);
-    CUDA_CHECK(cudaMemcpyAsync(&num, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    csr_sum_all(nnz, vA, cx.scal, st);
+    CUDA_CHECK(cudaMemcpyAsync(&num, cx.scal, sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(::geneo::sync_stream(st));
-    csr_sum_all(nnz, vB, scal.p, st);
-    CUDA_CHECK(cudaMemcpyAsync(&den, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    csr_sum_all(nnz, vB, cx.scal, st);
+    CUDA_CHECK(cudaMemcpyAsync(&den, cx.scal, sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(::geneo::sync_stream(st));
     if (std::fabs(num / den) <= (double)FLT_EPSILON) addOne = true;
   }
@@ -1225,7 +1301,9 @@ void GeneoPC::numeric_pipeline() {
   while ((int)lanes.size() < want) {
     lanes.emplace_back(new Lane());
     CUDA_CHECK(cudaStreamCreateWithFlags(&lanes.back()->st, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&lanes.back()->est, cudaStreamNonBlocking));
     CUDA_CHECK(cudaHostAlloc((void**)&lanes.back()->hc, 6 * sizeof(int), cudaHostAllocDefault));
+    lanes.back()->scal.alloc(16);
   }
   const int NL = (int)lanes.size();
   // every allocation of the concurrent region happens here, before it starts (the block cache is stream-ordered on ONE stream)
@@ -1333,39 +1411,93 @@ void GeneoPC::numeric_pipeline() {
   });
   struct Joiner { std::thread& t; std::mutex& m; std::condition_variable& c; bool& ab; ~Joiner() { { std::lock_guard<std::mutex> lk(m); ab = true; } c.notify_all(); if (t.joinable()) t.join(); } } joiner{helper, mtx, cv, abortAll};
 
-  if (l2) {
-    for (int p = 0; p < P; p++) {
-      SubdomainState& s = subs[p];
-      Lane& L = *lanes[p % NL];
+  // ---- the eigen-solves, one lane group at a time: the pencils of a group run in LOCK-STEP (one host thread each, one
+  //      forest solve per step over the group's shift-invert factors) while the helper keeps the lanes busy with the
+  //      level-1 factorizations of this group and the S / A_neu factorizations of the next one
+  static const bool groupEig = getenv("GENEO_GROUP_EIG") ? atoi(getenv("GENEO_GROUP_EIG")) != 0 : true;
+  if ((int)groupSolvers.size() < (P + NL - 1) / NL) groupSolvers.resize((P + NL - 1) / NL);
+  bool mainAbort = false;
+  for (int g0 = 0; l2 && g0 < P && !mainAbort; g0 += NL) {
+    const int g1 = std::min(P, g0 + NL);
+    std::vector<int> est(g1 - g0, 0);
+    for (int p = g0; p < g1; p++) {
       {
         std::unique_lock<std::mutex> lk(mtx);
         cv.wait(lk, [&]() { return enqueued[p] != 0 || abortAll; });
-        if (abortAll && !enqueued[p]) break;
+        if (abortAll && !enqueued[p]) { mainAbort = true; break; }
       }
-      int est = 0;
       if (syl) {
         const double t0 = now_s();
         CUDA_CHECK(cudaEventSynchronize(evS[p]));
-        est = sylvester_estimate(s, L.hc[0], L.hc[1], true, opt.cut);
+        est[p - g0] = sylvester_estimate(subs[p], lanes[p - g0]->hc[0], lanes[p - g0]->hc[1], true, opt.cut);
         lvl2SetupSylTime += now_s() - t0; lvl2SetupTauSylTime += now_s() - t0;
       }
-      std::vector<double> vals;
-      std::vector<DevBuf<double>> vecs;
-      std::vector<int> counts;
-      const double t0 = now_s();
-      CUDA_CHECK(cudaEventSynchronize(evN[p]));
-      if (opt.noSyl || est > 0) eigen_finish(s, *tmpF[p], s.vNeu.p, s.vB.p, opt.tau, true, est, opt.cut, vals, vecs, counts);
-      lvl2SetupEigTime += now_s() - t0; lvl2SetupTauEigTime += now_s() - t0;
-      assemble_z(s, vals, vecs, counts);
-      CUDA_CHECK(::geneo::sync_stream(st));  // the library's stream is done with the transient factor
-      {
-        std::lock_guard<std::mutex> lk(mtx);
-        L.T = std::move(tmpF[p]->L);
-        s.plan->selfL = nullptr;  // the plan's single-factor forest must re-read the factor pointer next time
+    }
+    if (mainAbort) break;
+    const double t0 = now_s();
+    for (int p = g0; p < g1; p++) CUDA_CHECK(cudaEventSynchronize(evN[p]));
+    std::vector<int> act;  // members with an eigen-solve to do
+    for (int p = g0; p < g1; p++)
+      if (opt.noSyl || est[p - g0] > 0) act.push_back(p);
+    // Do the Lanczos buffers of all members fit at once?  (basis + its B image: 2 n maxDim doubles per pencil -- 20 GB for a
+    // heat subdomain that wants 200 pairs.)  If not, the pencils run one after the other on the library's stream, as in
+    // the sequential path, and share one workspace.
+    bool threaded = groupEig && act.size() >= 2 && !g_hostprof;
+    if (threaded) {
+      double need = 0.;
+      for (int p : act) {
+        const int b = eig_block(est[p - g0], opt.cut);
+        const int nev = std::max(1, est[p - g0]) + 2;
+        const double maxDim = opt.epsMaxDim > 0 ? opt.epsMaxDim : std::max(6 * nev + 8 * b, 128);
+        need += 8. * subs[p].n * (2. * maxDim + 8. * b) - (double)(lanes[p - g0]->eig.Q.cap + lanes[p - g0]->eig.BQ.cap);
+      }
+      size_t freeB = 0, totB = 0;
+      CUDA_CHECK(cudaMemGetInfo(&freeB, &totB));
+      if (need > (double)freeB - 3e9) threaded = false;
+    }
+    // group solver: same Lanczos block for everybody, at least two pencils
+    GroupSolver* grp = nullptr;
+    bool uniform = threaded;    std::vector<std::vector<double>> gvals(g1 - g0);
+    std::vector<std::vector<DevBuf<double>>> gvecs(g1 - g0);
+    std::vector<std::vector<int>> gcounts(g1 - g0);
+    std::vector<std::string> gerr(g1 - g0);
+    std::vector<std::thread> eth;
+    for (size_t a = 0; a < act.size(); a++) {
+      const int p = act[a];
+      auto work = [&, a, p]() {
+        try {
+          CUDA_CHECK(cudaSetDevice(dev));
+          Lane& L = *lanes[p - g0];
+          EigCtx cx;
+          if (threaded) { cx.st = L.est; cx.ws = &L.eig; cx.scal = L.scal.p; cx.grp = grp; cx.member = grp ? (int)a : -1; }
+          else { cx.st = st; cx.ws = &eigWs; cx.scal = scal.p; }
+          eigen_finish(subs[p], *tmpF[p], subs[p].vNeu.p, subs[p].vB.p, opt.tau, true, est[p - g0], opt.cut, gvals[p - g0], gvecs[p - g0],
+                       gcounts[p - g0], cx);
+          assemble_z(subs[p], gvals[p - g0], gvecs[p - g0], gcounts[p - g0], cx.st);
+          CUDA_CHECK(cudaStreamSynchronize(cx.st));
+        } catch (std::exception& e) {
+          gerr[p - g0] = e.what();
+          if (grp) grp->leave();
+        }
+      };
+      if (threaded) eth.emplace_back(work);
+      else work();
+    }
+    for (auto& t : eth) t.join();
+    for (auto& e : gerr) if (!e.empty()) throw Error(e);
+    for (int p = g0; p < g1; p++)
+      if (std::find(act.begin(), act.end(), p) == act.end()) assemble_z(subs[p], gvals[p - g0], gvecs[p - g0], gcounts[p - g0], st);  // constant vector
+    if (grp) CUDA_CHECK(cudaStreamSynchronize(grp->st));
+    lvl2SetupEigTime += now_s() - t0; lvl2SetupTauEigTime += now_s() - t0;
+    {
+      std::lock_guard<std::mutex> lk(mtx);
+      for (int p = g0; p < g1; p++) {
+        lanes[p - g0]->T = std::move(tmpF[p]->L);
+        subs[p].plan->selfL = nullptr;  // the plan's single-factor forest must re-read the factor pointer next time
         eigDone[p] = 1;
       }
-      cv.notify_all();
     }
+    cv.notify_all();
   }
   { std::lock_guard<std::mutex> lk(mtx); if (!helperErr.empty()) abortAll = true; }
   helper.join();

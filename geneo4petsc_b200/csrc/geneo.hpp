@@ -142,13 +142,17 @@ class GeneoPC {
   int eigen_local_problem(SubdomainState& s, const double* vA, const double* vB, double param, bool tauPb, int cut,
                           LdltWorkspace& ws, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs,
                           std::vector<int>& counts);
+  // where an eigen-solve runs: the library's stream and workspace (sequential path) or one of the pipeline's eigen threads
+  struct EigCtx { cudaStream_t st = 0; EigWorkspace* ws = nullptr; double* scal = nullptr; struct GroupSolver* grp = nullptr; int member = -1; };
   int eigen_finish(SubdomainState& s, const LdltFactor& fac, const double* vA, const double* vB, double param, bool tauPb, int est,
-                   int cut, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts);
+                   int cut, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts, const EigCtx& cx);
+  int eig_block(int est, int cut) const;  // Lanczos block of a pencil that wants est pairs
   int sylvester_estimate(SubdomainState& s, int neg, int perturbedS, bool tauPb, int cut);
-  void assemble_z(SubdomainState& s, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts);
+  void assemble_z(SubdomainState& s, std::vector<double>& vals, std::vector<DevBuf<double>>& vecs, std::vector<int>& counts, cudaStream_t zs);
   void account_subdomain(const SubdomainState& s);
   double local_gamma(const SubdomainState& s) const;
   struct Lane;
+  std::vector<std::unique_ptr<struct GroupSolver>> groupSolvers;  // lock-step block solves of the pencils of a lane group
   std::vector<std::unique_ptr<Lane>> lanes;  // streams + workspaces of the pipelined numeric setup, kept between re-setups
   void build_coarse();
   void level1(const double* xin, double* yout, bool addQ);
