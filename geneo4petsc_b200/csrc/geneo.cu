@@ -483,7 +483,7 @@ struct GroupSolver {
   std::mutex m;
   std::condition_variable cv;
   int members = 0, arrived = 0;
-  long gen = 0;
+  long gen = 0, refused = 0;
   bool on = false;
   ~GroupSolver() {
     for (auto e : evIn) if (e) cudaEventDestroy(e);
@@ -493,7 +493,7 @@ struct GroupSolver {
   bool solve(int i, int j0, int nr, cudaStream_t ist) {
     CUDA_CHECK(cudaEventRecord(evIn[i], ist));
     std::unique_lock<std::mutex> lk(m);
-    if (!on) return false;
+    if (!on) { refused++; return false; }
     const long my = gen;
     if (++arrived == members) {
       try {
@@ -1457,7 +1457,37 @@ void GeneoPC::numeric_pipeline() {
     }
     // group solver: same Lanczos block for everybody, at least two pencils
     GroupSolver* grp = nullptr;
-    bool uniform = threaded;    std::vector<std::vector<double>> gvals(g1 - g0);
+    bool uniform = threaded;
+    for (size_t a = 1; a < act.size() && uniform; a++)
+      uniform = eig_block(est[act[a] - g0], opt.cut) == eig_block(est[act[0] - g0], opt.cut) && subs[act[a]].n > 64;
+    if (uniform && subs[act[0]].n > 64) {
+      std::unique_ptr<GroupSolver>& slot = groupSolvers[g0 / NL];
+      std::vector<const LdltPlan*> plans;
+      for (int p : act) plans.push_back(subs[p].plan.get());
+      const int ld = (eig_block(est[act[0] - g0], opt.cut) + 7) / 8 * 8;
+      if (!slot || slot->plans != plans) {
+        slot.reset(new GroupSolver());
+        slot->plans = plans;
+        int64_t o = 0;
+        for (int p : act) { slot->off.push_back(o); o += subs[p].n; }
+        slot->forest.build(plans, slot->off);
+        CUDA_CHECK(cudaStreamCreateWithFlags(&slot->st, cudaStreamNonBlocking));
+        slot->evIn.assign(act.size(), nullptr);
+        for (auto& e : slot->evIn) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : slot->evOut) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
+      grp = slot.get();
+      const size_t rows = (size_t)(grp->off.back() + subs[act.back()].n);
+      if (grp->xs.n < rows * ld) { grp->xs.alloc(rows * ld); grp->w.alloc(rows * ld); }
+      grp->ld = ld;
+      grp->members = (int)act.size();
+      grp->arrived = 0;
+      grp->gen = grp->refused = 0;
+      grp->on = true;
+      std::vector<const double*> Ls;
+      for (int p : act) Ls.push_back(tmpF[p]->L.p);
+      grp->forest.set_factors(Ls, grp->st);
+    }    std::vector<std::vector<double>> gvals(g1 - g0);
     std::vector<std::vector<DevBuf<double>>> gvecs(g1 - g0);
     std::vector<std::vector<int>> gcounts(g1 - g0);
     std::vector<std::string> gerr(g1 - g0);
@@ -1488,6 +1518,9 @@ void GeneoPC::numeric_pipeline() {
     for (int p = g0; p < g1; p++)
       if (std::find(act.begin(), act.end(), p) == act.end()) assemble_z(subs[p], gvals[p - g0], gvecs[p - g0], gcounts[p - g0], st);  // constant vector
     if (grp) CUDA_CHECK(cudaStreamSynchronize(grp->st));
+    if (getenv("GENEO_DEBUG_GROUP"))
+      fprintf(stderr, "DEBUG group %d: %d pencils, threaded %d, group solver %d, combined solves %ld, solo after dissolve %ld, %.3f s\n", g0 / NL,
+              (int)act.size(), (int)threaded, grp ? 1 : 0, grp ? grp->gen : 0, grp ? grp->refused : 0, now_s() - t0);
     lvl2SetupEigTime += now_s() - t0; lvl2SetupTauEigTime += now_s() - t0;
     {
       std::lock_guard<std::mutex> lk(mtx);

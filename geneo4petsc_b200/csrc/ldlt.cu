@@ -1375,6 +1375,10 @@ void SolveForest::build_generic() const {
   genericBuilt = true;
 }
 
+static int ring8_min_cspan() {
+  static const int v = [] { const char* e = getenv("GENEO_RING8_CSPAN"); const int c = e ? atoi(e) : 32; return c >= 128 ? 128 : c >= 64 ? 64 : 32; }();
+  return v;
+}
 // Item lists of the ring kernel.  Per level the host picks the span of an item from the amount of work in the level: a
 // level with many tiles per warp gets wide (forward: up to all 128 columns of a panel) / tall (backward: up to 512 rows)
 // items -- fewer records, x / y fetches and atomics per byte --, a level near the root gets the finest tiles so that every
@@ -1405,7 +1409,11 @@ void SolveForest::build_ring(int which) const {
         bytes += 8. * F.h * F.k;
       }
     }
-    const int cspan = 32 * pow2_floor(tiles / (4 * nw), 1, 4);
+    int cspan = 32 * pow2_floor(tiles / (4 * nw), 1, 4);
+    // (experiment hook GENEO_RING8_CSPAN: a wider minimum span for the block solves quarters their FP64 atomics per byte --
+    //  measured on 8 x 100^3: 3.25 s of eigen-solves with 32, 3.30 s with 64, 3.48 s with 128: not atomic-bound, the finest
+    //  tiles stay the default)
+    if (which >= 1) cspan = std::max(cspan, ring8_min_cspan());
     ranges[l] = (int64_t)items.size();
     for (int s = 0; s < ns; s++) {
       const Symbolic& S = plans_[s]->sym;
