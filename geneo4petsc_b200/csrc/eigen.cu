@@ -53,7 +53,9 @@ void block_lanczos(int n, const LdltFactor& F, const int64_t* ptr, const int* id
   if (n <= 64) { b = n; maxDim = n; }
   else {
     b = std::max(1, opt.block);
-    maxDim = opt.maxDim > 0 ? opt.maxDim : std::max(6 * nev + 8 * b, 128);
+    // basis bound: 4 nev + 8 b columns (measured: 205 wanted pairs converge in a 590-column basis, 10 in 104-136); when it
+    // is reached the iteration restarts thickly.  (6 nev before: 2 x 14 GB of basis for a 10^6-row pencil that wants 260 pairs.)
+    maxDim = opt.maxDim > 0 ? opt.maxDim : std::max(4 * nev + 8 * b, 128);
     maxDim = std::min(maxDim, n);
     maxDim = std::max(b, maxDim / b * b);
   }

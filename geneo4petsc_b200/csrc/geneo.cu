@@ -1294,7 +1294,8 @@ void GeneoPC::numeric_pipeline() {
     int64_t have = 0;  // what the existing lanes already hold
     for (auto& L : lanes) have += (int64_t)(L->T.cap + L->ws.u0.cap + L->ws.u1.cap + L->ws.uc.cap + L->ws.w0.cap + L->ws.w1.cap);
     const double perLane = 8. * ((l2 ? (double)maxL : 0.) + (double)maxArena);
-    const double avail = (double)freeB + (double)have - 8. * (double)sumL - 6e9;  // resident factors still to come, Lanczos buffers, slack
+    // resident factors still to come; Lanczos bases, Z and slack: 15 % of the device
+    const double avail = (double)freeB + (double)have - 8. * (double)sumL - std::max(6e9, 0.15 * (double)totB);
     while (want > 1 && perLane * want > avail) want--;
   }
   while ((int)lanes.size() > want) lanes.pop_back();
@@ -1448,7 +1449,7 @@ void GeneoPC::numeric_pipeline() {
       for (int p : act) {
         const int b = eig_block(est[p - g0], opt.cut);
         const int nev = std::max(1, est[p - g0]) + 2;
-        const double maxDim = opt.epsMaxDim > 0 ? opt.epsMaxDim : std::max(6 * nev + 8 * b, 128);
+        const double maxDim = opt.epsMaxDim > 0 ? opt.epsMaxDim : std::max(4 * nev + 8 * b, 128);
         need += 8. * subs[p].n * (2. * maxDim + 8. * b) - (double)(lanes[p - g0]->eig.Q.cap + lanes[p - g0]->eig.BQ.cap);
       }
       size_t freeB = 0, totB = 0;
