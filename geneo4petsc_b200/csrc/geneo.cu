@@ -808,6 +808,7 @@ void GeneoPC::numeric_begin() {
   allFactorSeconds = allFactorFlops = 0.;
   allFactorCount = 0;
   for (auto& s : subs) {
+    s.prevNev = std::max(s.prevNev, s.nev);  // (sizes the memory reserve of the next pipelined setup)
     s.estim = s.nicolaides = s.eigSteps = s.eigDim = s.negL1 = s.perturbed = 0;
     s.nev = 0;
   }
@@ -1286,17 +1287,46 @@ void GeneoPC::numeric_pipeline() {
     maxArena = std::max(maxArena, 2 * S.uArena + S.cArena + 2 * S.wArena);
     if (!s.L1 || (int64_t)s.L1->L.n < S.lSize) sumL += S.lSize;
   }
-  int want = std::min(P, 4);
+  // How many lanes?  Each costs its update arenas + a transient factor (17.8 GB at 100^3); what the eigen-solves and the
+  // coarse vectors will need next to them (Lanczos bases 2 n maxDim, Z_i = n nev_i) depends on the eigen-counts, which a FIRST
+  // setup does not know (a heat subdomain wants 200+ pairs, a Laplacian one 10): two lanes then, which already give most of
+  // the overlap (8 factorizations: 2.06 s on one lane, 1.87 s on two, 1.82 s on four); a re-setup sizes the reserve from
+  // the eigen-counts of the previous one and takes up to four.
+  int prevMaxNev = 0;
+  double zGrowth = 0.;
+  for (auto& s : subs) {
+    prevMaxNev = std::max(prevMaxNev, s.prevNev);
+    zGrowth += std::max(0., 8. * (double)s.n * std::max(s.prevNev, 1) - (double)s.Z.cap);
+  }
+  const bool history = l2 && prevMaxNev > 0;
+  int want = std::min(P, (history || !l2) ? 4 : 2);
   if (const char* e = getenv("GENEO_LANES")) want = std::max(1, std::min(P, atoi(e)));
   {
     size_t freeB = 0, totB = 0;
     CUDA_CHECK(cudaMemGetInfo(&freeB, &totB));
     int64_t have = 0;  // what the existing lanes already hold
-    for (auto& L : lanes) have += (int64_t)(L->T.cap + L->ws.u0.cap + L->ws.u1.cap + L->ws.uc.cap + L->ws.w0.cap + L->ws.w1.cap);
+    double eigHave = 0.;
+    for (auto& L : lanes) {
+      have += (int64_t)(L->T.cap + L->ws.u0.cap + L->ws.u1.cap + L->ws.uc.cap + L->ws.w0.cap + L->ws.w1.cap);
+      eigHave += (double)(L->eig.Q.cap + L->eig.BQ.cap);
+    }
+    eigHave += (double)(eigWs.Q.cap + eigWs.BQ.cap);
     const double perLane = 8. * ((l2 ? (double)maxL : 0.) + (double)maxArena);
-    // resident factors still to come; Lanczos bases, Z and slack: 15 % of the device
-    const double avail = (double)freeB + (double)have - 8. * (double)sumL - std::max(6e9, 0.15 * (double)totB);
-    while (want > 1 && perLane * want > avail) want--;
+    int64_t nmax = 0;
+    for (auto& s : subs) nmax = std::max<int64_t>(nmax, s.n);
+    auto eig_need = [&](int lanesNow) {  // one Lanczos workspace per lane (lock-step group) or one shared one, + Ritz vectors
+      const int b = eig_block(prevMaxNev, opt.cut);
+      const double maxDim = opt.epsMaxDim > 0 ? opt.epsMaxDim : std::max(4 * (prevMaxNev + 2) + 8 * b, 128);
+      const double one = 8. * (double)nmax * (2. * maxDim + 8. * b + 2. * (prevMaxNev + 2));
+      return one * lanesNow;
+    };
+    while (want > 1) {
+      const double reserve = history ? std::max(0., eig_need(want) - eigHave) + zGrowth + 0.05 * (double)totB
+                                     : std::max(6e9, 0.15 * (double)totB);
+      // resident factors still to come, the reserve, the lanes
+      if (perLane * want <= (double)freeB + (double)have - 8. * (double)sumL - reserve) break;
+      want--;
+    }
   }
   while ((int)lanes.size() > want) lanes.pop_back();
   while ((int)lanes.size() < want) {

@@ -45,7 +45,7 @@ struct GeneoOptions {
 };
 
 struct SubdomainState {
-  int id = 0, n = 0, nev = 0;
+  int id = 0, n = 0, nev = 0, prevNev = 0;
   int64_t off = 0;   // into the concatenated subdomain vectors
   int zoff = 0;      // into the coarse vector
   std::shared_ptr<LdltPlan> plan;
