@@ -1642,19 +1642,30 @@ void GeneoPC::build_coarse() {
   auto plan = std::make_shared<LdltPlan>(nE, pe.ptr.data(), pe.idx.data(), so);
   LdltFactor LE(plan);
   LdltWorkspace ws;
+  // Symmetric equilibration E' = S E S, S = diag(E_ii)^-1/2 (MUMPS scales by default too): with a 10^6 coefficient contrast
+  // the diagonal of E spans 12 orders of magnitude (tiny GenEO eigenvalues next to Nicolaides vectors of stiff
+  // subdomains) and the null-pivot test, relative to max |E_ii|, would throw genuine coarse modes away.
+  std::vector<double> sc(nE, 1.);
+  for (int i = 0; i < nE; i++) {
+    const double dii = hE[(size_t)i * nE + i];
+    sc[i] = dii > 0. ? 1. / std::sqrt(dii) : 1.;
+  }
+  for (int i = 0; i < nE; i++)
+    for (int j = 0; j < nE; j++) hE[(size_t)i * nE + j] *= sc[i] * sc[j];
   dE.upload(hE, st);
-  double emax = 0.;
-  for (int i = 0; i < nE; i++) emax = std::max(emax, std::fabs(hE[(size_t)i * nE + i]));
-  FactorStats fs = LE.factorize(dE.p, opt.pivRel * std::max(emax, 1e-300), ws, st);
+  FactorStats fs = LE.factorize(dE.p, opt.pivRel, ws, st);  // (unit diagonal after scaling)
   if (fs.neg > 0 || fs.perturbed > 0)
-    fprintf(stderr, "WRNG: geneo_b200: coarse operator E is not positive definite (neg %d, perturbed %d)\n", fs.neg, fs.perturbed);
+    fprintf(stderr, "WRNG: geneo_b200: coarse operator E is not positive definite (neg %d, null pivots %d)\n", fs.neg, fs.perturbed);
+  // E^-1 = S E'^-1 S: solve for the columns of S, then scale the rows
   std::vector<double> hI((size_t)nE * nEp, 0.);
-  for (int i = 0; i < nE; i++) hI[(size_t)i * nEp + i] = 1.;
-  DevBuf<double> dI;
+  for (int i = 0; i < nE; i++) hI[(size_t)i * nEp + i] = sc[i];
+  DevBuf<double> dI, dS;
   dI.upload(hI, st);
+  dS.upload(sc, st);
   Einv.alloc((size_t)nE * nEp);
   Einv.zero(st);
   for (int j0 = 0; j0 < nEp; j0 += 8) LE.solve_permuted(dI.p, Einv.p, nEp, j0, 8, st);
+  if (nE > 0) rows_scale(nE, nEp, dS.p, Einv.p, st);
   w.alloc(nEp); w2.alloc(nEp);
   CUDA_CHECK(::geneo::sync_stream(st));
 }
