@@ -489,13 +489,18 @@ def run_b200(a):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback 6650",
                      "traffic": traffic, "algorithmic_bytes_per_launch": tri_b, "launches_timed": klaunch, "avg_launch_ms": kavg},
         "roofline_factorization": {
-            "kernel": "block LDL^T factorizations (k_schur / k_schur2 / k_panel DMMA tiles + assembly), all of a step, rank 0",
+            "kernel": "block LDL^T factorization kernels (k_schur2 / k_schur / k_panel DMMA tiles, k_diag_invert, assembly): the level-1 "
+                      "factorizations of all local subdomains, alone on the device, rank 0",
             "bound": "tensor", "achieved": fac_tf, "peak": gemm_tf, "unit": "TFLOP/s", "frac": fac_tf / gemm_tf if gemm_tf else None,
             "peak_source": "cuBLAS DGEMM 6144^3 through torch.matmul measured in this run (no FP64 entry in MEASURED_PEAKS.json; "
                            "nominal FP64 tensor peak of B200 ~ 37-40 TFLOP/s)",
-            "flops_per_step": fac_f / a.steps, "seconds_per_step": fac_s / a.steps, "share_of_step": fac_s / a.steps / (ms * 1e-3),
-            "how": "flops = sum over fronts of k^3/3 + m k^2 + m^2 k (symbolic analysis) for every factorization of the step; "
-                   "seconds = device time of the factorization calls (each ends with a stream synchronisation)"},
+            "flops_timed": fb_f, "seconds_timed": fb_s,
+            "in_step": {"flops_per_step": fac_f / a.steps, "pipeline_span_s_per_step": fac_s / a.steps, "TFLOPs": pipe_tf,
+                        "share_of_step": fac_s / a.steps / (ms * 1e-3),
+                        "note": "span of the factorization pipeline inside the timed steps: 3 factorizations per subdomain on several "
+                                "streams; the block-Lanczos eigen-solves run inside the same span and take the SMs in turn"},
+            "how": "flops = sum over fronts of k^3/3 + m k^2 + m^2 k (symbolic analysis); achieved = the level-1 factorizations of all "
+                   "local subdomains run once more, alone on the device, between two CUDA events (geneo_pc_factor_bench)"},
         "detail": {"n_dof": n, "iterations": r["its"], "reason": r["reason_name"], "rnorm": r["rnorm"], "max_rel_err_vs_1..N": err,
                    "setup_numeric_s": setup_s / a.steps, "iter_s": iter_s / a.steps, "dimE": info["nE"],
                    "nev_min_max": [info["realMin"], info["realMax"]],
@@ -515,20 +520,23 @@ def run_b200(a):
                                "scaling": scaling_rows(table)}
         p3 = g.Problem().set_mesh(mesh.nb_node, mesh.elem_ptr, mesh.elem_idx, mesh.mat_val)
         p3.decompose(a.subs_per_gpu, True, 0, elem_part=rep.part[0])
-        torch.cuda.synchronize()
-        ta = time.perf_counter()
-        pc3 = g.GeneoPC(["-geneo_lvl", a.lvl, "-geneo_tau", a.tau] + extra).setup(p3)
-        b3 = rep.b
-        r3 = pc3.ksp_solve(b3, ksp=a.ksp, rtol=a.rtol, atol=1e-50, restart=30)
-        tb = time.perf_counter()
+        gpu_t = []
+        for _ in range(2):  # twice: the first run of a fresh handle pays for pinned buffers, streams and the lanes' allocations
+            torch.cuda.synchronize()
+            ta = time.perf_counter()
+            pc3 = g.GeneoPC(["-geneo_lvl", a.lvl, "-geneo_tau", a.tau] + extra).setup(p3)
+            b3 = rep.b
+            r3 = pc3.ksp_solve(b3, ksp=a.ksp, rtol=a.rtol, atol=1e-50, restart=30)
+            tb = time.perf_counter()
+            gpu_t.append(tb - ta)
         est_gpu = [pc3.sub_info(s)["estim"] for s in range(a.subs_per_gpu)]
         est_cpu = [int(s.estim) for s in rep.pc.sub]
         out["parity"] = {"sample": "size %d, same partition arrays, same options" % s_edge,
                          "its_gpu": r3["its"], "its_cpu": its, "dimE_gpu": pc3.info()["nE"], "dimE_cpu": int(rep.pc.e.shape[0]),
                          "eigen_counts_equal": est_gpu == est_cpu,
                          "x_rel_diff": float(np.linalg.norm(r3["x"] - rep.ksp.x) / np.linalg.norm(rep.ksp.x)),
-                         "same_size": {"edge": s_edge, "gpu_e2e_dofs_per_s": nn / (tb - ta), "cpu_dofs_per_s": nn / secs,
-                                       "ratio": secs / (tb - ta)}}
+                         "same_size": {"edge": s_edge, "gpu_e2e_dofs_per_s": nn / gpu_t[0], "gpu_e2e_dofs_per_s_second_run": nn / gpu_t[1],
+                                       "cpu_dofs_per_s": nn / secs, "ratio": secs / gpu_t[0], "ratio_second_run": secs / gpu_t[1]}}
         del pc3
     print(json.dumps(out), flush=True)
     if os.environ.get("GENEO_PROFILE"):

@@ -79,9 +79,20 @@ inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64
 
 Comm::~Comm() { reset(); }
 
+// One NCCL communicator per PROCESS and (rank, world), shared by every preconditioner the process sets up -- the way MPI
+// hands the reference one PETSC_COMM_WORLD for all its PCs.  ncclCommInitRank and the lazily established peer connections of
+// the first send / recv / allreduce cost seconds on 8 GPUs; a second PCSetUp in the same job must not pay them again.
+// (GENEO_COMM_PER_PC=1: the old behaviour, a fresh communicator per setup.)
+namespace {
+struct SharedComm { int rank, world; ncclComm_t c; };
+std::vector<SharedComm>& shared_comms() { static std::vector<SharedComm>* v = new std::vector<SharedComm>(); return *v; }
+bool comm_per_pc() { static const bool v = getenv("GENEO_COMM_PER_PC") != nullptr; return v; }
+}  // namespace
+
 void Comm::reset() {
-  if (comm_) api().CommDestroy((ncclComm_t)comm_);
+  if (comm_ && owned_) api().CommDestroy((ncclComm_t)comm_);
   comm_ = nullptr;
+  owned_ = false;
   rank = 0; world = 1; nOwn = nGhost = 0; bufWidth_ = 0;
   sendPtr_.clear(); recvPtr_.clear();
 }
@@ -98,10 +109,17 @@ void Comm::init(int rank_, int world_, const void* uid128, const RankLayout& L, 
   nOwn = L.nOwn(); nGhost = L.nGhost();
   if (world <= 1) return;
   GENEO_CHECK(uid128 != nullptr, "multi-GPU setup without an NCCL unique id");
-  NcclUid id;
-  std::memcpy(&id, uid128, sizeof(id));
   ncclComm_t c = nullptr;
-  NCCL_CHECK(api().CommInitRank(&c, world, id, rank));
+  if (!comm_per_pc())
+    for (auto& sc : shared_comms())
+      if (sc.rank == rank && sc.world == world) c = sc.c;  // (every rank takes the same branch: they all set up the same sequence of PCs)
+  if (!c) {
+    NcclUid id;
+    std::memcpy(&id, uid128, sizeof(id));
+    NCCL_CHECK(api().CommInitRank(&c, world, id, rank));
+    if (comm_per_pc()) owned_ = true;
+    else shared_comms().push_back(SharedComm{rank, world, c});
+  }
   comm_ = c;
   sendPtr_.assign(world + 1, 0);
   recvPtr_.assign(L.ghostPtr.begin(), L.ghostPtr.end());

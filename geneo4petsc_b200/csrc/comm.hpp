@@ -31,6 +31,7 @@ class Comm {
   int64_t bytesSent = 0;  // per-process NVLink traffic issued (statistics)
  private:
   void* comm_ = nullptr;  // ncclComm_t
+  bool owned_ = false;    // false: the process-wide communicator of (rank, world), never destroyed by a PC
   std::vector<int64_t> sendPtr_, recvPtr_;  // [world+1]: rows sent to / received from each peer
   DevBuf<int> dSendIdx_;
   DevBuf<double> sendBuf_, recvBuf_, tmp_;

@@ -830,13 +830,16 @@ void GeneoPC::numeric_end() {
     std::vector<int64_t> xoff;
     std::vector<const double*> Ls;
     for (auto& s : subs) { plans.push_back(s.plan.get()); xoff.push_back(s.off); Ls.push_back(s.L1->L.p); }
+    const double tf = now_s();
     if (forest.nlev == 0) forest.build(plans, xoff);
     forest.set_factors(Ls, st);
+    if (getenv("GENEO_COLD_TIMING")) fprintf(stderr, "COLD rank %d: level-1 forest %.3f s\n", comm.rank, now_s() - tf);
   }
   if (opt.lvl2 >= 1) {
     const double te = now_s();
     build_coarse();
     lvl2SetupETime = now_s() - te;
+    if (getenv("GENEO_COLD_TIMING")) fprintf(stderr, "COLD rank %d: coarse operator %.3f s\n", comm.rank, lvl2SetupETime);
     infoL2 = "blocklanczos ldlt";
   }
   CUDA_CHECK(::geneo::sync_stream(st));
@@ -1209,6 +1212,17 @@ int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double
     eo.solve = [G, mi](int j0, int nr, cudaStream_t ist) { return G->solve(mi, j0, nr, ist); };
     eo.leave = [G]() { G->leave(); };
   }
+  {  // fail with a message, not with a 100 GB cudaMalloc: tau = 0.4 on a 100^3 subdomain asks for thousands of pairs
+    const int want = std::min(nev + guard, n);
+    const double maxDim = eo.maxDim > 0 ? eo.maxDim : std::max(4 * want + 8 * eo.block, 128);
+    const double need = 8. * (double)n * (2. * std::min<double>(maxDim, n) + 2. * want) - (double)(cx.ws ? cx.ws->Q.cap + cx.ws->BQ.cap : 0);
+    size_t freeB = 0, totB = 0;
+    CUDA_CHECK(cudaMemGetInfo(&freeB, &totB));
+    if (need > (double)freeB)
+      throw Error("geneo_b200: the eigen-solve of subdomain " + std::to_string(s.id) + " wants " + std::to_string(want) + " pairs of a pencil of order " +
+                  std::to_string(n) + ": its Lanczos basis and Ritz vectors need " + std::to_string((long long)(need / 1e9)) + " GB, " +
+                  std::to_string((long long)(freeB / 1e9)) + " GB are free -- lower -geneo_tau or cap the count with -geneo_cut");
+  }
   EigResult er;
   {
     HostProfScope hp("eig block_lanczos");
@@ -1277,6 +1291,8 @@ int GeneoPC::eigen_finish(SubdomainState& s, const LdltFactor& fac, const double
 // DMMA tiles of the other lanes.  Dependencies: CUDA events between streams, two host flags per subdomain between the threads.
 // =====================================================================================================================
 void GeneoPC::numeric_pipeline() {
+  const double tCold0 = now_s();
+  static const bool coldTiming = getenv("GENEO_COLD_TIMING") != nullptr;
   const int P = (int)subs.size();
   const bool l2 = opt.lvl2 >= 1, syl = l2 && !opt.noSyl;
   // ---- lanes: as many as fit next to the resident factors (each lane = update arenas + one transient factor) -------------
@@ -1349,6 +1365,7 @@ void GeneoPC::numeric_pipeline() {
     if (l2 && (int64_t)lanes[j]->T.n < maxL) lanes[j]->T.alloc((size_t)maxL);
   }
   CUDA_CHECK(cudaDeviceSynchronize());
+  const double tCold1 = now_s();
 
   std::vector<cudaEvent_t> evS(P, nullptr), evN(P, nullptr), evD(P, nullptr);
   for (int p = 0; p < P; p++) {
@@ -1580,6 +1597,9 @@ void GeneoPC::numeric_pipeline() {
     allFactorCount += 1 + (l2 ? 1 : 0) + (syl ? 1 : 0);
   }
   allFactorSeconds += now_s() - tPipe0;  // span of the factorization pipeline (the eigen-solves run inside it)
+  if (coldTiming)
+    fprintf(stderr, "COLD rank %d: pipeline allocations (lanes %d, resident factors, value buffers) %.3f s, pipeline %.3f s\n", comm.rank, NL,
+            tCold1 - tCold0, now_s() - tCold1);
 }
 
 // Z offsets (all_gather of nev_i, src/geneo.cpp:363-375), E = Z^T A Z (MatPtAP :1033), E^-1 (dcs2_, :1059-1065)

@@ -13,7 +13,7 @@ import json
 try:
     d=json.loads(open("gpurun_out/${TAG}_bench_box.json").read().strip().splitlines()[-1])
     print("ms_per_step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["seconds"], "sym", d["e2e"]["symbolic_s"], "ord", d["e2e"]["ordering_reuse_s"], "num", d["e2e"]["numeric_s"])
-    print("roofline", d["roofline"]["frac"], "factor TF", d["roofline_factorization"]["achieved"], d["roofline_factorization"]["seconds_per_step"])
+    print("roofline", d["roofline"]["frac"], "factor TF", d["roofline_factorization"]["achieved"], d["roofline_factorization"]["in_step"]["pipeline_span_s_per_step"])
     print("phases", d["detail"]["numeric_phases_s_rank0"], "its", d["detail"]["iterations"], "dimE", d["detail"]["dimE"])
     print("parity", d.get("parity"))
 except Exception as e:
