@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--tau", default="0.1")
     ap.add_argument("--ksp", default="", help="cg | gmres (default: cg, gmres for --kind graph: BASELINE configs[3])")
     ap.add_argument("--rtol", type=float, default=1e-5)
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-size", type=int, default=0, help="grid edge of the CPU sample; 0 = the largest that fits --cpu-budget")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg of the b200 arm")
     ap.add_argument("--ref-budget", type=float, default=200.0, help="seconds for the whole --impl reference run")
@@ -479,6 +479,7 @@ def run_b200(a):
         "config": cfg,
         "clocks": clk.summary(),
         "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "seconds": e2e_s,
+                "seconds_runs": [round(t, 3) for t in e2e_t],
                 "symbolic_s": sym_max, "upload_s": tm2["upload"], "numeric_s": num_max, "ordering_reuse_s": fs2["ordering_reuse_s"],
                 "gen_s": gen_max, "part_decomp_s": pd_max,
                 "note": "seconds = create + setup (host analysis, H2D, numeric) + solve with host b/x; gen_s / part_decomp_s (mesh "
