@@ -46,7 +46,7 @@ extern bool g_profile;
 void profile_tick(const char* file, int line);
 // every host wait of the library goes through here: in profile mode a marker event closes the interval of the last
 // kernel, so that the idle gap while the host works is accounted to "host" and not to that kernel
-extern double g_sync_wait_s;  // host time spent waiting for the device (what is left of a phase is host-side work)
+extern thread_local double g_sync_wait_s;  // host time this THREAD spent waiting for the device (what is left of a phase is host-side work)
 inline cudaError_t sync_stream(cudaStream_t s) {
   if (g_profile) profile_tick("<host wait / idle>", 0);
   const double t0 = now_s();

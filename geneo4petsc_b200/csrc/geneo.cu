@@ -127,7 +127,7 @@ void h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   }
 }
 
-double g_sync_wait_s = 0.;
+thread_local double g_sync_wait_s = 0.;
 namespace {
 const bool g_hostprof = getenv("GENEO_HOSTPROF") != nullptr;
 struct HostProfRec { std::string name; double s = 0.; long n = 0; };
@@ -1018,7 +1018,11 @@ void GeneoPC::assemble_z(SubdomainState& s, std::vector<double>& vals, std::vect
     s.eigvals = vals;
   }
   CUDA_CHECK(::geneo::sync_stream(zs));
-  lvl2SetupZTime += now_s() - tz;
+  {  // (several eigen threads of a lane group end here)
+    static std::mutex zTimerMtx;
+    std::lock_guard<std::mutex> lk(zTimerMtx);
+    lvl2SetupZTime += now_s() - tz;
+  }
 }
 
 // every factorization and eigen-solve of one subdomain, one after the other on the library's stream (level 2 first: its
