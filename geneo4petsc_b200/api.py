@@ -374,3 +374,23 @@ class Symbolic:
         if getattr(self, "h", None) and self.h:
             lib.geneo_symbolic_destroy(self.h)
             self.h = None
+
+
+def host_prepare_probe(a_csr, perm=None, nb=128, helper=False, scatter_len=0, sort=True):
+    """Per-subdomain host preparation of a symmetric CSR matrix (host only): (stage seconds, digest[, scattered factor])."""
+    a = a_csr.tocsr()
+    if sort:
+        a.sort_indices()
+    n = a.shape[0]
+    ptr = np.ascontiguousarray(a.indptr, dtype=np.int64)
+    idx = np.ascontiguousarray(a.indices, dtype=np.int32)
+    val = np.ascontiguousarray(a.data, dtype=np.float64)
+    sec = np.zeros(4)
+    dig = C.c_uint64(0)
+    pp = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    out = np.zeros(scatter_len) if scatter_len else None
+    _chk(lib.geneo_host_prepare_probe(C.c_int(n), _p(ptr, _i64p), _p(idx, _i32p), _p(val, _f64p),
+                                      None if pp is None else _p(pp, _i32p), C.c_int(nb), C.c_int(int(helper)),
+                                      _p(sec, _f64p), C.byref(dig), None if out is None else _p(out, _f64p),
+                                      C.c_int64(scatter_len)))
+    return (sec, int(dig.value)) if out is None else (sec, int(dig.value), out)

@@ -666,6 +666,13 @@ int geneo_host_sym_eig_rows(int n, double* a, const int32_t* rows, int nrows, do
   sym_eig_rows(n, a, rows, nrows, w, yrows);
   ABI_CATCH
 }
+int geneo_host_prepare_probe(int n, const int64_t* ptr, const int32_t* idx, const double* val, const int32_t* perm, int nb, int helper,
+                             double seconds[4], uint64_t* digest, double* scatterOut, int64_t scatterLen) {
+  ABI_TRY
+  ABI_REQ(ptr && idx && val && seconds && digest && n > 0, "null argument");
+  host_prepare_probe(n, ptr, idx, val, perm, nb, helper, seconds, digest, scatterOut, scatterLen);
+  ABI_CATCH
+}
 int geneo_host_sym_eig(int n, double* a, double* w) { ABI_TRY ABI_REQ(a && w && n >= 0, "null argument"); sym_eig(n, a, w); ABI_CATCH }
 
 int geneo_microbench(int kind, int n, int reps, double result[2]) {

@@ -296,6 +296,7 @@ struct HostPrep {  // everything the host prepares for one subdomain (worker thr
   std::vector<int> userPerm;    // ordering inherited from the reference box (see plan_ordering_reuse); empty: METIS on this subdomain
   double anorm = 0.;
   int maxMult = 1;
+  double stageS[4] = {0., 0., 0., 0.};  // symbolic analysis, permuted values, work lists, (spare)
   std::string err;
 };
 
@@ -388,51 +389,137 @@ void plan_ordering_reuse(const Decomposition& dec, const std::vector<const Subdo
   }
 }
 
-void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth, HostPrep& H) {
+void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth, HostPrep& H, bool helper, bool forceGeneral = false) {
   const int n = (int)S.nodes.size();
   SymbolicOptions so;
   so.nb = opt.nb;
   so.ordering = opt.ordering;
   so.ndDepth = ndDepth;
+  so.skipAsm = true;
   if (!H.userPerm.empty()) { so.ordering = 3; so.userPerm = H.userPerm.data(); }
-  symbolic_analyze(n, S.aDir.ptr.data(), S.aDir.idx.data(), so, H.sym);
+  const bool ptm = getenv("GENEO_PREP_TIMING") != nullptr;
+  double tq = now_s(), tl = tq;
+  auto lap = [&](const char* what) { if (ptm) { const double t = now_s(); fprintf(stderr, "prepare n=%d %s %.3fs\n", n, what, t - tl); tl = t; } };
+  const int64_t nnz = S.aDir.nnz();
+  // ---- everything that does not depend on the ordering (a second thread when the cores allow it): positions of the
+  //      transposed entries, A_neu expanded to the A_dir pattern, and the first touch of the large output arrays (fresh
+  //      pages cost about as much as the passes that fill them)
+  std::vector<int64_t> tT, asmSrc, asmDst;
+  std::vector<double> neuExp;
+  bool haveT = false;
+  std::string sideErr;
+  auto side = [&]() {
+    try {
+      int64_t ndiag = 0;
+      haveT = nnz > 0 && !forceGeneral && transpose_positions(n, S.aDir.ptr.data(), S.aDir.idx.data(), tT, &ndiag);
+      if (!haveT) std::vector<int64_t>().swap(tT);
+      neuExp.assign((size_t)nnz, 0.);
+      for (int r = 0; r < n; r++) {
+        int64_t q = S.aDir.ptr[r];
+        for (int64_t t = S.aNeu.ptr[r]; t < S.aNeu.ptr[r + 1]; t++) {
+          while (q < S.aDir.ptr[r + 1] && S.aDir.idx[q] < S.aNeu.idx[t]) q++;
+          GENEO_CHECK(q < S.aDir.ptr[r + 1] && S.aDir.idx[q] == S.aNeu.idx[t], "A_neu entry outside the A_dir pattern");
+          neuExp[q] = S.aNeu.val[t];
+        }
+      }
+      H.patP.n = H.patP.ncols = n;
+      H.patP.ptr.assign(n + 1, 0);
+      H.patP.idx.resize((size_t)nnz);
+      H.patP.val.resize((size_t)nnz);
+      H.vNeuP.resize((size_t)nnz);
+      if (haveT) {  // symmetric pattern: as many entries below the diagonal as above
+        asmSrc.resize((size_t)(ndiag + (nnz - ndiag) / 2));
+        asmDst.resize(asmSrc.size());
+      }
+    } catch (std::exception& e) { sideErr = e.what(); }
+  };
+  std::thread sideThread;
+  if (helper) sideThread = std::thread(side);
+  try {
+    symbolic_analyze(n, S.aDir.ptr.data(), S.aDir.idx.data(), so, H.sym);
+  } catch (...) {
+    if (sideThread.joinable()) sideThread.join();
+    throw;
+  }
+  H.stageS[0] = now_s() - tq; tq = now_s();
+  lap("analysis");
+  if (sideThread.joinable()) sideThread.join();
+  else side();
+  if (!sideErr.empty()) throw Error(sideErr);
+  lap(helper ? "wait for the side thread" : "transposed positions, A_neu, first touch");
   const std::vector<int>& perm = H.sym.perm;
   const std::vector<int>& iperm = H.sym.iperm;
-  // A_neu expanded to the A_dir pattern (natural order), then everything permuted to the solver order
-  const int64_t nnz = S.aDir.nnz();
-  std::vector<double> neuExp((size_t)nnz, 0.);
-  for (int r = 0; r < n; r++) {
-    int64_t q = S.aDir.ptr[r];
-    for (int64_t t = S.aNeu.ptr[r]; t < S.aNeu.ptr[r + 1]; t++) {
-      while (q < S.aDir.ptr[r + 1] && S.aDir.idx[q] < S.aNeu.idx[t]) q++;
-      GENEO_CHECK(q < S.aDir.ptr[r + 1] && S.aDir.idx[q] == S.aNeu.idx[t], "A_neu entry outside the A_dir pattern");
-      neuExp[q] = S.aNeu.val[t];
+  if (haveT) {
+    // Sorted rows, symmetric pattern: ONE pass over the matrix in the new row order fills P A P^T through the transposed
+    // entries -- every row comes out sorted by new column without a sort -- and, the rows running front by front, the
+    // scatter map of the lower triangle with it (position of a row in the front of column k: one table lookup).
+    Symbolic& Y = H.sym;
+    std::vector<int64_t> fill(n);
+    for (int k = 0; k < n; k++) H.patP.ptr[k + 1] = H.patP.ptr[k] + (S.aDir.ptr[perm[k] + 1] - S.aDir.ptr[perm[k]]);
+    for (int k = 0; k < n; k++) fill[k] = H.patP.ptr[k];
+    std::vector<int> where(n, 0);
+    double amax = 0.;
+    int64_t w = 0;
+    int kNext = 0;
+    const int64_t wMax = (int64_t)asmSrc.size();
+    for (const Front& F : Y.fronts) {
+      GENEO_CHECK(F.col0 == kNext, "host preparation: fronts do not cover the columns in order");
+      kNext = F.col0 + F.k;
+      const int* rows = &Y.rowIdx[F.rowOff];
+      for (int q = 0; q < F.h; q++) where[rows[q]] = q;
+      for (int k = F.col0; k < F.col0 + F.k; k++) {
+        const int ro = perm[k];
+        const int64_t colBase = F.lOff + (int64_t)(k - F.col0) * F.ld;
+        for (int64_t t = S.aDir.ptr[ro]; t < S.aDir.ptr[ro + 1]; t++) {
+          const int i = iperm[S.aDir.idx[t]];
+          const int64_t q = fill[i]++;
+          const int64_t src = tT[t];  // the entry (idx[t], ro) of the input = entry (i, k) of the permuted matrix
+          const double v = S.aDir.val[src];
+          H.patP.idx[q] = k;
+          H.patP.val[q] = v;
+          H.vNeuP[q] = neuExp[src];
+          amax = std::max(amax, std::fabs(v));
+          if (i >= k) {
+            const int pos = where[i];
+            GENEO_CHECK(pos < F.h && rows[pos] == i && w < wMax, "symbolic: matrix entry outside the predicted structure");
+            asmSrc[(size_t)w] = q;
+            asmDst[(size_t)w] = colBase + pos;
+            w++;
+          }
+        }
+      }
     }
-  }
-  H.patP.n = H.patP.ncols = n;
-  H.patP.ptr.assign(n + 1, 0);
-  H.patP.idx.resize((size_t)nnz);
-  H.patP.val.resize((size_t)nnz);
-  H.vNeuP.resize((size_t)nnz);
-  std::vector<int64_t> origToPerm((size_t)nnz);
-  std::vector<std::pair<int, int64_t>> row;
-  for (int k = 0; k < n; k++) {
-    const int ro = perm[k];
-    row.clear();
-    for (int64_t t = S.aDir.ptr[ro]; t < S.aDir.ptr[ro + 1]; t++) row.emplace_back(iperm[S.aDir.idx[t]], t);
-    std::sort(row.begin(), row.end());
-    int64_t q = H.patP.ptr[k];
-    for (auto& e : row) {
-      H.patP.idx[q] = e.first;
-      H.patP.val[q] = S.aDir.val[e.second];
-      H.vNeuP[q] = neuExp[e.second];
-      origToPerm[e.second] = q;
-      H.anorm = std::max(H.anorm, std::fabs(S.aDir.val[e.second]));
-      q++;
+    GENEO_CHECK(kNext == n && w == wMax, "host preparation: scatter map lost entries");
+    H.anorm = std::max(H.anorm, amax);
+    Y.asmSrc.swap(asmSrc);
+    Y.asmDst.swap(asmDst);
+    lap("permuted values + scatter map");
+  } else {
+    // general input (unsorted rows or an unsymmetric pattern): sort every permuted row, binary searches for the scatter map
+    symbolic_asm_map(n, S.aDir.ptr.data(), S.aDir.idx.data(), nullptr, H.sym);
+    std::vector<int64_t> origToPerm((size_t)nnz);
+    std::vector<std::pair<int, int64_t>> row;
+    for (int k = 0; k < n; k++) {
+      const int ro = perm[k];
+      row.clear();
+      for (int64_t t = S.aDir.ptr[ro]; t < S.aDir.ptr[ro + 1]; t++) row.emplace_back(iperm[S.aDir.idx[t]], t);
+      std::sort(row.begin(), row.end());
+      int64_t q = H.patP.ptr[k];
+      for (auto& e : row) {
+        H.patP.idx[q] = e.first;
+        H.patP.val[q] = S.aDir.val[e.second];
+        H.vNeuP[q] = neuExp[e.second];
+        origToPerm[e.second] = q;
+        H.anorm = std::max(H.anorm, std::fabs(S.aDir.val[e.second]));
+        q++;
+      }
+      H.patP.ptr[k + 1] = q;
     }
-    H.patP.ptr[k + 1] = q;
+    for (auto& s : H.sym.asmSrc) s = origToPerm[s];
+    lap("permuted values + scatter map (general input)");
   }
-  for (auto& s : H.sym.asmSrc) s = origToPerm[s];
+  std::vector<double>().swap(neuExp);
+  std::vector<int64_t>().swap(tT);
   H.dP.resize(n);
   H.gidx.resize(n);
   for (int k = 0; k < n; k++) {
@@ -449,11 +536,69 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
           if (S.mult[perm[H.patP.idx[q]]] > 1) H.vRobP[q] += opt.optim * H.vNeuP[q];
       }
   }
+  lap("partition of unity, Robin");
+  H.stageS[1] = now_s() - tq; tq = now_s();
   // the work lists of every factorization level are host work too: built here, uploaded by the thread that owns the device
   H.plan = std::make_shared<LdltPlan>(std::move(H.sym), LdltPlan::HostOnly{});
+  H.stageS[2] = now_s() - tq;
 }
 
 }  // namespace
+
+// Host-only test hook: the per-subdomain host preparation (analysis, permuted values, scatter map, work lists) of a plain
+// symmetric CSR matrix taken as A_dir = A_neu, with its stage stopwatches and a digest of everything it produced.
+void host_prepare_probe(int n, const int64_t* ptr, const int* idx, const double* val, const int* userPerm, int nb, int helper,
+                        double seconds[4], uint64_t* digest, double* scatterOut, int64_t scatterLen) {
+  Subdomain S;
+  S.nodes.resize(n); for (int i = 0; i < n; i++) S.nodes[i] = i;
+  S.mult.assign(n, 1);
+  S.aDir.n = S.aDir.ncols = n;
+  S.aDir.ptr.assign(ptr, ptr + n + 1);
+  S.aDir.idx.assign(idx, idx + ptr[n]);
+  S.aDir.val.assign(val, val + ptr[n]);
+  S.aNeu = S.aDir;
+  GeneoOptions opt;
+  opt.nb = nb;
+  opt.lvl1ORAS = true;
+  opt.optim = 0.5;
+  HostPrep H;
+  if (userPerm) H.userPerm.assign(userPerm, userPerm + n);
+  prepare_subdomain(S, opt, 0, H, (helper & 1) != 0, (helper & 2) != 0);
+  for (int a = 0; a < 4; a++) seconds[a] = H.stageS[a];
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t bytes) {
+    const unsigned char* c = (const unsigned char*)p;
+    // 8 bytes at a time (FNV-like; the arrays are large)
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) { uint64_t v; memcpy(&v, c + i, 8); h = (h ^ v) * 1099511628211ull; }
+    for (; i < bytes; i++) h = (h ^ c[i]) * 1099511628211ull;
+  };
+  const Symbolic& Y = H.plan->sym;
+  mix(H.patP.ptr.data(), H.patP.ptr.size() * 8); mix(H.patP.idx.data(), H.patP.idx.size() * 4);
+  mix(H.patP.val.data(), H.patP.val.size() * 8); mix(H.vNeuP.data(), H.vNeuP.size() * 8);
+  mix(H.vRobP.data(), H.vRobP.size() * 8); mix(H.dP.data(), H.dP.size() * 8); mix(H.gidx.data(), H.gidx.size() * 4);
+  mix(Y.perm.data(), Y.perm.size() * 4); mix(Y.rowIdx.data(), Y.rowIdx.size() * 4); mix(Y.rel.data(), Y.rel.size() * 4);
+  // the scatter map as a set of (src, dst) pairs: order-independent sum of a pair hash
+  uint64_t acc = 0;
+  for (size_t t = 0; t < Y.asmSrc.size(); t++) {
+    uint64_t v = (uint64_t)Y.asmSrc[t] * 0x9E3779B97F4A7C15ull ^ ((uint64_t)Y.asmDst[t] + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+    v ^= v >> 29; v *= 0xBF58476D1CE4E5B9ull; v ^= v >> 32;
+    acc += v;
+  }
+  mix(&acc, 8);
+  const uint64_t na = Y.asmSrc.size();
+  mix(&na, 8);
+  for (const Front& F : Y.fronts) {
+    const int64_t q[8] = {F.col0, F.k, F.h, F.parent, F.lOff, F.uOff, F.wOff, F.relOff};
+    mix(q, sizeof(q));
+  }
+  *digest = h;
+  if (scatterOut) {  // what the assembly kernel would write: the factor array holding the scattered lower triangle
+    GENEO_CHECK(scatterLen == Y.lSize, "host_prepare_probe: scatterLen must be the factor size of the analysis");
+    std::fill(scatterOut, scatterOut + scatterLen, 0.);
+    for (size_t t = 0; t < Y.asmSrc.size(); t++) scatterOut[Y.asmDst[t]] = H.patP.val[(size_t)Y.asmSrc[t]];
+  }
+}
 
 // one lane of the pipelined numeric setup (numeric_pipeline): a stream, its update arenas and a transient factor
 struct GeneoPC::Lane {
@@ -625,6 +770,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
   std::atomic<int> ticket(0);
   std::vector<std::thread> pool;
   std::string orchErr;
+  bool sideThreads = false;
   // The shared reference ordering (one METIS call for all box subdomains) and then the analysis workers are started from
   // an orchestrating thread: this thread assembles and uploads the operator meanwhile.  Single process only -- with
   // several ranks the ordering is a collective on the library's stream and stays on this thread.
@@ -637,6 +783,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
       int nInherit = 0;
       for (auto& H : prep) nInherit += H.userPerm.empty() ? 0 : 1;
       if (nInherit == P) { inFlight = std::max(1, std::min<int>(P, (int)hw)); ndDepth = 0; }  // no METIS call left: one thread per subdomain
+      sideThreads = (unsigned)(2 * inFlight) <= hw;  // a second thread per subdomain for the ordering-independent part
     } catch (std::exception& e) { orchErr = e.what(); }
     for (int w = 0; w < inFlight; w++)
       pool.emplace_back([&]() {
@@ -644,7 +791,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
           const int p = ticket.fetch_add(1);
           if (p >= P) break;
           if (!orchErr.empty()) prep[p].err = orchErr;
-          else try { prepare_subdomain(*mine[p], opt, ndDepth, prep[p]); } catch (std::exception& e) { prep[p].err = e.what(); }
+          else try { prepare_subdomain(*mine[p], opt, ndDepth, prep[p], sideThreads); } catch (std::exception& e) { prep[p].err = e.what(); }
           { std::lock_guard<std::mutex> lk(mtx); ready[p] = 1; }
           cv.notify_all();
         }

@@ -173,4 +173,8 @@ class GeneoPC {
   cudaEvent_t evFork = nullptr;
 };
 
+// host-only test hook (geneo.cu): per-subdomain host preparation of a symmetric CSR matrix, stage stopwatches + digest
+void host_prepare_probe(int n, const int64_t* ptr, const int* idx, const double* val, const int* userPerm, int nb, int helper,
+                        double seconds[4], uint64_t* digest, double* scatterOut, int64_t scatterLen);
+
 }  // namespace geneo

@@ -648,6 +648,61 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
   // ---- 7. scatter map of the input values (lower triangle of P A P^T) into the panels --------------------------------
   S.perm = perm;
   S.iperm = iperm;
+  if (!opt.skipAsm) {
+    std::vector<int64_t> tT;
+    const bool haveT = transpose_positions(n, ptr, idx, tT, nullptr);
+    symbolic_asm_map(n, ptr, idx, haveT ? &tT : nullptr, S);
+  }
+  lap("asm map");
+}
+
+bool transpose_positions(int n, const int64_t* ptr, const int* idx, std::vector<int64_t>& tT, int64_t* ndiag) {
+  tT.resize((size_t)ptr[n]);
+  std::vector<int64_t> next(ptr, ptr + n);
+  int64_t nd = 0;
+  for (int r = 0; r < n; r++)
+    for (int64_t t = ptr[r]; t < ptr[r + 1]; t++) {
+      const int c = idx[t];
+      if (c < 0 || c >= n) return false;
+      const int64_t q = next[c];  // rows run in ascending order: the next unused entry of row c must be the column r
+      if (q >= ptr[c + 1] || idx[q] != r) return false;
+      tT[t] = q;
+      next[c] = q + 1;
+      nd += (c == r);
+    }
+  if (ndiag) *ndiag = nd;
+  return true;
+}
+
+void symbolic_asm_map(int n, const int64_t* ptr, const int* idx, const std::vector<int64_t>* tTp, Symbolic& S) {
+  const std::vector<int>& perm = S.perm;
+  const std::vector<int>& iperm = S.iperm;
+  const std::vector<int>& rowIdx = S.rowIdx;
+  S.asmSrc.clear();
+  S.asmDst.clear();
+  if (tTp && (int64_t)tTp->size() == ptr[n]) {
+    const std::vector<int64_t>& tT = *tTp;
+    S.asmSrc.reserve(ptr[n] / 2 + n);
+    S.asmDst.reserve(ptr[n] / 2 + n);
+    std::vector<int> where(n, 0);  // position of a row in the current front (checked: stale entries are harmless)
+    for (const Front& F : S.fronts) {
+      const int* rows = &rowIdx[F.rowOff];
+      for (int q = 0; q < F.h; q++) where[rows[q]] = q;
+      for (int j = F.col0; j < F.col0 + F.k; j++) {
+        const int jo = perm[j];
+        const int64_t colBase = F.lOff + (int64_t)(j - F.col0) * F.ld;
+        for (int64_t t = ptr[jo]; t < ptr[jo + 1]; t++) {  // row perm[j]: the transposed entries of column j
+          const int i = iperm[idx[t]];
+          if (i < j) continue;
+          const int pos = where[i];
+          GENEO_CHECK(pos < F.h && rows[pos] == i, "symbolic: matrix entry outside the predicted structure");
+          S.asmSrc.push_back(tT[t]);
+          S.asmDst.push_back(colBase + pos);
+        }
+      }
+    }
+    return;
+  }
   S.asmSrc.reserve(ptr[n] / 2 + n);
   S.asmDst.reserve(ptr[n] / 2 + n);
   for (int ro = 0; ro < n; ro++) {
@@ -669,7 +724,6 @@ void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicO
       S.asmDst.push_back(F.lOff + pos + (int64_t)(j - F.col0) * F.ld);
     }
   }
-  lap("asm map");
 }
 
 }  // namespace geneo

@@ -80,6 +80,8 @@ struct SymbolicOptions {
   bool chainInplace = true;  // update matrices of supernode chains stay in place (see Front::inplace)
   bool chainPairs = true;    // rank-256 trailing updates along in-place chains (see Front::pair)
   int subtreeCols = 64; // subtrees of the assembly tree with at most this many columns are merged into one dense front
+  bool skipAsm = false;  // leave asmSrc / asmDst empty: the caller builds the scatter map itself (symbolic_asm_map, or
+                         // fused with its own pass over the matrix as GeneoPC's host preparation does)
   int ndDepth = 0;     // top levels of the nested dissection done here (METIS_ComputeVertexSeparator) with the two halves
                        // ordered by concurrent threads: 2^ndDepth threads per matrix; 0 = plain METIS_NodeND
 };
@@ -93,5 +95,14 @@ void box_reference_ordering(const int dims[3], int nst, const int* stencil, int 
 
 // ptr/idx: CSR pattern of a structurally symmetric n x n matrix (both triangles; column order irrelevant).
 void symbolic_analyze(int n, const int64_t* ptr, const int* idx, const SymbolicOptions& opt, Symbolic& s);
+
+// tT[t] = position of the entry (c, r) for the entry t = (r, c).  Needs sorted rows and a symmetric pattern: returns false
+// (tT unspecified) otherwise.  ndiag (optional) = number of diagonal entries present.
+bool transpose_positions(int n, const int64_t* ptr, const int* idx, std::vector<int64_t>& tT, int64_t* ndiag);
+
+// Scatter map of an analysed matrix (asmSrc = positions in the INPUT value array).  Entry (i, j), i >= j, of P A P^T takes
+// the value stored in row perm[i] of the input.  With tT (transpose_positions) the map is built front by front with one
+// table lookup per entry; without it, row by row with a binary search per entry.
+void symbolic_asm_map(int n, const int64_t* ptr, const int* idx, const std::vector<int64_t>* tT, Symbolic& s);
 
 }  // namespace geneo

@@ -184,6 +184,14 @@ int geneo_symbolic_info(geneo_symbolic_t s, int64_t ints[11], double reals[1]);
 /* fronts: 17 int64 per front = {col0,k,h,parent,level,chain,nchild,rowOff,lOff,uOff,wOff,relOff,ld,uLd,uArena,inplace,pair} */
 int geneo_symbolic_get(geneo_symbolic_t s, int32_t* perm, int64_t* fronts, int32_t* rowIdx, int32_t* rel, int64_t* asmSrc,
                        int64_t* asmDst);
+/* the whole per-subdomain host preparation (analysis, values permuted to the solver order, scatter map, work lists of
+ * every factorization level) of a symmetric CSR matrix taken as A_dir = A_neu; perm may be NULL (METIS).
+ * helper & 1: the ordering-independent part runs on a second thread, as in a cold setup with spare cores;
+ * helper & 2: force the general path (row sorts + binary searches) that unsymmetric patterns take.
+ * scatterOut (optional, scatterLen = factor size of the analysis): the factor array as the assembly kernel fills it.
+ * seconds = {analysis, permuted values, work lists, 0}; digest = hash of everything produced (regression checks) */
+int geneo_host_prepare_probe(int n, const int64_t* ptr, const int32_t* idx, const double* val, const int32_t* perm, int nb, int helper,
+                             double seconds[4], uint64_t* digest, double* scatterOut, int64_t scatterLen);
 int geneo_host_sym_eig(int n, double* a /* row-major in, eigenvectors (columns) out */, double* w);
 /* eigenvalues + selected rows of the eigenvector matrix (the Rayleigh-Ritz shortcut of the block Lanczos solver):
  * yrows[t * n + j] = component rows[t] of the eigenvector of w[j]; a is destroyed */

@@ -349,6 +349,46 @@ def test_box_subdomains_inherit_the_reference_ordering():
         assert np.linalg.norm(a @ _emul.solve(sym, L, b) - b) <= 1e-9 * np.linalg.norm(b)
 
 
+def test_host_preparation_fast_and_general_paths_agree():
+    """The cold setup permutes the values of a subdomain and builds the scatter map of its factor in ONE pass when the rows
+    are sorted and the pattern symmetric (transposed positions, a second thread for the ordering-independent part), and
+    falls back to sorting rows + binary searches otherwise: same permuted matrix, same scattered factor, and the same
+    entries of an UNSYMMETRIC-valued input are read (row perm[i], column perm[j] for i >= j)."""
+    from geneo4petsc_b200.api import host_prepare_probe
+    a = _box_matrix((9, 8, 7)).tocsr()
+    a.sort_indices()
+    rng = np.random.default_rng(5)
+    a.data = a.data * (1.0 + 0.1 * rng.standard_normal(a.nnz))  # symmetric pattern, unsymmetric values
+    perm = g.Symbolic(a, nb=16).perm.copy()
+    sym = g.Symbolic(a, nb=16, perm=perm)
+    lsize = sym.info["lSize"]
+    L0 = np.zeros(lsize)
+    L0[sym.asm_dst] = a.data[sym.asm_src]
+    assert len(np.unique(sym.asm_dst)) == len(sym.asm_dst) == (a.nnz + a.shape[0]) // 2
+    _, d0, s0 = host_prepare_probe(a, perm, nb=16, helper=False, scatter_len=lsize)
+    _, d1, s1 = host_prepare_probe(a, perm, nb=16, helper=True, scatter_len=lsize)
+    _, d2, s2 = host_prepare_probe(a, perm, nb=16, helper=2, scatter_len=lsize)  # general path forced
+    # the same matrix with the columns of every row in random order (analysis entry point only: subdomain matrices are
+    # validated to have sorted rows)
+    b = a.copy()
+    for r in range(b.shape[0]):
+        lo, hi = b.indptr[r], b.indptr[r + 1]
+        o = rng.permutation(hi - lo)
+        b.indices[lo:hi] = b.indices[lo:hi][o]
+        b.data[lo:hi] = b.data[lo:hi][o]
+    b.has_sorted_indices = False
+    assert d0 == d1 == d2
+    assert np.array_equal(s0, L0) and np.array_equal(s1, L0) and np.array_equal(s2, L0)
+    symu = g.Symbolic(b, nb=16, perm=perm)  # analysis entry point on unsorted rows: binary-search scatter map
+    Lu = np.zeros(lsize)
+    Lu[symu.asm_dst] = b.data[symu.asm_src]
+    assert np.array_equal(Lu, L0)
+    # METIS inside the probe (no inherited ordering)
+    _, d3 = host_prepare_probe(a, None, nb=16, helper=True)
+    _, d4 = host_prepare_probe(a, None, nb=16, helper=False)
+    assert d3 == d4
+
+
 def test_geometric_nested_dissection_is_a_valid_ordering():
     """-geneo_ordering 2 (coordinate bisection, separators from the cut): O(n log n), no METIS call; a valid permutation whose
     symbolic structures drive a correct factorization."""
