@@ -457,6 +457,18 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
     std::vector<int64_t> fill(n);
     for (int k = 0; k < n; k++) H.patP.ptr[k + 1] = H.patP.ptr[k] + (S.aDir.ptr[perm[k] + 1] - S.aDir.ptr[perm[k]]);
     for (int k = 0; k < n; k++) fill[k] = H.patP.ptr[k];
+    // with a second thread: the A_neu values take the same walk on their own (the random writes are the cost)
+    std::thread neuThread;
+    auto neuWalk = [&]() {
+      std::vector<int64_t> fill2(H.patP.ptr.begin(), H.patP.ptr.end() - 1);
+      for (int k = 0; k < n; k++) {
+        const int ro = perm[k];
+        for (int64_t t = S.aDir.ptr[ro]; t < S.aDir.ptr[ro + 1]; t++) H.vNeuP[(size_t)fill2[iperm[S.aDir.idx[t]]]++] = neuExp[(size_t)tT[t]];
+      }
+    };
+    if (helper) neuThread = std::thread(neuWalk);
+    struct Join { std::thread& t; ~Join() { if (t.joinable()) t.join(); } } joinNeu{neuThread};
+    const bool neuHere = !helper;
     std::vector<int> where(n, 0);
     double amax = 0.;
     int64_t w = 0;
@@ -477,7 +489,7 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
           const double v = S.aDir.val[src];
           H.patP.idx[q] = k;
           H.patP.val[q] = v;
-          H.vNeuP[q] = neuExp[src];
+          if (neuHere) H.vNeuP[q] = neuExp[src];
           amax = std::max(amax, std::fabs(v));
           if (i >= k) {
             const int pos = where[i];
@@ -489,6 +501,7 @@ void prepare_subdomain(const Subdomain& S, const GeneoOptions& opt, int ndDepth,
         }
       }
     }
+    if (neuThread.joinable()) neuThread.join();
     GENEO_CHECK(kNext == n && w == wMax, "host preparation: scatter map lost entries");
     H.anorm = std::max(H.anorm, amax);
     Y.asmSrc.swap(asmSrc);
