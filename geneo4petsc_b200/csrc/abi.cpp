@@ -342,7 +342,7 @@ int geneo_layout_set_send(geneo_layout_t l, int peer, const int32_t* globalIds, 
   for (int64_t i = 0; i < n; i++) {
     const int g = globalIds[i];
     ABI_REQ(g >= 0 && g < l->L.nbNode, "halo request outside the mesh");
-    const int li = l->L.g2l[g];
+    const int li = l->L.local(g);
     ABI_REQ(li >= 0 && li < l->L.nOwn(), "halo request for a node this rank does not own");
     s[i] = li;
   }

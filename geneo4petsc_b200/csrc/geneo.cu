@@ -745,7 +745,7 @@ void GeneoPC::setup(const Decomposition& dec, const RankLayout* layout, const vo
       if (S.aNeu.n > 0) mine.push_back(&S);
     GENEO_CHECK((int)mine.size() == dec.nbPart, "single-process setup needs every subdomain's matrices");
   }
-  auto localIndex = [&](int g) -> int { return layout ? layout->g2l[g] : g; };
+  auto localIndex = [&](int g) -> int { return layout ? layout->local(g) : g; };
   if (opt.lvl2 == 2 && !opt.lvl1ORAS)
     throw Error("geneo_b200: GenEO-2 needs an optimised level 1 (ORAS/SORAS) -- untested/unsupported in the reference too");
 

@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <set>
 #include <sstream>
@@ -80,14 +82,23 @@ void generate_grid(const GridGenOptions& o, Mesh& m, std::vector<int>* elemPartO
   m.nbNode = (int)npts;
   m.grid[0] = n1; m.grid[1] = n2; m.grid[2] = n3;
   m.elemPtr.clear(); m.elemIdx.clear(); m.matVal.clear();
+  if (elemPartOut) elemPartOut->clear();
   const bool sub = o.keepHi[0] >= 0;
-  if (!sub) {
-    m.elemPtr.reserve(npts * (o.dim + 0) + n1 * n2 + 1);
-    m.elemIdx.reserve(npts * 2 * o.dim);
-    m.matVal.reserve(npts * 4 * o.dim);
+  // sub-mesh: only the coordinates from one below the kept region can emit an element (a neighbour is +1 along one axis)
+  int lo[3] = {0, 0, 0}, hi[3] = {n1, n2, n3};
+  if (sub)
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::max(0, std::min(o.keepLo[a] - 1, hi[a]));
+      hi[a] = std::max(lo[a], std::min(hi[a], o.keepHi[a]));
+    }
+  {
+    const int64_t vol = (int64_t)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    m.elemPtr.reserve(vol * (o.dim + 0) + n1 * n2 + 1);
+    m.elemIdx.reserve(vol * 2 * o.dim);
+    m.matVal.reserve(vol * 4 * o.dim);
+    if (elemPartOut) elemPartOut->reserve(vol * o.dim + n1 * n2);
   }
   m.elemPtr.push_back(0);
-  if (elemPartOut) elemPartOut->clear();
   const int nn[3] = {n1, n2, n3};
   auto inside = [&](int a, int b, int c) {
     return !sub || (a >= o.keepLo[0] && a < o.keepHi[0] && b >= o.keepLo[1] && b < o.keepHi[1] && c >= o.keepLo[2] && c < o.keepHi[2]);
@@ -118,9 +129,9 @@ void generate_grid(const GridGenOptions& o, Mesh& m, std::vector<int>* elemPartO
     }
     m.elemPtr.push_back((int64_t)m.elemIdx.size());
   };
-  for (int d3 = 0; d3 < n3; d3++)
-    for (int d2 = 0; d2 < n2; d2++)
-      for (int d1 = 0; d1 < n1; d1++) {
+  for (int d3 = lo[2]; d3 < hi[2]; d3++)
+    for (int d2 = lo[1]; d2 < hi[1]; d2++)
+      for (int d1 = lo[0]; d1 < hi[0]; d1++) {
         const int c = d1 + n1 * d2 + n1 * n2 * d3;
         const double kappa = k1[d1] * k2[d2] * k3[d3];
         const bool inC = inside(d1, d2, d3);
@@ -348,187 +359,314 @@ void coo_to_csr(int n, std::vector<int>& rows, std::vector<int>& cols, std::vect
   }
 }
 
+// One CSR row at a time: contributions are summed per column in ARRIVAL order (MatSetValues ADD_VALUES semantics, the
+// same sums to the bit as a stable sort of the triplets), the columns of a finished row are sorted and appended.
+struct RowAccumulator {
+  std::vector<int> stamp, slot, cols;
+  std::vector<double> vals;
+  std::vector<std::pair<int, int>> order;
+  int cur = -1;
+  void reset(int ncols) { stamp.assign(ncols, -1); slot.resize(ncols); cur = -1; }
+  void begin(int row) { cur = row; cols.clear(); vals.clear(); }
+  void add(int c, double v) {
+    if (stamp[c] != cur) { stamp[c] = cur; slot[c] = (int)cols.size(); cols.push_back(c); vals.push_back(0. + v); }
+    else vals[slot[c]] += v;
+  }
+  void flush(CsrHost& a) {
+    order.clear();
+    for (size_t q = 0; q < cols.size(); q++) order.emplace_back(cols[q], (int)q);
+    std::sort(order.begin(), order.end());
+    for (auto& o : order) { a.idx.push_back(o.first); a.val.push_back(vals[o.second]); }
+    a.ptr.push_back((int64_t)a.idx.size());
+  }
+};
+
+void run_threads(unsigned nthreads, const std::function<void(unsigned)>& fn) {
+  std::vector<std::thread> pool;
+  std::vector<std::string> errs(nthreads);
+  for (unsigned tid = 0; tid < nthreads; tid++)
+    pool.emplace_back([&, tid]() { try { fn(tid); } catch (std::exception& ex) { errs[tid] = ex.what(); } });
+  for (auto& t : pool) t.join();
+  for (auto& e : errs) GENEO_CHECK(e.empty(), e);
+}
+
 }  // namespace
+
+void NodeIndex::build(int nbNode, const std::vector<int>& elemIdx) {
+  *this = NodeIndex();
+  nn = nbNode;
+  const size_t words = ((size_t)nbNode + 63) / 64;
+  bits.assign(words, 0);
+  for (int g : elemIdx) {
+    GENEO_CHECK(g >= 0 && g < nbNode, "mesh: node id out of range");
+    bits[(size_t)g >> 6] |= 1ull << (g & 63);
+  }
+  pre.resize(words + 1);
+  int c = 0;
+  for (size_t w = 0; w < words; w++) { pre[w] = c; c += __builtin_popcountll(bits[w]); }
+  pre[words] = c;
+  nc = c;
+  if (nc == nn) {  // every node is held: identity
+    std::vector<uint64_t>().swap(bits);
+    std::vector<int>().swap(pre);
+    return;
+  }
+  active = true;
+  present.resize(nc);
+  int q = 0;
+  for (size_t w = 0; w < words; w++)
+    for (uint64_t x = bits[w]; x; x &= x - 1) present[q++] = (int)(w * 64 + (size_t)__builtin_ctzll(x));
+}
 
 void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, const std::vector<int>& nodePart,
                bool dual, int overlap, const std::vector<char>& owner, Decomposition& d) {
   const int ne = m.nbElem(), nn = m.nbNode;
+  const bool tm = getenv("GENEO_DECOMP_TIMING") != nullptr;
+  double tq = now_s();
+  auto lap = [&](const char* what) { if (tm) { const double t = now_s(); fprintf(stderr, "decompose nn=%d ne=%d %s %.3fs\n", nn, ne, what, t - tq); tq = t; } };
   d = Decomposition();
   d.nbPart = nbPart; d.nbNode = nn; d.nbElem = ne;
   for (int a = 0; a < 3; a++) d.grid[a] = m.grid[a];
-  d.nodeMult.assign(nn, 0);
+  // Every per-node array below is indexed by the DENSE id of the node among the nodes this mesh holds (ascending global
+  // id): a rank of an N-GPU run holds a sub-mesh with 1/N of the nodes under global ids.
+  d.index.build(nn, m.elemIdx);
+  const NodeIndex& ix = d.index;
+  const int nc = ix.size();
+  std::vector<int> denseStore;
+  const int* eidx = m.elemIdx.data();
+  if (ix.active) {
+    denseStore.resize(m.elemIdx.size());
+    for (size_t t = 0; t < m.elemIdx.size(); t++) denseStore[t] = ix(m.elemIdx[t]);
+    eidx = denseStore.data();
+  }
+  d.nodeMult.assign(nc, 0);
   d.elemMult.assign(ne, 0);
   d.subs.resize(nbPart);
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
 
-  // inverse topology node -> elements (always needed here: nodal mode, overlap and aDir use it)
-  std::vector<int64_t> n2ePtr(nn + 1, 0);
-  for (size_t t = 0; t < m.elemIdx.size(); t++) n2ePtr[m.elemIdx[t] + 1]++;
-  for (int i = 0; i < nn; i++) n2ePtr[i + 1] += n2ePtr[i];
+  // inverse topology node -> elements, ascending element ids (counting sort; start(c) = n2ePtr[c], end(c) = n2ePtr[c + 1])
+  std::vector<int64_t> n2ePtr((size_t)nc + 2, 0);
+  for (size_t t = 0; t < m.elemIdx.size(); t++) n2ePtr[(size_t)eidx[t] + 2]++;
+  for (int c = 0; c < nc; c++) n2ePtr[(size_t)c + 2] += n2ePtr[(size_t)c + 1];
   std::vector<int> n2e(m.elemIdx.size());
-  {
-    std::vector<int64_t> pos(n2ePtr.begin(), n2ePtr.end() - 1);
-    for (int e = 0; e < ne; e++)
-      for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) n2e[pos[m.elemIdx[t]]++] = e;
-  }
+  for (int e = 0; e < ne; e++)
+    for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) n2e[n2ePtr[(size_t)eidx[t] + 1]++] = e;
+  n2ePtr.pop_back();
+  lap("node -> elements");
 
   // -- element / node sets -----------------------------------------------------------------------------------------
   std::vector<std::vector<int>> partElems(nbPart);
   if (dual) {
+    std::vector<int> cnt(nbPart, 0);
     for (int e = 0; e < ne; e++) {
       GENEO_CHECK(elemPart[e] >= 0 && elemPart[e] < nbPart, "bad element partition");
-      partElems[elemPart[e]].push_back(e);
+      cnt[elemPart[e]]++;
     }
+    for (int p = 0; p < nbPart; p++) partElems[p].reserve(cnt[p]);
+    for (int e = 0; e < ne; e++) partElems[elemPart[e]].push_back(e);
   } else {
     std::vector<std::vector<int>> partNodes(nbPart);
-    for (int i = 0; i < nn; i++) {
-      GENEO_CHECK(nodePart[i] >= 0 && nodePart[i] < nbPart, "bad node partition");
-      partNodes[nodePart[i]].push_back(i);
+    for (int c = 0; c < nc; c++) {
+      const int q = nodePart[ix.global(c)];
+      GENEO_CHECK(q >= 0 && q < nbPart, "bad node partition");
+      partNodes[q].push_back(c);
     }
     std::vector<int> stamp(ne, -1);
     for (int p = 0; p < nbPart; p++)  // an element belongs to p if one of its nodes does
-      for (int g : partNodes[p])
-        for (int64_t t = n2ePtr[g]; t < n2ePtr[g + 1]; t++) {
+      for (int c : partNodes[p])
+        for (int64_t t = n2ePtr[c]; t < n2ePtr[c + 1]; t++) {
           int e = n2e[t];
           if (stamp[e] != p) { stamp[e] = p; partElems[p].push_back(e); }
         }
   }
+  // dense node lists of the subdomains (subs[p].nodes holds the global ids)
+  std::vector<std::vector<int>> denseNodes(ix.active ? nbPart : 0);
+  auto nodesOf = [&](int p) -> const std::vector<int>& { return ix.active ? denseNodes[p] : d.subs[p].nodes; };
   {
-    std::vector<int> estamp(ne, -1), nstamp(nn, -1);
-    for (int p = 0; p < nbPart; p++) {
-      std::vector<int>& el = partElems[p];
-      for (int e : el) estamp[e] = p;
-      size_t layerBegin = 0;
-      for (int l = 0; l < overlap; l++) {  // one layer = every element sharing a node with the current set
-        // (the reference rescans the whole set each time; scanning only the last layer + first pass is equivalent
-        //  because older elements' neighbours were already added)
-        size_t cur = el.size();
-        size_t from = (l == 0) ? 0 : layerBegin;
-        for (size_t q = from; q < cur; q++) {
-          int e = el[q];
-          for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) {
-            int g = m.elemIdx[t];
-            for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
-              int e2 = n2e[u];
-              if (estamp[e2] != p) { estamp[e2] = p; el.push_back(e2); }
+    const unsigned nthreads = std::max(1u, std::min((unsigned)nbPart, hw));
+    std::atomic<int> ticket(0);
+    run_threads(nthreads, [&](unsigned) {
+      std::vector<int> estamp, nstamp(nc, -1);
+      if (overlap > 0) estamp.assign(ne, -1);
+      for (;;) {
+        const int p = ticket.fetch_add(1);
+        if (p >= nbPart) break;
+        std::vector<int>& el = partElems[p];
+        if (overlap > 0) {
+          for (int e : el) estamp[e] = p;
+          size_t layerBegin = 0;
+          for (int l = 0; l < overlap; l++) {  // one layer = every element sharing a node with the current set
+            // (the reference rescans the whole set each time; scanning only the last layer + first pass is equivalent
+            //  because older elements' neighbours were already added)
+            size_t cur = el.size();
+            size_t from = (l == 0) ? 0 : layerBegin;
+            for (size_t q = from; q < cur; q++) {
+              int e = el[q];
+              for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) {
+                int c = eidx[t];
+                for (int64_t u = n2ePtr[c]; u < n2ePtr[c + 1]; u++) {
+                  int e2 = n2e[u];
+                  if (estamp[e2] != p) { estamp[e2] = p; el.push_back(e2); }
+                }
+              }
             }
+            layerBegin = cur;
           }
         }
-        layerBegin = cur;
+        std::sort(el.begin(), el.end());
+        Subdomain& s = d.subs[p];
+        s.id = p;
+        s.elems.swap(el);
+        std::vector<int> dn;
+        for (int e : s.elems)
+          for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) {
+            int c = eidx[t];
+            if (nstamp[c] != p) { nstamp[c] = p; dn.push_back(c); }
+          }
+        std::sort(dn.begin(), dn.end());
+        if (ix.active) {
+          s.nodes.resize(dn.size());
+          for (size_t l = 0; l < dn.size(); l++) s.nodes[l] = ix.present[dn[l]];
+          denseNodes[p].swap(dn);
+        } else s.nodes.swap(dn);
       }
-      std::sort(el.begin(), el.end());
-      Subdomain& s = d.subs[p];
-      s.id = p;
-      s.elems = el;
-      for (int e : el) {
-        d.elemMult[e]++;
-        for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) {
-          int g = m.elemIdx[t];
-          if (nstamp[g] != p) { nstamp[g] = p; s.nodes.push_back(g); }
-        }
-      }
-      std::sort(s.nodes.begin(), s.nodes.end());
-      for (int g : s.nodes) d.nodeMult[g]++;
-      std::vector<int>().swap(partElems[p]);
+    });
+    for (int p = 0; p < nbPart; p++) {
+      for (int e : d.subs[p].elems) d.elemMult[e]++;
+      for (int c : nodesOf(p)) d.nodeMult[c]++;
     }
   }
+  lap("element / node sets");
 
   // -- multiplicities + intersections (local indices, ascending) -----------------------------------------------------
-  std::vector<int64_t> n2dPtr(nn + 1, 0);
-  for (int i = 0; i < nn; i++) n2dPtr[i + 1] = n2dPtr[i] + d.nodeMult[i];
-  std::vector<int> n2d(n2dPtr[nn]);
+  d.nodeSubPtr.assign((size_t)nc + 1, 0);
+  for (int c = 0; c < nc; c++) d.nodeSubPtr[c + 1] = d.nodeSubPtr[c] + d.nodeMult[c];
+  d.nodeSub.resize((size_t)d.nodeSubPtr[nc]);
   {
-    std::vector<int64_t> pos(n2dPtr.begin(), n2dPtr.end() - 1);
+    std::vector<int64_t> pos(d.nodeSubPtr.begin(), d.nodeSubPtr.end() - 1);
     for (int p = 0; p < nbPart; p++)
-      for (int g : d.subs[p].nodes) n2d[pos[g]++] = p;
+      for (int c : nodesOf(p)) d.nodeSub[pos[c]++] = p;
   }
-  d.nodeSubPtr = n2dPtr;
-  d.nodeSub = n2d;
-  for (int p = 0; p < nbPart; p++) {
-    Subdomain& s = d.subs[p];
-    const int nl = (int)s.nodes.size();
-    s.mult.resize(nl);
-    s.intersect.assign(nbPart, std::vector<int>());
-    for (int l = 0; l < nl; l++) {
-      int g = s.nodes[l];
-      s.mult[l] = d.nodeMult[g];
-      if (d.nodeMult[g] > 1)
-        for (int64_t t = n2dPtr[g]; t < n2dPtr[g + 1]; t++)
-          if (n2d[t] != p) s.intersect[n2d[t]].push_back(l);
-    }
+  const std::vector<int64_t>& n2dPtr = d.nodeSubPtr;
+  const std::vector<int>& n2d = d.nodeSub;
+  {
+    std::atomic<int> ticket(0);
+    run_threads(std::max(1u, std::min((unsigned)nbPart, hw)), [&](unsigned) {
+      for (;;) {
+        const int p = ticket.fetch_add(1);
+        if (p >= nbPart) break;
+        Subdomain& s = d.subs[p];
+        const std::vector<int>& dn = nodesOf(p);
+        const int nl = (int)dn.size();
+        s.mult.resize(nl);
+        s.intersect.assign(nbPart, std::vector<int>());
+        for (int l = 0; l < nl; l++) {
+          const int c = dn[l];
+          s.mult[l] = d.nodeMult[c];
+          if (d.nodeMult[c] > 1)
+            for (int64_t t = n2dPtr[c]; t < n2dPtr[c + 1]; t++)
+              if (n2d[t] != p) s.intersect[n2d[t]].push_back(l);
+        }
+      }
+    });
   }
+  lap("multiplicities + intersections");
 
-  // -- local matrices for owned subdomains ---------------------------------------------------------------------------
+  // -- local matrices for owned subdomains: assembled row by row (no triplet lists) ------------------------------------
   std::vector<int> mine;
   for (int p = 0; p < nbPart; p++)
     if (owner.empty() || owner[p]) mine.push_back(p);
-  unsigned nthreads = std::max(1u, std::min((unsigned)mine.size(), std::thread::hardware_concurrency()));
-  std::vector<std::thread> pool;
-  std::vector<std::string> errs(nthreads);
-  for (unsigned tid = 0; tid < nthreads; tid++) {
-    pool.emplace_back([&, tid]() {
-      try {
-        std::vector<int> g2l(nn, -1), estamp(ne, -1);
-        for (size_t w = tid; w < mine.size(); w += nthreads) {
-          const int p = mine[w];
-          Subdomain& s = d.subs[p];
-          const int nl = (int)s.nodes.size();
-          for (int l = 0; l < nl; l++) g2l[s.nodes[l]] = l;
-          std::vector<int> rows, cols;
-          std::vector<double> vals;
-          // Neumann: own elements weighted by 1/elemMult (buildDomain :473-476, fillALoc :688-708)
-          size_t cap = 0;
-          for (int e : s.elems) { int64_t k = m.elemPtr[e + 1] - m.elemPtr[e]; cap += (size_t)(k * k); }
-          rows.reserve(cap); cols.reserve(cap); vals.reserve(cap);
-          for (int e : s.elems) {
+  {
+    const unsigned nthreads = std::max(1u, std::min((unsigned)mine.size(), hw));
+    std::atomic<int> ticket(0);
+    run_threads(nthreads, [&](unsigned) {
+      std::vector<int> g2l(nc, -1), emark(ne, -1);
+      RowAccumulator acc;
+      std::vector<std::pair<int, int>> touching;  // (first local node of the element, element)
+      for (;;) {
+        const int w = ticket.fetch_add(1);
+        if (w >= (int)mine.size()) break;
+        const int p = mine[w];
+        Subdomain& s = d.subs[p];
+        const std::vector<int>& dn = nodesOf(p);
+        const int nl = (int)dn.size();
+        for (int l = 0; l < nl; l++) g2l[dn[l]] = l;
+        for (int e : s.elems) emark[e] = p;
+        acc.reset(nl);
+        // Neumann: own elements weighted by 1/elemMult (buildDomain :473-476, fillALoc :688-708); the contributions of a
+        // row arrive in ascending element order
+        s.aNeu = CsrHost();
+        s.aNeu.n = s.aNeu.ncols = nl;
+        s.aNeu.ptr.reserve((size_t)nl + 1);
+        s.aNeu.ptr.push_back(0);
+        for (int l = 0; l < nl; l++) {
+          const int c = dn[l];
+          acc.begin(l);
+          for (int64_t u = n2ePtr[c]; u < n2ePtr[c + 1]; u++) {
+            const int e = n2e[u];
+            if (emark[e] != p) continue;
             const int64_t b = m.elemPtr[e];
             const int k = (int)(m.elemPtr[e + 1] - b);
             const double w8 = 1. / ((double)d.elemMult[e]);
             const double* K = &m.matVal[m.matPtr[e]];
-            for (int i = 0; i < k; i++)
-              for (int j = 0; j < k; j++) {
-                rows.push_back(g2l[m.elemIdx[b + i]]);
-                cols.push_back(g2l[m.elemIdx[b + j]]);
-                vals.push_back(K[i * k + j] * w8);
-              }
+            for (int i = 0; i < k; i++) {
+              if (eidx[b + i] != c) continue;
+              for (int j = 0; j < k; j++) acc.add(g2l[eidx[b + j]], K[i * k + j] * w8);
+            }
           }
-          coo_to_csr(nl, rows, cols, vals, s.aNeu);
-          // Dirichlet R A R^T: every element touching the subdomain, restricted to its nodes, full weight
-          rows.clear(); cols.clear(); vals.clear();
-          for (int l = 0; l < nl; l++) {
-            const int g = s.nodes[l];
-            for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
-              const int e = n2e[u];
-              if (estamp[e] == p) continue;
-              estamp[e] = p;
-              const int64_t b = m.elemPtr[e];
-              const int k = (int)(m.elemPtr[e + 1] - b);
-              const double* K = &m.matVal[m.matPtr[e]];
-              for (int i = 0; i < k; i++) {
-                const int li = g2l[m.elemIdx[b + i]];
-                if (li < 0) continue;
-                for (int j = 0; j < k; j++) {
-                  const int lj = g2l[m.elemIdx[b + j]];
-                  if (lj < 0) continue;
-                  rows.push_back(li); cols.push_back(lj); vals.push_back(K[i * k + j]);
-                }
+          acc.flush(s.aNeu);
+        }
+        // Dirichlet R A R^T: every element touching the subdomain, restricted to its nodes, full weight.  Elements
+        // contribute in the order of their first local node, then of their id (the order a sweep over the nodes meets them)
+        s.aDir = CsrHost();
+        s.aDir.n = s.aDir.ncols = nl;
+        s.aDir.ptr.reserve((size_t)nl + 1);
+        s.aDir.ptr.push_back(0);
+        s.aDir.idx.reserve(s.aNeu.idx.size());
+        s.aDir.val.reserve(s.aNeu.idx.size());
+        for (int l = 0; l < nl; l++) {
+          const int c = dn[l];
+          touching.clear();
+          for (int64_t u = n2ePtr[c]; u < n2ePtr[c + 1]; u++) {
+            const int e = n2e[u];
+            int first = l;
+            for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++) {
+              const int lj = g2l[eidx[t]];
+              if (lj >= 0 && lj < first) first = lj;
+            }
+            touching.emplace_back(first, e);
+          }
+          std::sort(touching.begin(), touching.end());
+          acc.begin(l);
+          for (auto& fe : touching) {
+            const int e = fe.second;
+            const int64_t b = m.elemPtr[e];
+            const int k = (int)(m.elemPtr[e + 1] - b);
+            const double* K = &m.matVal[m.matPtr[e]];
+            for (int i = 0; i < k; i++) {
+              if (eidx[b + i] != c) continue;
+              for (int j = 0; j < k; j++) {
+                const int lj = g2l[eidx[b + j]];
+                if (lj >= 0) acc.add(lj, K[i * k + j]);
               }
             }
           }
-          coo_to_csr(nl, rows, cols, vals, s.aDir);
-          for (int l = 0; l < nl; l++) g2l[s.nodes[l]] = -1;
+          acc.flush(s.aDir);
         }
-      } catch (std::exception& ex) { errs[tid] = ex.what(); }
+        for (int l = 0; l < nl; l++) g2l[dn[l]] = -1;
+      }
     });
   }
-  for (auto& t : pool) t.join();
-  for (auto& e : errs) GENEO_CHECK(e.empty(), e);
   d.nnzNeuTotal = 0;
   for (int p : mine) d.nnzNeuTotal += d.subs[p].aNeu.nnz();
+  lap("local matrices");
 }
 
 void finish_predecomposed(Decomposition& d) {
   const int nn = d.nbNode, P = d.nbPart;
   GENEO_CHECK((int)d.subs.size() == P && P >= 1 && nn >= 1, "pre-decomposed problem: bad sizes");
+  d.index = NodeIndex();
+  d.index.nn = nn;  // every DOF belongs to a subdomain (checked below): identity
   d.nodeMult.assign(nn, 0);
   for (int p = 0; p < P; p++) {
     Subdomain& s = d.subs[p];
@@ -605,75 +743,121 @@ void build_rank_layout(const Mesh& m, const Decomposition& d, const std::vector<
   const int nn = m.nbNode, ne = m.nbElem();
   GENEO_CHECK((int)subRank.size() == d.nbPart, "layout: one rank per subdomain expected");
   GENEO_CHECK(rank >= 0 && rank < world, "layout: bad rank");
+  const bool tm = getenv("GENEO_DECOMP_TIMING") != nullptr;
+  double tq = now_s();
+  auto lap = [&](const char* what) { if (tm) { const double t = now_s(); fprintf(stderr, "layout nn=%d ne=%d %s %.3fs\n", nn, ne, what, t - tq); tq = t; } };
   L = RankLayout();
   L.rank = rank; L.world = world; L.nbNode = nn; L.subRank = subRank;
-  auto ownerRank = [&](int g) -> int {  // rank of the lowest-numbered subdomain containing g (-1: in no subdomain)
-    return d.nodeSubPtr[g] < d.nodeSubPtr[g + 1] ? subRank[d.nodeSub[d.nodeSubPtr[g]]] : -1;
+  // dense node ids of the (sub-)mesh, as in decompose (d.nodeSubPtr is indexed by them)
+  L.index = d.index;
+  const NodeIndex& ix = L.index;
+  const int nc = ix.size();
+  GENEO_CHECK((int)d.nodeSubPtr.size() == nc + 1, "layout: the decomposition was built on another mesh");
+  std::vector<int> denseStore;
+  const int* eidx = m.elemIdx.data();
+  if (ix.active) {
+    denseStore.resize(m.elemIdx.size());
+    for (size_t t = 0; t < m.elemIdx.size(); t++) {
+      denseStore[t] = ix(m.elemIdx[t]);
+      GENEO_CHECK(denseStore[t] >= 0, "layout: the decomposition was built on another mesh");
+    }
+    eidx = denseStore.data();
+  }
+  auto ownerRank = [&](int c) -> int {  // rank of the lowest-numbered subdomain containing the node (-1: in no subdomain)
+    return d.nodeSubPtr[c] < d.nodeSubPtr[c + 1] ? subRank[d.nodeSub[d.nodeSubPtr[c]]] : -1;
   };
   // 1 = owned, 2 = ghost
-  std::vector<char> flag(nn, 0);
+  std::vector<char> flag(nc, 0);
   for (int p = 0; p < d.nbPart; p++) {
     if (subRank[p] != rank) continue;
-    for (int g : d.subs[p].nodes) flag[g] = (ownerRank(g) == rank) ? 1 : 2;
+    for (int g : d.subs[p].nodes) { const int c = ix(g); flag[c] = (ownerRank(c) == rank) ? 1 : 2; }
   }
-  // node -> elements, for the owned rows only
-  std::vector<int64_t> n2ePtr(nn + 1, 0);
+  // node -> elements, for the owned rows only (ascending element ids)
+  std::vector<int64_t> n2ePtr((size_t)nc + 2, 0);
+  for (size_t t = 0; t < m.elemIdx.size(); t++)
+    if (flag[eidx[t]] == 1) n2ePtr[(size_t)eidx[t] + 2]++;
+  for (int c = 0; c < nc; c++) n2ePtr[(size_t)c + 2] += n2ePtr[(size_t)c + 1];
+  std::vector<int> n2e((size_t)n2ePtr[(size_t)nc + 1]);
   for (int e = 0; e < ne; e++)
     for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++)
-      if (flag[m.elemIdx[t]] == 1) n2ePtr[m.elemIdx[t] + 1]++;
-  for (int i = 0; i < nn; i++) n2ePtr[i + 1] += n2ePtr[i];
-  std::vector<int> n2e(n2ePtr[nn]);
-  {
-    std::vector<int64_t> pos(n2ePtr.begin(), n2ePtr.end() - 1);
-    for (int e = 0; e < ne; e++)
-      for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++)
-        if (flag[m.elemIdx[t]] == 1) n2e[pos[m.elemIdx[t]]++] = e;
-  }
+      if (flag[eidx[t]] == 1) n2e[n2ePtr[(size_t)eidx[t] + 1]++] = e;
+  n2ePtr.pop_back();
   // columns of owned rows that are in none of the rank's subdomains become ghosts too
-  for (int g = 0; g < nn; g++) {
-    if (flag[g] != 1) continue;
-    for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
+  for (int c = 0; c < nc; c++) {
+    if (flag[c] != 1) continue;
+    for (int64_t u = n2ePtr[c]; u < n2ePtr[c + 1]; u++) {
       const int e = n2e[u];
       for (int64_t t = m.elemPtr[e]; t < m.elemPtr[e + 1]; t++)
-        if (flag[m.elemIdx[t]] == 0) flag[m.elemIdx[t]] = 2;
+        if (flag[eidx[t]] == 0) flag[eidx[t]] = 2;
     }
   }
   std::vector<std::vector<int>> byOwner(world);
-  for (int g = 0; g < nn; g++) {
-    if (flag[g] == 1) L.owned.push_back(g);
-    else if (flag[g] == 2) {
-      const int q = ownerRank(g);
+  std::vector<int> ownedDense;
+  for (int c = 0; c < nc; c++) {
+    if (flag[c] == 1) { L.owned.push_back(ix.global(c)); ownedDense.push_back(c); }
+    else if (flag[c] == 2) {
+      const int q = ownerRank(c);
       GENEO_CHECK(q >= 0 && q < world && q != rank, "layout: ghost node without a remote owner");
-      byOwner[q].push_back(g);
+      byOwner[q].push_back(c);
     }
   }
+  L.c2l.assign(nc, -1);
+  for (int i = 0; i < L.nOwn(); i++) L.c2l[ownedDense[i]] = i;
   L.ghostPtr.assign(world + 1, 0);
   for (int q = 0; q < world; q++) {
-    L.ghost.insert(L.ghost.end(), byOwner[q].begin(), byOwner[q].end());
+    for (int c : byOwner[q]) { L.c2l[c] = L.nOwn() + (int)L.ghost.size(); L.ghost.push_back(ix.global(c)); }
     L.ghostPtr[q + 1] = (int64_t)L.ghost.size();
   }
-  L.g2l.assign(nn, -1);
-  for (int i = 0; i < L.nOwn(); i++) L.g2l[L.owned[i]] = i;
-  for (int i = 0; i < L.nGhost(); i++) L.g2l[L.ghost[i]] = L.nOwn() + i;
   L.sendIdx.assign(world, std::vector<int>());
-  // owned rows of A = sum over ALL elements touching the node, full weight (== sum_i R_i^T A_neu,i R_i, SURVEY.md 8a note 1)
-  std::vector<int> rows, cols;
-  std::vector<double> vals;
-  for (int i = 0; i < L.nOwn(); i++) {
-    const int g = L.owned[i];
-    for (int64_t u = n2ePtr[g]; u < n2ePtr[g + 1]; u++) {
-      const int e = n2e[u];
-      const int64_t b = m.elemPtr[e];
-      const int k = (int)(m.elemPtr[e + 1] - b);
-      const double* K = &m.matVal[m.matPtr[e]];
-      for (int a = 0; a < k; a++) {
-        if (m.elemIdx[b + a] != g) continue;
-        for (int j = 0; j < k; j++) { rows.push_back(i); cols.push_back(L.g2l[m.elemIdx[b + j]]); vals.push_back(K[a * k + j]); }
+  lap("owned / ghost sets");
+  // owned rows of A = sum over ALL elements touching the node, full weight (== sum_i R_i^T A_neu,i R_i, SURVEY.md 8a note 1),
+  // assembled row by row in ascending element order; row blocks in parallel, concatenated afterwards
+  const int nOwn = L.nOwn(), ncols = nOwn + L.nGhost();
+  const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, nOwn / 4096)));
+  std::vector<CsrHost> piece(nthreads);
+  run_threads(nthreads, [&](unsigned tid) {
+    const int i0 = (int)((int64_t)nOwn * tid / nthreads), i1 = (int)((int64_t)nOwn * (tid + 1) / nthreads);
+    RowAccumulator acc;
+    acc.reset(ncols);
+    CsrHost& a = piece[tid];
+    a.ptr.reserve((size_t)(i1 - i0) + 1);
+    a.ptr.push_back(0);
+    for (int i = i0; i < i1; i++) {
+      const int c = ownedDense[i];
+      acc.begin(i);
+      for (int64_t u = n2ePtr[c]; u < n2ePtr[c + 1]; u++) {
+        const int e = n2e[u];
+        const int64_t b = m.elemPtr[e];
+        const int k = (int)(m.elemPtr[e + 1] - b);
+        const double* K = &m.matVal[m.matPtr[e]];
+        for (int a2 = 0; a2 < k; a2++) {
+          if (eidx[b + a2] != c) continue;
+          for (int j = 0; j < k; j++) acc.add(L.c2l[eidx[b + j]], K[a2 * k + j]);
+        }
       }
+      acc.flush(a);
     }
+  });
+  L.A = CsrHost();
+  L.A.n = nOwn;
+  L.A.ncols = ncols;
+  L.A.ptr.assign((size_t)nOwn + 1, 0);
+  int64_t total = 0;
+  for (auto& a : piece) total += a.nnz();
+  L.A.idx.reserve((size_t)total);
+  L.A.val.reserve((size_t)total);
+  {
+    int row = 0;
+    for (auto& a : piece) {
+      const int64_t base = (int64_t)L.A.idx.size();
+      for (size_t r = 1; r < a.ptr.size(); r++) L.A.ptr[++row] = base + a.ptr[r];
+      L.A.idx.insert(L.A.idx.end(), a.idx.begin(), a.idx.end());
+      L.A.val.insert(L.A.val.end(), a.val.begin(), a.val.end());
+      a = CsrHost();
+    }
+    GENEO_CHECK(row == nOwn, "layout: operator rows lost");
   }
-  coo_to_csr(L.nOwn(), rows, cols, vals, L.A);
-  L.A.ncols = L.nOwn() + L.nGhost();
+  lap("owned rows of A");
 }
 
 }  // namespace geneo

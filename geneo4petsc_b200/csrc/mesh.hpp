@@ -59,6 +59,26 @@ int read_rhs_file(const std::string& path, int n, std::vector<double>& b);      
 // METIS_PartMeshDual / METIS_PartMeshNodal with the reference's options (MINCONN=1, KWAY, CUT, ncommon=1).
 int metis_partition(const Mesh& m, int nbPart, bool dual, std::vector<int>& elemPart, std::vector<int>& nodePart);
 
+// Global node id -> dense index over the nodes a (sub-)mesh actually holds, ascending (identity when it holds them all).
+// A rank of a multi-GPU run holds 1/world of the nodes under GLOBAL ids: per-node work arrays are sized by size(), not by
+// the global node count (one bit per global node + one counter per 64 is all that scales with the whole problem).
+struct NodeIndex {
+  bool active = false;
+  int nn = 0, nc = 0;
+  std::vector<uint64_t> bits;  // presence bitmap
+  std::vector<int> pre;        // present nodes before each 64-bit word
+  std::vector<int> present;    // dense -> global
+  void build(int nbNode, const std::vector<int>& elemIdx);
+  int size() const { return active ? nc : nn; }
+  int operator()(int g) const {  // -1: not held
+    if (!active) return g;
+    const uint64_t w = bits[(size_t)g >> 6], b = 1ull << (g & 63);
+    if (!(w & b)) return -1;
+    return pre[(size_t)g >> 6] + __builtin_popcountll(w & (b - 1));
+  }
+  int global(int c) const { return active ? present[c] : c; }
+};
+
 struct Subdomain {
   int id = 0;
   std::vector<int> nodes;  // sorted global node ids == local numbering (rank in the sorted set)
@@ -72,6 +92,7 @@ struct Subdomain {
 struct Decomposition {
   int nbPart = 0, nbNode = 0, nbElem = 0;
   int grid[3] = {0, 0, 0};      // copy of Mesh::grid (0: unstructured) -- lets congruent box subdomains share one nested dissection
+  NodeIndex index;              // nodeMult / nodeSubPtr below are indexed by index(global id)
   std::vector<int> nodeMult, elemMult;
   std::vector<Subdomain> subs;  // ALL subdomains' index sets; matrices only for the ones in `mine`
   int64_t nnzNeuTotal = 0;      // "nnz coefs" of the INFO line (sum over all local matrices)
@@ -99,7 +120,9 @@ struct RankLayout {
   std::vector<int64_t> ghostPtr;            // [world+1] into ghost, by owner rank
   std::vector<std::vector<int>> sendIdx;    // per peer: local OWNED indices it needs (set after the request exchange)
   CsrHost A;                                // owned rows of A = sum_e K_e, local column numbering
-  std::vector<int> g2l;                     // global -> local (-1 when absent); size nbNode
+  NodeIndex index;                          // global -> local (-1 when absent) through the dense index of the sub-mesh
+  std::vector<int> c2l;
+  int local(int g) const { const int c = index(g); return c < 0 ? -1 : c2l[c]; }
   int nOwn() const { return (int)owned.size(); }
   int nGhost() const { return (int)ghost.size(); }
 };

@@ -440,3 +440,21 @@ def test_reference_plot_script_parses_the_cli_log():
     assert (j.estimDimE, j.estimDimEMin, j.estimDimEMax, j.realDimE, j.realDimEMin, j.realDimEMax, j.nicolaides) == (0, 0, 0, 2, 1, 1, 2)
     assert j.nbIt == 6 and j.setUpSolve > 0 and j.itSolve > 0 and abs(j.solve - (j.setUpSolve + j.itSolve)) < 1e-4
     assert j.getSurfName() == "metis=dual-overlap=0-ksp=gmres-pc=geneo1ASM-L1=ldlt-tau=0.10-L2=blocklanczos+ldlt-distribE"
+
+
+def test_decomposition_and_layout_digests_are_pinned():
+    """SHA-256 of everything the decomposition and the rank layouts produce (index sets, multiplicities, intersections,
+    weighted Neumann / Dirichlet matrices, owned rows of A, ghosts) over 22 small configurations -- box partitions seen by
+    single ranks of 1/2/4/8-GPU runs, METIS dual / nodal parts with overlap 0..2, parts grouped onto 2 and 3 ranks, the
+    graph generator.  The digests were written by the triplet-list implementation the oracle comparisons pinned
+    (tools/host_decomp_digest.py); the row-wise assembly on dense node ids has to reproduce them to the bit."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("host_decomp_digest", os.path.join(root, "tools", "host_decomp_digest.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(root, "tests", "golden", "decomposition_digests.json")))
+    got = mod.run()
+    assert set(got) == set(want)
+    assert [k for k in got if got[k] != want[k]] == []
