@@ -1,6 +1,6 @@
 """CPU: stage stopwatches + digest of the per-subdomain host preparation (geneo_host_prepare_probe) on an n^3 Q1 box.
 
-python tools/host_prepare_probe.py [edge] [--metis]   (inherited reference-box ordering by default)
+python tools/host_prepare_probe.py [edge] [--metis] [--seven]   (inherited reference-box ordering, 27-point pattern by default)
 """
 import os
 import sys
@@ -13,9 +13,13 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from geneo4petsc_b200 import api  # noqa: E402
 
 
-def q1_box(n, seed=0):
+def q1_box(n, seed=0, seven=False):
     b = sp.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1], format="csr")
-    pat = sp.kron(sp.kron(b, b), b).tocsr()
+    i = sp.identity(n, format="csr")
+    if seven:  # 7-point pattern (the bench's laplacian / heat generators: 2-node elements along the axes)
+        pat = (sp.kron(sp.kron(b, i), i) + sp.kron(sp.kron(i, b), i) + sp.kron(sp.kron(i, i), b)).tocsr()
+    else:      # 27-point pattern (Q1 hexahedra)
+        pat = sp.kron(sp.kron(b, b), b).tocsr()
     rng = np.random.default_rng(seed)
     w = sp.triu(pat, 1).tocoo()
     v = -rng.uniform(0.5, 1.5, w.nnz)
@@ -29,10 +33,13 @@ def q1_box(n, seed=0):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 64
-    a = q1_box(n)
+    seven = "--seven" in sys.argv
+    a = q1_box(n, seven=seven)
     perm = None
     if "--metis" not in sys.argv:
         st = [(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) if (i, j, k) > (0, 0, 0)]
+        if seven:
+            st = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
         t = time.time()
         rank = api.box_ordering((n, n, n), stencil=st, threads=os.cpu_count())
         print("reference ordering %.2f s" % (time.time() - t))
