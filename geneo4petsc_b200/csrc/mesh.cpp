@@ -373,13 +373,35 @@ struct RowAccumulator {
     else vals[slot[c]] += v;
   }
   void flush(CsrHost& a) {
-    order.clear();
-    for (size_t q = 0; q < cols.size(); q++) order.emplace_back(cols[q], (int)q);
-    std::sort(order.begin(), order.end());
-    for (auto& o : order) { a.idx.push_back(o.first); a.val.push_back(vals[o.second]); }
+    const int m = (int)cols.size();
+    if (m <= 48) {  // the usual case (stencil rows): insertion sort of the column / value pairs in place
+      for (int q = 1; q < m; q++) {
+        const int c = cols[q];
+        const double v = vals[q];
+        int r = q - 1;
+        for (; r >= 0 && cols[r] > c; r--) { cols[r + 1] = cols[r]; vals[r + 1] = vals[r]; }
+        cols[r + 1] = c; vals[r + 1] = v;
+      }
+      a.idx.insert(a.idx.end(), cols.begin(), cols.end());
+      a.val.insert(a.val.end(), vals.begin(), vals.end());
+    } else {
+      order.clear();
+      for (int q = 0; q < m; q++) order.emplace_back(cols[q], q);
+      std::sort(order.begin(), order.end());
+      for (auto& o : order) { a.idx.push_back(o.first); a.val.push_back(vals[o.second]); }
+    }
     a.ptr.push_back((int64_t)a.idx.size());
   }
 };
+
+// host threads of THIS process: the cores divided by the ranks sharing the node (torchrun exports LOCAL_WORLD_SIZE), at most
+// 16 -- every thread of the passes below owns per-node work arrays
+unsigned host_threads() {
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  if (const char* e = getenv("GENEO_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  else if (const char* e2 = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1u, hw / (unsigned)std::max(1, atoi(e2)));
+  return std::min(hw, 16u);
+}
 
 void run_threads(unsigned nthreads, const std::function<void(unsigned)>& fn) {
   std::vector<std::thread> pool;
@@ -442,7 +464,7 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
   d.nodeMult.assign(nc, 0);
   d.elemMult.assign(ne, 0);
   d.subs.resize(nbPart);
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const unsigned hw = host_threads();
 
   // inverse topology node -> elements, ascending element ids (counting sort; start(c) = n2ePtr[c], end(c) = n2ePtr[c + 1])
   std::vector<int64_t> n2ePtr((size_t)nc + 2, 0);
@@ -599,6 +621,13 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
         s.aNeu.n = s.aNeu.ncols = nl;
         s.aNeu.ptr.reserve((size_t)nl + 1);
         s.aNeu.ptr.push_back(0);
+        {
+          size_t cap = 0;  // upper bound: every (row, column) pair of every element once
+          for (int e : s.elems) { const size_t k = (size_t)(m.elemPtr[e + 1] - m.elemPtr[e]); cap += k * k; }
+          cap = std::min(cap, (size_t)nl * 32);
+          s.aNeu.idx.reserve(cap);
+          s.aNeu.val.reserve(cap);
+        }
         for (int l = 0; l < nl; l++) {
           const int c = dn[l];
           acc.begin(l);
@@ -627,6 +656,7 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
         for (int l = 0; l < nl; l++) {
           const int c = dn[l];
           touching.clear();
+          bool sorted = true;
           for (int64_t u = n2ePtr[c]; u < n2ePtr[c + 1]; u++) {
             const int e = n2e[u];
             int first = l;
@@ -634,9 +664,10 @@ void decompose(const Mesh& m, int nbPart, const std::vector<int>& elemPart, cons
               const int lj = g2l[eidx[t]];
               if (lj >= 0 && lj < first) first = lj;
             }
+            sorted = sorted && (touching.empty() || touching.back() < std::make_pair(first, e));
             touching.emplace_back(first, e);
           }
-          std::sort(touching.begin(), touching.end());
+          if (!sorted) std::sort(touching.begin(), touching.end());
           acc.begin(l);
           for (auto& fe : touching) {
             const int e = fe.second;
@@ -813,7 +844,7 @@ void build_rank_layout(const Mesh& m, const Decomposition& d, const std::vector<
   // owned rows of A = sum over ALL elements touching the node, full weight (== sum_i R_i^T A_neu,i R_i, SURVEY.md 8a note 1),
   // assembled row by row in ascending element order; row blocks in parallel, concatenated afterwards
   const int nOwn = L.nOwn(), ncols = nOwn + L.nGhost();
-  const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, nOwn / 4096)));
+  const unsigned nthreads = std::max(1u, std::min(host_threads(), (unsigned)std::max(1, nOwn / 4096)));
   std::vector<CsrHost> piece(nthreads);
   run_threads(nthreads, [&](unsigned tid) {
     const int i0 = (int)((int64_t)nOwn * tid / nthreads), i1 = (int)((int64_t)nOwn * (tid + 1) / nthreads);
