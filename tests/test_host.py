@@ -458,3 +458,24 @@ def test_decomposition_and_layout_digests_are_pinned():
     got = mod.run()
     assert set(got) == set(want)
     assert [k for k in got if got[k] != want[k]] == []
+
+
+def test_decomposition_of_a_mesh_that_does_not_hold_every_node_id():
+    """A (sub-)mesh whose elements use only part of the global node ids -- what every rank of a multi-GPU run holds -- goes
+    through the dense node index: the same subdomains, multiplicities, intersections and matrices as the mesh renumbered
+    from zero, with the global ids shifted."""
+    mesh = go.gen_grid(2, 6, 1e-2)
+    ep, ei, em = np.asarray(mesh.elem_ptr), np.asarray(mesh.elem_idx), np.asarray(mesh.mat_val)
+    p = g.Problem().set_mesh(mesh.nb_node + 8, ep, ei + 3, em)  # 3 unused ids in front, 5 behind
+    q = g.Problem().set_mesh(mesh.nb_node, ep, ei, em)
+    for prob in (p, q):
+        prob.decompose(3, True, 1)
+    for s in range(3):
+        a, ma = p.sub_nodes(s)
+        b, mb = q.sub_nodes(s)
+        assert np.array_equal(a, b + 3) and np.array_equal(ma, mb)
+        for which in (0, 1):
+            A, B = p.sub_matrix(s, which), q.sub_matrix(s, which)
+            assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+        for t in range(3):
+            assert np.array_equal(p.sub_intersect(s, t), q.sub_intersect(s, t))
